@@ -1,0 +1,143 @@
+/* kb2e_b200 -- C ABI of the B200-native KB2E hot path (TransE / TransH / TransR margin-ranking SGD
+ * epochs and filtered link-prediction ranking).  Plain pointers and sizes only; every function
+ * returns 0 on success or a KB2E_ERR_* code and never exits the process -- the host mains turn
+ * errors into the reference's messages / exit codes.
+ *
+ * Each entry point names the reference interface it replaces (citations into eriq-augustine/KB2E):
+ *   kb2e_create / kb2e_destroy      common::Trainer::Trainer (common/trainer.cpp:15-24) and
+ *                                   common::EmbeddingEvaluation ctor (common/evaluation.cpp:23-33)
+ *   kb2e_set_train_triples          Trainer::add / heads_,tails_,relations_,triples_ (common/trainer.cpp:26-32)
+ *   kb2e_set_bern                   relation{Head,Tail}MeanCooccurrence_ (common/trainer.cpp:171-194)
+ *   kb2e_init_embeddings            Trainer::prepTrain + initialEmbeddingValue (common/trainer.cpp:34-58,
+ *                                   transe/trainer.cpp:21, transh/trainer.cpp:61,77-88, transr/trainer.cpp:66-86)
+ *   kb2e_upload / kb2e_download     the nested-vector tables entityVec_/relationVec_/weights_
+ *                                   (common/trainer.h:36-37, transh/trainer.h:17, transr/trainer.h:31),
+ *                                   TransR seeding (transr/trainer.cpp:88-113), loadEmbeddings
+ *                                   (common/evaluation.cpp:74-105), write (common/trainer.cpp:109-127)
+ *   kb2e_train_epochs               Trainer::bfgs (common/trainer.cpp:69-107) incl. the sampler (:78-98),
+ *                                   train_kb (:130-149), <model>::gradientUpdate / prebatch / postbatch
+ *   kb2e_score                      <model>::tripleEnergy (transe/transe.cpp:10, transh/transh.cpp:10, transr/transr.cpp:13)
+ *   kb2e_set_test_triples /
+ *   kb2e_add_filter_triples         EmbeddingEvaluation::loadTriples / add (common/evaluation.cpp:41-72)
+ *   kb2e_rank                       EmbeddingEvaluation::run + evalCorruption (common/evaluation.cpp:124-251)
+ *   kb2e_sample_batch,
+ *   kb2e_train_batch_pairs          test hooks onto the sampler and onto one batch of train_kb calls
+ *
+ * Threading: one context per host thread; a context owns one CUDA device, its own stream and all
+ * device memory.  Multi-GPU = one process (context) per GPU; ranks shard queries through
+ * kb2e_rank's [first, first+count) window and add the four int64 sums with their own collective.
+ */
+#ifndef KB2E_B200_H_
+#define KB2E_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB2E_MODEL_TRANSE 0
+#define KB2E_MODEL_TRANSH 1
+#define KB2E_MODEL_TRANSR 2
+
+#define KB2E_METHOD_UNIF 0 /* common/constants.h:8-9 */
+#define KB2E_METHOD_BERN 1
+#define KB2E_DISTANCE_L1 0 /* common/constants.h:16-17; "L2" is the SQUARED L2 distance */
+#define KB2E_DISTANCE_L2 1
+
+#define KB2E_TABLE_ENTITY 0   /* [num_entities][dim] */
+#define KB2E_TABLE_RELATION 1 /* [num_relations][dim] */
+#define KB2E_TABLE_WEIGHTS 2  /* TransH: [num_relations][dim]; TransR: [num_relations*dim][dim] = M[r][j=in][i=out] */
+
+#define KB2E_OK 0
+#define KB2E_ERR_ARG 1    /* bad argument / wrong call order */
+#define KB2E_ERR_CUDA 2   /* CUDA runtime failure (message in kb2e_last_error) */
+#define KB2E_ERR_NO_GPU 3 /* no usable CUDA device: there is NO CPU fallback */
+#define KB2E_ERR_LIMIT 4  /* size outside what the kernels support */
+
+/* flags */
+#define KB2E_FLAG_RANK_EXACT_ONLY 1u /* rank with the exact fp64 kernel only (no fp32 / tensor-core pre-filter) */
+#define KB2E_FLAG_TRANSR_NO_QUIRK 2u /* do not replicate transr/trainer.cpp:187 (constraint on entity[relation]) */
+
+typedef struct kb2e_ctx kb2e_ctx;
+
+typedef struct kb2e_config {
+   int32_t model;    /* KB2E_MODEL_* */
+   int32_t dim;      /* -size     (common/constants.h:45) */
+   int32_t method;   /* -method   0 unif, 1 bern */
+   int32_t distance; /* -distance 0 L1, 1 squared L2 (ignored by TransH, transh/transh.cpp:24-26) */
+   int32_t batches;  /* -batches  */
+   int32_t device;   /* CUDA device ordinal */
+   int64_t num_entities;
+   int64_t num_relations;
+   double rate;   /* -rate   */
+   double margin; /* -margin */
+   uint64_t seed; /* -seed: keys the counter-based RNG (sampler and initialisation) */
+   uint32_t flags;
+   uint32_t reserved;
+} kb2e_config;
+
+typedef struct kb2e_train_stats {
+   uint64_t samples;      /* (pos, neg) pairs processed since the context was created */
+   uint64_t active;       /* pairs whose hinge was active (normal + margin > corrupted) */
+   uint64_t touched_ent;  /* entity rows renormalised + published, summed over batches */
+   uint64_t touched_rel;  /* relation-side rows renormalised + published, summed over batches */
+   uint64_t launches;     /* kernels launched by kb2e_train_epochs / kb2e_train_batch_pairs */
+   double kernel_ms;      /* CUDA-event time of those launches */
+} kb2e_train_stats;
+
+typedef struct kb2e_rank_stats {
+   uint64_t queries;      /* queries ranked since the context was created */
+   uint64_t rechecked;    /* (query, candidate) pairs re-scored in exact fp64 after a pre-filter */
+   uint64_t launches;
+   double kernel_ms;      /* CUDA-event time of all ranking kernels */
+   double main_kernel_ms; /* of which: the all-candidates scoring kernel(s) */
+} kb2e_rank_stats;
+
+int kb2e_create(const kb2e_config* cfg, kb2e_ctx** out);
+void kb2e_destroy(kb2e_ctx* ctx);
+/* Message of the last failure on ctx (or of the last failed kb2e_create when ctx is NULL). */
+const char* kb2e_last_error(const kb2e_ctx* ctx);
+/* The context's CUDA stream (a cudaStream_t), so callers can time with events on the launching stream. */
+void* kb2e_stream(kb2e_ctx* ctx);
+
+/* ---- training ------------------------------------------------------------------------------- */
+int kb2e_set_train_triples(kb2e_ctx* ctx, const int32_t* heads, const int32_t* tails, const int32_t* relations, int64_t n);
+/* Per relation: mean #triples per distinct head / per distinct tail (0 for unused relations). */
+int kb2e_set_bern(kb2e_ctx* ctx, const double* head_mean, const double* tail_mean);
+int kb2e_init_embeddings(kb2e_ctx* ctx);
+int kb2e_upload(kb2e_ctx* ctx, int table, const double* host, int64_t rows, int64_t cols);
+int kb2e_download(kb2e_ctx* ctx, int table, double* host, int64_t rows, int64_t cols);
+/* Epochs [first_epoch, first_epoch + n_epochs): every batch of every epoch runs on the device in
+ * one persistent launch.  loss_per_epoch[n_epochs] = the value the reference prints per epoch. */
+int kb2e_train_epochs(kb2e_ctx* ctx, int32_t first_epoch, int32_t n_epochs, double* loss_per_epoch);
+int kb2e_get_train_stats(kb2e_ctx* ctx, kb2e_train_stats* out);
+
+/* ---- scoring / ranking ---------------------------------------------------------------------- */
+/* Energies of n triples from the CURRENT tables: precision 0 = the fp32 scoring code the training
+ * kernels use, 1 = the exact fp64 code the ranking uses (reference operation order). */
+int kb2e_score(kb2e_ctx* ctx, const int32_t* heads, const int32_t* tails, const int32_t* relations, int64_t n,
+               int32_t precision, double* out);
+int kb2e_set_test_triples(kb2e_ctx* ctx, const int32_t* heads, const int32_t* tails, const int32_t* relations, int64_t n);
+/* Known-true triples besides the test set (train, valid); may be called repeatedly.  n = 0 with
+ * NULL pointers clears the set. */
+int kb2e_add_filter_triples(kb2e_ctx* ctx, const int32_t* heads, const int32_t* tails, const int32_t* relations, int64_t n);
+/* Rank test triples [first, first+count): entry 2*i is the head corruption of triple first+i,
+ * 2*i+1 its tail corruption.  rank = 1 + #{candidates with strictly lower energy}; *_ties = number
+ * of OTHER candidates with exactly equal energy (the reference's std::sort places the truth
+ * anywhere inside [rank, rank+ties]).  sums = {raw rank sum, filtered rank sum, raw hits@10,
+ * filtered hits@10}.  Any output pointer may be NULL. */
+int kb2e_rank(kb2e_ctx* ctx, int64_t first, int64_t count,
+              int32_t* raw_rank, int32_t* filt_rank, int32_t* raw_ties, int32_t* filt_ties, int64_t sums[4]);
+int kb2e_get_rank_stats(kb2e_ctx* ctx, kb2e_rank_stats* out);
+
+/* ---- test hooks ----------------------------------------------------------------------------- */
+/* The device sampler's output for samples [0, count) of (epoch, batch): count x {h,t,r,h',t',r'}. */
+int kb2e_sample_batch(kb2e_ctx* ctx, int32_t epoch, int32_t batch, int64_t count, int32_t* pairs_out);
+/* One batch made of the given (pos, neg) pairs instead of sampled ones, through the same kernel. */
+int kb2e_train_batch_pairs(kb2e_ctx* ctx, const int32_t* pairs, int64_t n, double* loss, int64_t* n_active);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KB2E_B200_H_ */

@@ -1,0 +1,97 @@
+// Internal context shared by the translation units of libkb2e_b200.so (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/kb2e_b200.h"
+
+struct kb2e_ctx {
+   kb2e_config cfg;
+   int D = 0;       // -size
+   int P = 0;       // row pitch in elements: D rounded up to a multiple of 4 (16-byte vector access)
+   int nE = 0, nR = 0;
+   int device = 0;
+   int num_sms = 0;
+   cudaStream_t stream = nullptr;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   std::string err;
+
+   // ---- fp32 training tables -------------------------------------------------------------------
+   // tab  : [nE + nR][P]  entity rows, then relation rows (one row-index space for the touched lists)
+   // dtab : same shape, the batch's accumulated update ("next - cur" of the reference's *_next_ copies)
+   // w    : TransH [nR][P] hyperplane normals; TransR [nR][D][P] = M[r][j=in][i=out]; dw same shape
+   float* tab = nullptr;
+   float* dtab = nullptr;
+   float* w = nullptr;
+   float* dw = nullptr;
+   size_t w_row = 0;           // elements per relation in w
+   uint8_t* flag = nullptr;    // [nE + nR] row touched in the current batch
+   int* rmin = nullptr;        // [nE] lowest / highest relation id that touched the entity row (TransH/R)
+   int* rmax = nullptr;
+   bool have32 = false;        // fp32 tables hold the current parameters
+
+   // ---- training set ---------------------------------------------------------------------------
+   int4* triples = nullptr;    // (h, t, r, 0)
+   int64_t n_train = 0;
+   uint64_t* hash = nullptr;   // open-addressing set of packed (h, r, t)
+   uint64_t hash_mask = 0;
+   double* pr = nullptr;       // [nR] the reference's `pr` in thousandths (common/trainer.cpp:82-86)
+   bool have_pr = false;
+
+   // persistent-launch scratch
+   uint32_t* barrier = nullptr;
+   double* loss_dev = nullptr;
+   int loss_cap = 0;
+   unsigned long long* counters = nullptr;  // [0] active [1] touched_ent [2] touched_rel
+   int32_t* pairs_dev = nullptr;
+   int64_t pairs_cap = 0;
+   int hook_batches = 0;      // batches run through kb2e_train_batch_pairs (keeps flag parity alternating)
+   kb2e_train_stats tstats{};
+
+   // ---- fp64 tables for ranking (exact copies of what was uploaded, or widened fp32 state) -----
+   double* ent64 = nullptr;  // [nE][D]
+   double* rel64 = nullptr;  // [nR][D]
+   double* w64 = nullptr;    // TransH [nR][D]; TransR [nR][D][D]
+   bool have64 = false;
+
+   // ---- evaluation set -------------------------------------------------------------------------
+   std::vector<int32_t> test_h, test_t, test_r;
+   std::vector<int32_t> filt_h, filt_t, filt_r;
+   bool filter_dirty = true;
+   struct RankState* rank = nullptr;
+   kb2e_rank_stats rstats{};
+};
+
+namespace kb2e {
+
+int fail(kb2e_ctx* ctx, int code, const std::string& msg);
+int cuda_fail(kb2e_ctx* ctx, cudaError_t e, const char* what);
+
+#define KB2E_CUDA(ctx, call)                                         \
+   do {                                                              \
+      cudaError_t e__ = (call);                                      \
+      if (e__ != cudaSuccess) return kb2e::cuda_fail(ctx, e__, #call); \
+   } while (0)
+
+// train.cu
+int train_alloc(kb2e_ctx* ctx);
+void train_free(kb2e_ctx* ctx);
+int train_set_triples(kb2e_ctx* ctx, const int32_t* h, const int32_t* t, const int32_t* r, int64_t n);
+int train_init_embeddings(kb2e_ctx* ctx);
+int train_run(kb2e_ctx* ctx, int first_epoch, int n_epochs, const int32_t* pairs_dev, int64_t n_pairs, double* loss_out);
+int train_sample(kb2e_ctx* ctx, int epoch, int batch, int64_t count, int32_t* pairs_dev);
+int train_score32(kb2e_ctx* ctx, const int32_t* h_dev, const int32_t* t_dev, const int32_t* r_dev, int64_t n, double* out_dev);
+int tables_32_to_64(kb2e_ctx* ctx);
+int tables_64_to_32(kb2e_ctx* ctx);
+
+// rank.cu
+int rank_run(kb2e_ctx* ctx, int64_t first, int64_t count, int32_t* raw_rank, int32_t* filt_rank,
+             int32_t* raw_ties, int32_t* filt_ties, int64_t sums[4]);
+int rank_score64(kb2e_ctx* ctx, const int32_t* h_dev, const int32_t* t_dev, const int32_t* r_dev, int64_t n, double* out_dev);
+void rank_free(kb2e_ctx* ctx);
+
+}  // namespace kb2e

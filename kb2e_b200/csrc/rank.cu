@@ -1,0 +1,659 @@
+// Filtered link-prediction ranking against all entities (exact fp64 path).
+//
+// Replaces (citations into eriq-augustine/KB2E):
+//   EmbeddingEvaluation::run            common/evaluation.cpp:181-251  relation-major loop, sums, hits@10
+//   EmbeddingEvaluation::evalCorruption common/evaluation.cpp:124-179  score all entities, sort, scan
+//   cachedTripleEnergy + the N_E^2 cache common/evaluation.cpp:107-120,194-218 (unnecessary here)
+//   transe/transh/transr::tripleEnergy   transe/transe.cpp:10-28, transh/transh.cpp:10-29, transr/transr.cpp:13-37
+//
+// No sort: rank = 1 + #{candidates with strictly smaller energy}; exact ties are counted separately
+// (the reference's std::sort places the truth anywhere among its equals).  Energies are computed
+// in fp64 with the reference's exact operation order -- per candidate a left-to-right sum over the
+// dimensions of |(t - h) - r| (or its square), no FMA contraction (explicit __dadd_rn/__dmul_rn and
+// -fmad=false) -- so `<` and `==` decide exactly as the reference's doubles do.
+//
+// All three models reduce to one kernel over a per-relation candidate matrix C (transposed,
+// C^T[i][c], so that consecutive threads = consecutive candidates read consecutive addresses):
+//   TransE  C = entity table                       (one slot for every relation)
+//   TransH  C_r[c] = e_c - (w_r . e_c) w_r         (transh/transh.cpp:18-25)
+//   TransR  C_r[c] = M_r^T e_c                     (transr/transr.cpp:20-25, work vectors zeroed)
+// and energy(head-corruption by c) = sum_i f((C[t]_i - C[c]_i) - d_i), energy(tail-corruption by c)
+// = sum_i f((C[c]_i - C[h]_i) - d_i) = sum_i f((V_i - C[c]_i) - d'_i) with V = C[fixed], d' = -d
+// (negation is exact), f = |.| or (.)^2.
+//
+// Filtered rank (common/evaluation.cpp:161-163): the known-true neighbours of each query live in a
+// device hash table keyed by (side, relation, fixed entity) -> CSR segment; their energies are
+// re-scored and those ranked before the truth are subtracted from the raw rank.
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+
+struct RankState {
+   // filter CSR + hash
+   uint64_t* seg_key = nullptr;   // hash slots: key or kEmptyKey
+   uint2* seg_val = nullptr;      // (offset, count) per slot
+   int32_t* nbr = nullptr;        // neighbour entity ids
+   uint64_t seg_mask = 0;
+   // candidate matrices
+   double* ct0 = nullptr;         // entity table transposed [D][ld]
+   double* pt = nullptr;          // projected slots [slots][D][ld]
+   size_t pt_slots = 0;
+   int ld = 0;
+   // per-call query arrays
+   int32_t* q_int = nullptr;      // fixed, truth, rel, side, slot, orig  (6 x cap)
+   double* q_etrue = nullptr;
+   int32_t* q_cnt = nullptr;      // less, eq, known_less, known_eq (4 x cap)
+   int4* tiles = nullptr;         // (first query, nq, slot, unused)
+   int64_t q_cap = 0, tile_cap = 0;
+   int32_t* slot_rel = nullptr;
+   int64_t slot_cap = 0;
+   unsigned long long* sums = nullptr;
+   int32_t* out = nullptr;        // 4 x cap results in original order
+   cudaEvent_t m0 = nullptr, m1 = nullptr;
+};
+
+namespace kb2e {
+
+constexpr int kQT = 16;          // queries per tile
+constexpr int kRankThreads = 256;
+
+__host__ __device__ __forceinline__ uint64_t seg_key_of(int side, int rel, int fixed) {
+   return ((uint64_t)side << 40) | ((uint64_t)(uint32_t)rel << 24) | (uint64_t)(uint32_t)fixed;
+}
+
+// ---- candidate matrices ----------------------------------------------------------------------------
+__global__ void transpose_kernel(const double* __restrict__ src, double* __restrict__ dst, int rows, int D, int ld) {
+   __shared__ double tile[32][33];
+   int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      int r = r0 + j, c = c0 + threadIdx.x;
+      tile[j][threadIdx.x] = (r < rows && c < D) ? src[(size_t)r * D + c] : 0.0;
+   }
+   __syncthreads();
+   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      int c = c0 + j, r = r0 + threadIdx.x;
+      if (c < D && r < ld) dst[(size_t)c * ld + r] = (r < rows) ? tile[threadIdx.x][j] : 0.0;
+   }
+}
+
+// TransH: p_i = e_i - (sum_k w_k e_k) * w_i, the sum taken left to right (transh/transh.cpp:18-25).
+__global__ void project_transh_kernel(const double* __restrict__ ct0, const double* __restrict__ w64,
+                                      const int32_t* __restrict__ slot_rel, double* __restrict__ pt, int nE, int D, int ld) {
+   int c = blockIdx.x * blockDim.x + threadIdx.x;
+   int slot = blockIdx.y;
+   if (c >= nE) return;
+   const double* w = w64 + (size_t)slot_rel[slot] * D;
+   double s = 0.0;
+   for (int i = 0; i < D; i++) s = __dadd_rn(s, __dmul_rn(__ldg(w + i), ct0[(size_t)i * ld + c]));
+   double* out = pt + (size_t)slot * D * ld;
+   for (int i = 0; i < D; i++) out[(size_t)i * ld + c] = __dsub_rn(ct0[(size_t)i * ld + c], __dmul_rn(s, __ldg(w + i)));
+}
+
+// TransR: p_i = sum_j M[j][i] * e_j, j ascending from a zero accumulator (transr/transr.cpp:20-25).
+__global__ void project_transr_kernel(const double* __restrict__ ct0, const double* __restrict__ w64,
+                                      const int32_t* __restrict__ slot_rel, double* __restrict__ pt, int nE, int D, int ld) {
+   extern __shared__ double sM[];  // [D][D]
+   int slot = blockIdx.y;
+   const double* M = w64 + (size_t)slot_rel[slot] * D * D;
+   for (int k = threadIdx.x; k < D * D; k += blockDim.x) sM[k] = M[k];
+   __syncthreads();
+   int c = blockIdx.x * blockDim.x + threadIdx.x;
+   if (c >= nE) return;
+   double* out = pt + (size_t)slot * D * ld;
+   for (int i0 = 0; i0 < D; i0 += 4) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      for (int j = 0; j < D; j++) {
+         double e = ct0[(size_t)j * ld + c];
+         const double* m = sM + j * D + i0;
+         a0 = __dadd_rn(a0, __dmul_rn(m[0], e));
+         if (i0 + 1 < D) a1 = __dadd_rn(a1, __dmul_rn(m[1], e));
+         if (i0 + 2 < D) a2 = __dadd_rn(a2, __dmul_rn(m[2], e));
+         if (i0 + 3 < D) a3 = __dadd_rn(a3, __dmul_rn(m[3], e));
+      }
+      out[(size_t)i0 * ld + c] = a0;
+      if (i0 + 1 < D) out[(size_t)(i0 + 1) * ld + c] = a1;
+      if (i0 + 2 < D) out[(size_t)(i0 + 2) * ld + c] = a2;
+      if (i0 + 3 < D) out[(size_t)(i0 + 3) * ld + c] = a3;
+   }
+}
+
+// ---- exact energy of one candidate (any thread; strided reads) -------------------------------------
+template <int L2>
+__device__ __forceinline__ double exact_energy(const double* __restrict__ ct, int ld, int D, int fixed, int cand,
+                                               const double* __restrict__ d, double dsign) {
+   double acc = 0.0;
+   for (int i = 0; i < D; i++) {
+      double u = __dsub_rn(ct[(size_t)i * ld + fixed], ct[(size_t)i * ld + cand]);
+      double v = __dsub_rn(u, dsign * d[i]);
+      acc = L2 ? __dadd_rn(acc, __dmul_rn(v, v)) : __dadd_rn(acc, fabs(v));
+   }
+   return acc;
+}
+
+struct RankArgs {
+   const double* ct;      // slot 0 base
+   const double* rel64;
+   const int32_t* q_fixed;
+   const int32_t* q_truth;
+   const int32_t* q_rel;
+   const int32_t* q_side;
+   const int32_t* q_slot;
+   double* q_etrue;
+   int32_t* q_cnt;        // [4][nq]: less, eq, known_less, known_eq
+   const int4* tiles;
+   const uint64_t* seg_key;
+   const uint2* seg_val;
+   const int32_t* nbr;
+   uint64_t seg_mask;
+   long long nq;        // total queries of this call (row stride of q_cnt)
+   long long q_begin;   // window of queries handled by etrue_kernel / filter_kernel
+   long long q_end;
+   int nE, D, ld, splits;
+};
+
+template <int L2>
+__global__ void etrue_kernel(const RankArgs a) {
+   long long q = a.q_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (q >= a.q_end) return;
+   const double* ct = a.ct + (size_t)a.q_slot[q] * a.D * a.ld;
+   const double* d = a.rel64 + (size_t)a.q_rel[q] * a.D;
+   a.q_etrue[q] = exact_energy<L2>(ct, a.ld, a.D, a.q_fixed[q], a.q_truth[q], d, a.q_side[q] ? -1.0 : 1.0);
+}
+
+// ---- the all-candidates kernel ---------------------------------------------------------------------
+// grid.x = query tiles, grid.y = candidate splits; each thread owns one candidate per 256-wide step
+// and keeps kQT running energies, reading the tile's (V_i, d'_i) pairs from shared memory.
+template <int L2>
+__global__ void __launch_bounds__(kRankThreads) rank_exact_kernel(const RankArgs a) {
+   extern __shared__ double2 s_vd[];  // [D][kQT]
+   __shared__ double s_et[kQT];
+   __shared__ int s_truth[kQT];
+   __shared__ int s_cnt[kQT][2];
+   const int4 tile = a.tiles[blockIdx.x];
+   const int q0 = tile.x, nq = tile.y;
+   const double* ct = a.ct + (size_t)tile.z * a.D * a.ld;
+   const int D = a.D, ld = a.ld;
+   for (int k = threadIdx.x; k < D * kQT; k += blockDim.x) {
+      int i = k / kQT, q = k % kQT;
+      double2 vd = make_double2(0.0, 0.0);
+      if (q < nq) {
+         int gq = q0 + q;
+         vd.x = ct[(size_t)i * ld + a.q_fixed[gq]];
+         double dv = a.rel64[(size_t)a.q_rel[gq] * D + i];
+         vd.y = a.q_side[gq] ? -dv : dv;
+      }
+      s_vd[k] = vd;
+   }
+   if (threadIdx.x < kQT) {
+      int q = threadIdx.x;
+      s_et[q] = q < nq ? a.q_etrue[q0 + q] : 0.0;
+      s_truth[q] = q < nq ? a.q_truth[q0 + q] : -1;
+      s_cnt[q][0] = 0;
+      s_cnt[q][1] = 0;
+   }
+   __syncthreads();
+   // candidate range of this split, in steps of blockDim.x
+   const int steps = (a.nE + kRankThreads - 1) / kRankThreads;
+   const int s_begin = (int)((long long)steps * blockIdx.y / a.splits);
+   const int s_end = (int)((long long)steps * (blockIdx.y + 1) / a.splits);
+   uint32_t cnt[kQT];
+#pragma unroll
+   for (int q = 0; q < kQT; q++) cnt[q] = 0;
+   for (int step = s_begin; step < s_end; step++) {
+      const int c = step * kRankThreads + threadIdx.x;
+      const bool valid = c < a.nE;
+      const int cc = valid ? c : 0;
+      double acc[kQT];
+#pragma unroll
+      for (int q = 0; q < kQT; q++) acc[q] = 0.0;
+#pragma unroll 2
+      for (int i = 0; i < D; i++) {
+         const double ci = ct[(size_t)i * ld + cc];
+         const double2* vd = s_vd + i * kQT;
+#pragma unroll
+         for (int q = 0; q < kQT; q++) {
+            double2 p = vd[q];
+            double v = __dsub_rn(__dsub_rn(p.x, ci), p.y);
+            acc[q] = L2 ? __dadd_rn(acc[q], __dmul_rn(v, v)) : __dadd_rn(acc[q], fabs(v));
+         }
+      }
+      if (valid) {
+#pragma unroll
+         for (int q = 0; q < kQT; q++) {
+            double et = s_et[q];
+            cnt[q] += (acc[q] < et ? 1u : 0u) + ((acc[q] == et && c != s_truth[q]) ? 0x10000u : 0u);
+         }
+      }
+   }
+   // block reduction of the packed (less | eq << 16) counters; per-thread counts are < 2^16
+#pragma unroll
+   for (int q = 0; q < kQT; q++) {
+      uint32_t lo = cnt[q] & 0xffffu, hi = cnt[q] >> 16;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+         lo += __shfl_xor_sync(0xffffffffu, lo, o);
+         hi += __shfl_xor_sync(0xffffffffu, hi, o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+         if (lo) atomicAdd(&s_cnt[q][0], (int)lo);
+         if (hi) atomicAdd(&s_cnt[q][1], (int)hi);
+      }
+   }
+   __syncthreads();
+   if (threadIdx.x < nq) {
+      int q = threadIdx.x;
+      if (a.splits == 1) {
+         a.q_cnt[0 * a.nq + q0 + q] = s_cnt[q][0];
+         a.q_cnt[1 * a.nq + q0 + q] = s_cnt[q][1];
+      } else {
+         if (s_cnt[q][0]) atomicAdd(a.q_cnt + 0 * a.nq + q0 + q, s_cnt[q][0]);
+         if (s_cnt[q][1]) atomicAdd(a.q_cnt + 1 * a.nq + q0 + q, s_cnt[q][1]);
+      }
+   }
+}
+
+// ---- filter adjustment: one warp per query walks the known-true neighbours -------------------------
+template <int L2>
+__global__ void filter_kernel(const RankArgs a) {
+   long long q = a.q_begin + (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+   int lane = threadIdx.x & 31;
+   if (q >= a.q_end) return;
+   int side = a.q_side[q], rel = a.q_rel[q], fixed = a.q_fixed[q], truth = a.q_truth[q];
+   uint64_t key = seg_key_of(side, rel, fixed);
+   uint64_t slot = mix64(key) & a.seg_mask;
+   uint2 seg = make_uint2(0, 0);
+   while (true) {
+      uint64_t k = __ldg(a.seg_key + slot);
+      if (k == key) { seg = __ldg(a.seg_val + slot); break; }
+      if (k == kEmptyKey) break;
+      slot = (slot + 1) & a.seg_mask;
+   }
+   const double* ct = a.ct + (size_t)a.q_slot[q] * a.D * a.ld;
+   const double* d = a.rel64 + (size_t)rel * a.D;
+   const double et = a.q_etrue[q];
+   int less = 0, eq = 0;
+   for (uint32_t k = lane; k < seg.y; k += 32) {
+      int c = __ldg(a.nbr + seg.x + k);
+      if (c == truth) continue;
+      double e = exact_energy<L2>(ct, a.ld, a.D, fixed, c, d, side ? -1.0 : 1.0);
+      less += e < et;
+      eq += e == et;
+   }
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      less += __shfl_xor_sync(0xffffffffu, less, o);
+      eq += __shfl_xor_sync(0xffffffffu, eq, o);
+   }
+   if (lane == 0) {
+      a.q_cnt[2 * a.nq + q] = less;
+      a.q_cnt[3 * a.nq + q] = eq;
+   }
+}
+
+// ranks in original order + the four sums (common/evaluation.cpp:169-178)
+__global__ void finalize_kernel(const int32_t* q_cnt, const int32_t* q_orig, long long nq, int32_t* out, unsigned long long* sums) {
+   long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   unsigned long long v[4] = {0, 0, 0, 0};
+   if (q < nq) {
+      int raw = 1 + q_cnt[q], ties = q_cnt[nq + q];
+      int filt = raw - q_cnt[2 * nq + q], fties = ties - q_cnt[3 * nq + q];
+      int o = q_orig[q];
+      out[0 * nq + o] = raw;
+      out[1 * nq + o] = filt;
+      out[2 * nq + o] = ties;
+      out[3 * nq + o] = fties;
+      v[0] = raw; v[1] = filt; v[2] = raw <= 10; v[3] = filt <= 10;
+   }
+#pragma unroll
+   for (int k = 0; k < 4; k++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(sums + k, v[k]);
+   }
+}
+
+// one thread per triple, exact energies (precision = 1 of kb2e_score)
+template <int L2>
+__global__ void score64_kernel(const double* ct, const double* rel64, const int32_t* slot_of_rel, int D, int ld,
+                               const int32_t* h, const int32_t* t, const int32_t* r, long long n, double* out) {
+   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (k >= n) return;
+   const double* c = ct + (size_t)(slot_of_rel ? slot_of_rel[r[k]] : 0) * D * ld;
+   // head-corruption form with the true head as candidate: (C[t] - C[h]) - d
+   out[k] = exact_energy<L2>(c, ld, D, t[k], h[k], rel64 + (size_t)r[k] * D, 1.0);
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+static int ensure_state(kb2e_ctx* c) {
+   if (!c->rank) c->rank = new RankState();
+   RankState* s = c->rank;
+   s->ld = ((c->nE + 31) / 32) * 32;
+   if (!s->ct0) KB2E_CUDA(c, cudaMalloc(&s->ct0, (size_t)c->D * s->ld * sizeof(double)));
+   if (!s->sums) KB2E_CUDA(c, cudaMalloc(&s->sums, 4 * sizeof(unsigned long long)));
+   if (!s->m0) {
+      KB2E_CUDA(c, cudaEventCreate(&s->m0));
+      KB2E_CUDA(c, cudaEventCreate(&s->m1));
+   }
+   return KB2E_OK;
+}
+
+static int build_filter(kb2e_ctx* c) {
+   RankState* s = c->rank;
+   if (!c->filter_dirty && s->seg_key) return KB2E_OK;
+   cudaFree(s->seg_key); cudaFree(s->seg_val); cudaFree(s->nbr);
+   s->seg_key = nullptr; s->seg_val = nullptr; s->nbr = nullptr;
+   // known triples = test + filter (common/evaluation.cpp:59-61); two CSRs in one key space
+   size_t n = c->test_h.size() + c->filt_h.size();
+   std::vector<std::pair<uint64_t, int32_t>> ent;
+   ent.reserve(2 * n);
+   auto add = [&](int32_t h, int32_t t, int32_t r) {
+      ent.emplace_back(seg_key_of(0, r, t), h);  // head corruption: fixed tail -> known heads
+      ent.emplace_back(seg_key_of(1, r, h), t);  // tail corruption: fixed head -> known tails
+   };
+   for (size_t i = 0; i < c->test_h.size(); i++) add(c->test_h[i], c->test_t[i], c->test_r[i]);
+   for (size_t i = 0; i < c->filt_h.size(); i++) add(c->filt_h[i], c->filt_t[i], c->filt_r[i]);
+   std::sort(ent.begin(), ent.end());
+   ent.erase(std::unique(ent.begin(), ent.end()), ent.end());
+   std::vector<int32_t> nbr(ent.size());
+   std::vector<uint64_t> keys;
+   std::vector<uint2> vals;
+   for (size_t i = 0; i < ent.size();) {
+      size_t j = i;
+      while (j < ent.size() && ent[j].first == ent[i].first) { nbr[j] = ent[j].second; j++; }
+      keys.push_back(ent[i].first);
+      vals.push_back(make_uint2((unsigned)i, (unsigned)(j - i)));
+      i = j;
+   }
+   uint64_t slots = 1024;
+   while (slots < 2 * keys.size()) slots <<= 1;
+   std::vector<uint64_t> hk(slots, kEmptyKey);
+   std::vector<uint2> hv(slots, make_uint2(0, 0));
+   for (size_t i = 0; i < keys.size(); i++) {
+      uint64_t p = mix64(keys[i]) & (slots - 1);
+      while (hk[p] != kEmptyKey) p = (p + 1) & (slots - 1);
+      hk[p] = keys[i];
+      hv[p] = vals[i];
+   }
+   s->seg_mask = slots - 1;
+   KB2E_CUDA(c, cudaMalloc(&s->seg_key, slots * sizeof(uint64_t)));
+   KB2E_CUDA(c, cudaMalloc(&s->seg_val, slots * sizeof(uint2)));
+   KB2E_CUDA(c, cudaMalloc(&s->nbr, std::max<size_t>(1, nbr.size()) * sizeof(int32_t)));
+   KB2E_CUDA(c, cudaMemcpyAsync(s->seg_key, hk.data(), slots * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+   KB2E_CUDA(c, cudaMemcpyAsync(s->seg_val, hv.data(), slots * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+   if (!nbr.empty())
+      KB2E_CUDA(c, cudaMemcpyAsync(s->nbr, nbr.data(), nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+   KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   c->filter_dirty = false;
+   return KB2E_OK;
+}
+
+static int ensure_query_buffers(kb2e_ctx* c, int64_t nq) {
+   RankState* s = c->rank;
+   if (nq <= s->q_cap) return KB2E_OK;
+   cudaFree(s->q_int); cudaFree(s->q_etrue); cudaFree(s->q_cnt); cudaFree(s->out);
+   s->q_int = nullptr; s->q_etrue = nullptr; s->q_cnt = nullptr; s->out = nullptr;
+   s->q_cap = 0;
+   KB2E_CUDA(c, cudaMalloc(&s->q_int, (size_t)nq * 6 * sizeof(int32_t)));
+   KB2E_CUDA(c, cudaMalloc(&s->q_etrue, (size_t)nq * sizeof(double)));
+   KB2E_CUDA(c, cudaMalloc(&s->q_cnt, (size_t)nq * 4 * sizeof(int32_t)));
+   KB2E_CUDA(c, cudaMalloc(&s->out, (size_t)nq * 4 * sizeof(int32_t)));
+   s->q_cap = nq;
+   return KB2E_OK;
+}
+
+// Project the relations in `rels` into slots (TransH / TransR); TransE uses ct0 directly.
+static int project(kb2e_ctx* c, const std::vector<int32_t>& rels) {
+   RankState* s = c->rank;
+   size_t slots = rels.size();
+   if (slots > s->pt_slots) {
+      cudaFree(s->pt);
+      s->pt = nullptr;
+      KB2E_CUDA(c, cudaMalloc(&s->pt, slots * (size_t)c->D * s->ld * sizeof(double)));
+      s->pt_slots = slots;
+   }
+   if ((int64_t)slots > s->slot_cap) {
+      cudaFree(s->slot_rel);
+      s->slot_rel = nullptr;
+      KB2E_CUDA(c, cudaMalloc(&s->slot_rel, slots * sizeof(int32_t)));
+      s->slot_cap = (int64_t)slots;
+   }
+   KB2E_CUDA(c, cudaMemcpyAsync(s->slot_rel, rels.data(), slots * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+   dim3 grid(nblk(c->nE, 128), (unsigned)slots);
+   if (c->cfg.model == KB2E_MODEL_TRANSH) {
+      project_transh_kernel<<<grid, 128, 0, c->stream>>>(s->ct0, c->w64, s->slot_rel, s->pt, c->nE, c->D, s->ld);
+   } else {
+      size_t smem = (size_t)c->D * c->D * sizeof(double);
+      if (smem > 200 * 1024) return fail(c, KB2E_ERR_LIMIT, "TransR ranking supports embedding sizes up to 160");
+      KB2E_CUDA(c, cudaFuncSetAttribute(project_transr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      project_transr_kernel<<<grid, 128, smem, c->stream>>>(s->ct0, c->w64, s->slot_rel, s->pt, c->nE, c->D, s->ld);
+   }
+   KB2E_CUDA(c, cudaGetLastError());
+   return KB2E_OK;
+}
+
+static int prepare_tables(kb2e_ctx* c) {
+   int rc = ensure_state(c);
+   if (rc) return rc;
+   rc = tables_32_to_64(c);
+   if (rc) return rc;
+   RankState* s = c->rank;
+   dim3 grid(nblk(s->ld, 32), nblk(c->D, 32));
+   transpose_kernel<<<grid, dim3(32, 8), 0, c->stream>>>(c->ent64, s->ct0, c->nE, c->D, s->ld);
+   KB2E_CUDA(c, cudaGetLastError());
+   return KB2E_OK;
+}
+
+int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32_t* filt_rank,
+             int32_t* raw_ties, int32_t* filt_ties, int64_t sums[4]) {
+   if (first < 0 || count < 0 || first + count > (int64_t)c->test_h.size())
+      return fail(c, KB2E_ERR_ARG, "rank window outside the test triples");
+   if (sums) sums[0] = sums[1] = sums[2] = sums[3] = 0;
+   if (count == 0) return KB2E_OK;
+   int rc = prepare_tables(c);
+   if (rc) return rc;
+   rc = build_filter(c);
+   if (rc) return rc;
+   RankState* s = c->rank;
+   const bool per_rel = c->cfg.model != KB2E_MODEL_TRANSE;
+   const bool l2 = c->cfg.model != KB2E_MODEL_TRANSH && c->cfg.distance == KB2E_DISTANCE_L2;
+   const int64_t nq = 2 * count;
+
+   // query order: grouped by relation (slot) for TransH/TransR, original order for TransE
+   std::vector<int64_t> order(count);
+   std::iota(order.begin(), order.end(), first);
+   std::vector<int32_t> rels;
+   if (per_rel) {
+      std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return c->test_r[x] < c->test_r[y]; });
+      for (int64_t i = 0; i < count; i++)
+         if (rels.empty() || rels.back() != c->test_r[order[i]]) rels.push_back(c->test_r[order[i]]);
+   }
+   // slots per pass bounded by a memory budget for the projected matrices
+   const size_t slot_bytes = (size_t)c->D * s->ld * sizeof(double);
+   const size_t budget = (size_t)16 << 30;
+   const size_t max_slots = std::max<size_t>(1, budget / slot_bytes);
+
+   rc = ensure_query_buffers(c, nq);
+   if (rc) return rc;
+   KB2E_CUDA(c, cudaMemsetAsync(s->q_cnt, 0, (size_t)nq * 4 * sizeof(int32_t), c->stream));
+   KB2E_CUDA(c, cudaMemsetAsync(s->sums, 0, 4 * sizeof(unsigned long long), c->stream));
+
+   // query arrays (SoA, nq each): fixed entity, true answer, relation, side, slot, original index
+   std::vector<int32_t> qi(6 * (size_t)nq);
+   int32_t* qf = qi.data();
+   int32_t* qt = qf + nq;
+   int32_t* qr = qt + nq;
+   int32_t* qs = qr + nq;
+   int32_t* qslot = qs + nq;
+   int32_t* qo = qslot + nq;
+   struct Pass { int64_t q_begin, q_end; size_t tile_begin, tile_end; std::vector<int32_t> rels; };
+   std::vector<Pass> passes(1);
+   std::vector<int4> tiles;  // (first query, #queries, slot, -)
+   {
+      int64_t q = 0, tile_start = 0;
+      int cur_slot = 0;
+      passes[0].q_begin = 0;
+      passes[0].tile_begin = 0;
+      auto close_tile = [&](int64_t end) {
+         if (end > tile_start) tiles.push_back(make_int4((int)tile_start, (int)(end - tile_start), cur_slot, 0));
+         tile_start = end;
+      };
+      for (int64_t i = 0; i < count; i++) {
+         const int64_t ti = order[i];
+         const int32_t h = c->test_h[ti], t = c->test_t[ti], r = c->test_r[ti];
+         if (per_rel) {
+            Pass& cur = passes.back();
+            if (cur.rels.empty() || cur.rels.back() != r) {
+               close_tile(q);
+               if (cur.rels.size() == max_slots) {
+                  cur.q_end = q;
+                  cur.tile_end = tiles.size();
+                  Pass next;
+                  next.q_begin = q;
+                  next.tile_begin = tiles.size();
+                  passes.push_back(next);
+               }
+               passes.back().rels.push_back(r);
+               cur_slot = (int)passes.back().rels.size() - 1;
+            }
+         }
+         for (int side = 0; side < 2; side++) {
+            if (q - tile_start == kQT) close_tile(q);
+            qf[q] = side == 0 ? t : h;  // the entity that stays
+            qt[q] = side == 0 ? h : t;  // the true answer among the candidates
+            qr[q] = r;
+            qs[q] = side;
+            qslot[q] = cur_slot;
+            qo[q] = (int32_t)(2 * (ti - first) + side);
+            q++;
+         }
+      }
+      close_tile(q);
+      passes.back().q_end = q;
+      passes.back().tile_end = tiles.size();
+   }
+   KB2E_CUDA(c, cudaMemcpyAsync(s->q_int, qi.data(), qi.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+   if ((int64_t)tiles.size() > s->tile_cap) {
+      cudaFree(s->tiles);
+      s->tiles = nullptr;
+      KB2E_CUDA(c, cudaMalloc(&s->tiles, tiles.size() * sizeof(int4)));
+      s->tile_cap = (int64_t)tiles.size();
+   }
+   KB2E_CUDA(c, cudaMemcpyAsync(s->tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+
+   RankArgs a;
+   memset(&a, 0, sizeof(a));
+   a.rel64 = c->rel64;
+   a.q_fixed = s->q_int; a.q_truth = s->q_int + nq; a.q_rel = s->q_int + 2 * nq; a.q_side = s->q_int + 3 * nq;
+   a.q_slot = s->q_int + 4 * nq;
+   a.q_etrue = s->q_etrue; a.q_cnt = s->q_cnt;
+   a.seg_key = s->seg_key; a.seg_val = s->seg_val; a.nbr = s->nbr; a.seg_mask = s->seg_mask;
+   a.nq = nq; a.nE = c->nE; a.D = c->D; a.ld = s->ld;
+
+   const size_t smem = (size_t)c->D * kQT * sizeof(double2);
+   if (smem > 200 * 1024) return fail(c, KB2E_ERR_LIMIT, "embedding size too large for the ranking kernel");
+   KB2E_CUDA(c, cudaFuncSetAttribute(rank_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   KB2E_CUDA(c, cudaFuncSetAttribute(rank_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+   float main_ms = 0.f;
+   KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+   for (size_t p = 0; p < passes.size(); p++) {
+      const Pass& ps = passes[p];
+      const unsigned ntiles = (unsigned)(ps.tile_end - ps.tile_begin);
+      if (ntiles == 0) continue;
+      if (per_rel) {
+         rc = project(c, ps.rels);
+         if (rc) return rc;
+         a.ct = s->pt;
+      } else {
+         a.ct = s->ct0;
+      }
+      a.tiles = s->tiles + ps.tile_begin;
+      a.q_begin = ps.q_begin;
+      a.q_end = ps.q_end;
+      // enough CTAs to fill the machine twice even when a pass has few query tiles; per-thread
+      // counters are 16-bit, so a split never covers more than 32768 candidate steps
+      const int steps = (c->nE + kRankThreads - 1) / kRankThreads;
+      long long splits = std::max<long long>(1, (2ll * c->num_sms + ntiles - 1) / ntiles);
+      splits = std::max<long long>(splits, (steps + 32767) / 32768);
+      splits = std::min<long long>(splits, steps);
+      a.splits = (int)splits;
+      const long long pq = ps.q_end - ps.q_begin;
+      if (l2) etrue_kernel<1><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
+      else etrue_kernel<0><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
+      KB2E_CUDA(c, cudaEventRecord(s->m0, c->stream));
+      if (l2) rank_exact_kernel<1><<<dim3(ntiles, (unsigned)splits), kRankThreads, smem, c->stream>>>(a);
+      else rank_exact_kernel<0><<<dim3(ntiles, (unsigned)splits), kRankThreads, smem, c->stream>>>(a);
+      KB2E_CUDA(c, cudaEventRecord(s->m1, c->stream));
+      if (l2) filter_kernel<1><<<nblk(pq * 32, 128), 128, 0, c->stream>>>(a);
+      else filter_kernel<0><<<nblk(pq * 32, 128), 128, 0, c->stream>>>(a);
+      KB2E_CUDA(c, cudaGetLastError());
+      // the projected slots are reused by the next pass
+      KB2E_CUDA(c, cudaEventSynchronize(s->m1));
+      float ms = 0.f;
+      KB2E_CUDA(c, cudaEventElapsedTime(&ms, s->m0, s->m1));
+      main_ms += ms;
+      c->rstats.launches += per_rel ? 4 : 3;
+   }
+   finalize_kernel<<<nblk(nq, 256), 256, 0, c->stream>>>(s->q_cnt, s->q_int + 5 * nq, nq, s->out, s->sums);
+   KB2E_CUDA(c, cudaGetLastError());
+   KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+   std::vector<int32_t> out(4 * (size_t)nq);
+   unsigned long long hs[4];
+   KB2E_CUDA(c, cudaMemcpyAsync(out.data(), s->out, out.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+   KB2E_CUDA(c, cudaMemcpyAsync(hs, s->sums, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+   KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   float ms = 0.f;
+   KB2E_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+   c->rstats.kernel_ms += ms;
+   c->rstats.main_kernel_ms += main_ms;
+   c->rstats.queries += (uint64_t)nq;
+   c->rstats.launches += 2;
+   if (raw_rank) memcpy(raw_rank, out.data(), (size_t)nq * sizeof(int32_t));
+   if (filt_rank) memcpy(filt_rank, out.data() + nq, (size_t)nq * sizeof(int32_t));
+   if (raw_ties) memcpy(raw_ties, out.data() + 2 * nq, (size_t)nq * sizeof(int32_t));
+   if (filt_ties) memcpy(filt_ties, out.data() + 3 * nq, (size_t)nq * sizeof(int32_t));
+   if (sums) for (int k = 0; k < 4; k++) sums[k] = (int64_t)hs[k];
+   return KB2E_OK;
+}
+
+int rank_score64(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t* r, int64_t n, double* out) {
+   int rc = prepare_tables(c);
+   if (rc) return rc;
+   RankState* s = c->rank;
+   const bool l2 = c->cfg.model != KB2E_MODEL_TRANSH && c->cfg.distance == KB2E_DISTANCE_L2;
+   const double* ct = s->ct0;
+   int32_t* slot_of_rel = nullptr;
+   if (c->cfg.model != KB2E_MODEL_TRANSE) {
+      // project every relation (test hook: small tables only)
+      std::vector<int32_t> rels(c->nR);
+      std::iota(rels.begin(), rels.end(), 0);
+      rc = project(c, rels);
+      if (rc) return rc;
+      ct = s->pt;
+      slot_of_rel = s->slot_rel;  // identity map
+   }
+   if (l2) score64_kernel<1><<<nblk(n, 128), 128, 0, c->stream>>>(ct, c->rel64, slot_of_rel, c->D, s->ld, h, t, r, n, out);
+   else score64_kernel<0><<<nblk(n, 128), 128, 0, c->stream>>>(ct, c->rel64, slot_of_rel, c->D, s->ld, h, t, r, n, out);
+   KB2E_CUDA(c, cudaGetLastError());
+   return KB2E_OK;
+}
+
+void rank_free(kb2e_ctx* c) {
+   RankState* s = c->rank;
+   if (!s) return;
+   cudaFree(s->seg_key); cudaFree(s->seg_val); cudaFree(s->nbr); cudaFree(s->ct0); cudaFree(s->pt);
+   cudaFree(s->q_int); cudaFree(s->q_etrue); cudaFree(s->q_cnt); cudaFree(s->tiles); cudaFree(s->slot_rel);
+   cudaFree(s->sums); cudaFree(s->out);
+   if (s->m0) { cudaEventDestroy(s->m0); cudaEventDestroy(s->m1); }
+   delete s;
+   c->rank = nullptr;
+}
+
+}  // namespace kb2e

