@@ -1,0 +1,45 @@
+// Command-line options of the six programs: the reference's flag set, defaults, banner and usage
+// text (common/args.h:9-28, common/args.cpp:18-142, common/constants.h:28-54), plus GPU-only
+// options that default to the reference's behaviour.
+#ifndef KB2E_HOST_ARGS_H_
+#define KB2E_HOST_ARGS_H_
+
+#include <string>
+
+namespace kb2e_host {
+
+const int kMethodUnif = 0;  // common/constants.h:8-9
+const int kMethodBern = 1;
+const int kDistanceL1 = 0;  // common/constants.h:16-17
+const int kDistanceL2 = 1;
+
+inline const char* methodName(int method) { return method == kMethodUnif ? "unif" : "bern"; }
+
+struct EmbeddingArguments {
+   std::string dataDir = "../data";
+   std::string outputDir = ".";
+   int embeddingSize = 100;
+   double learningRate = 0.001;
+   double margin = 1.0;
+   int method = kMethodBern;
+   int numBatches = 100;
+   int maxEpochs = 1000;
+   int distanceType = kDistanceL1;
+   std::string seedDataDir = ".";
+   int seedMethod = kMethodUnif;
+   unsigned int seed;
+   // GPU-only (not in the reference; never printed in the Options banner)
+   int device = 0;
+
+   EmbeddingArguments();
+   std::string to_string() const;  // the "Options: [...]" banner, byte-compatible with the reference
+};
+
+// Exits like the reference: --help prints the usage and exits 0; a flag without its value prints
+// "Argument missing for <flag>" and exits 1; unknown flags are ignored.
+EmbeddingArguments parseArgs(int argc, char** argv);
+void printUsage(const char* invokedFile);
+
+}  // namespace kb2e_host
+
+#endif  // KB2E_HOST_ARGS_H_

@@ -1,0 +1,175 @@
+#include "trainer.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <set>
+#include <utility>
+
+#include "kb2e_b200.h"
+#include "loader.h"
+
+namespace kb2e_host {
+
+Trainer::Trainer(int model, const EmbeddingArguments& args) : model_(model), args_(args) {}
+
+Trainer::~Trainer() {
+   if (ctx_) kb2e_destroy(ctx_);
+}
+
+void Trainer::die(const char* what) {
+   printf("%s failed: %s\n", what, kb2e_last_error(ctx_));
+   exit(3);
+}
+
+void Trainer::add(int head, int tail, int relation) {
+   heads_.push_back(head);
+   tails_.push_back(tail);
+   relations_.push_back(relation);
+}
+
+void Trainer::setCounts(int numEntities, int numRelations) {
+   numEntities_ = numEntities;
+   numRelations_ = numRelations;
+}
+
+// Per relation: (#triples with r) / (#distinct heads of r) and / (#distinct tails of r), 0 for an
+// unused relation -- what the reference accumulates in two map-of-maps (common/trainer.cpp:157-194).
+void Trainer::computeBernStatistics() {
+   headMean_.assign(numRelations_, 0.0);
+   tailMean_.assign(numRelations_, 0.0);
+   std::vector<double> count(numRelations_, 0.0);
+   std::vector<std::pair<int, int>> byHead(heads_.size()), byTail(heads_.size());
+   for (size_t i = 0; i < heads_.size(); i++) {
+      count[relations_[i]] += 1.0;
+      byHead[i] = std::make_pair(relations_[i], heads_[i]);
+      byTail[i] = std::make_pair(relations_[i], tails_[i]);
+   }
+   for (int side = 0; side < 2; side++) {
+      std::vector<std::pair<int, int>>& v = side == 0 ? byHead : byTail;
+      std::sort(v.begin(), v.end());
+      v.erase(std::unique(v.begin(), v.end()), v.end());
+      std::vector<double> distinct(numRelations_, 0.0);
+      for (size_t i = 0; i < v.size(); i++) distinct[v[i].first] += 1.0;
+      std::vector<double>& out = side == 0 ? headMean_ : tailMean_;
+      for (int r = 0; r < numRelations_; r++) out[r] = distinct[r] > 0 ? count[r] / distinct[r] : 0.0;
+   }
+}
+
+void Trainer::loadFiles() {
+   IdMap entity2id, relation2id;
+   if (!loadIdFile(args_.dataDir + "/entity2id.txt", entity2id) || !loadIdFile(args_.dataDir + "/relation2id.txt", relation2id)) {
+      printf("Could not read the id files in: %s\n", args_.dataDir.c_str());
+      exit(2);
+   }
+   // the id files fix the table sizes (common/trainer.cpp:196-197); ids must be 0..N-1
+   numEntities_ = (int)entity2id.size();
+   numRelations_ = (int)relation2id.size();
+   const int nE = numEntities_, nR = numRelations_;
+   bool ok = loadTripleFile(args_.dataDir + "/train.txt", entity2id, relation2id, [this, nE, nR](int h, int t, int r) {
+      if (h < 0 || h >= nE || t < 0 || t >= nE || r < 0 || r >= nR) {
+         printf("Triple (%d, %d, %d) has an id outside 0..N-1; ids in the id files must be dense.\n", h, t, r);
+         exit(1);
+      }
+      this->add(h, t, r);
+   });
+   if (!ok) {
+      printf("Could not read: %s/train.txt\n", args_.dataDir.c_str());
+      exit(2);
+   }
+   computeBernStatistics();
+   std::cout << "Number of Relations: " << numRelations_ << std::endl;
+   std::cout << "Number of Entities: " << numEntities_ << std::endl;
+}
+
+void Trainer::prepTrain() {
+   kb2e_config cfg;
+   cfg.model = model_;
+   cfg.dim = args_.embeddingSize;
+   cfg.method = args_.method;
+   cfg.distance = args_.distanceType;
+   cfg.batches = args_.numBatches;
+   cfg.device = args_.device;
+   cfg.num_entities = numEntities_;
+   cfg.num_relations = numRelations_;
+   cfg.rate = args_.learningRate;
+   cfg.margin = args_.margin;
+   cfg.seed = args_.seed;
+   cfg.flags = 0;
+   cfg.reserved = 0;
+   if (kb2e_create(&cfg, &ctx_) != KB2E_OK) {
+      printf("kb2e_create failed: %s\n", kb2e_last_error(NULL));
+      exit(3);
+   }
+   if (kb2e_set_train_triples(ctx_, heads_.data(), tails_.data(), relations_.data(), (int64_t)heads_.size())) die("kb2e_set_train_triples");
+   if (kb2e_set_bern(ctx_, headMean_.data(), tailMean_.data())) die("kb2e_set_bern");
+   if (kb2e_init_embeddings(ctx_)) die("kb2e_init_embeddings");
+   if (model_ == KB2E_MODEL_TRANSR) {
+      // transr/trainer.cpp:88-113: entity and relation tables come from a previous (TransE) run;
+      // entity rows are scaled to unit length, relation rows are taken as they are.
+      const size_t D = (size_t)args_.embeddingSize;
+      std::vector<double> table;
+      std::string path = args_.seedDataDir + "/entity2vec." + methodName(args_.seedMethod);
+      if (!loadTable(path, (size_t)numEntities_, D, table)) {
+         printf("Failed to read embedding values from seed file: '%s'\n", path.c_str());
+         exit(1);
+      }
+      for (int i = 0; i < numEntities_; i++) {
+         double len = 0;
+         for (size_t j = 0; j < D; j++) len += table[i * D + j] * table[i * D + j];
+         len = std::sqrt(len);
+         for (size_t j = 0; j < D; j++) table[i * D + j] /= len;
+      }
+      if (kb2e_upload(ctx_, KB2E_TABLE_ENTITY, table.data(), numEntities_, (int64_t)D)) die("kb2e_upload");
+      path = args_.seedDataDir + "/relation2vec." + methodName(args_.seedMethod);
+      if (!loadTable(path, (size_t)numRelations_, D, table)) {
+         printf("Failed to read embedding values from seed file: '%s'\n", path.c_str());
+         exit(1);
+      }
+      if (kb2e_upload(ctx_, KB2E_TABLE_RELATION, table.data(), numRelations_, (int64_t)D)) die("kb2e_upload");
+   }
+}
+
+void Trainer::bfgs() {
+   // Every batch of every epoch runs inside persistent device launches; the host only prints the
+   // reference's per-epoch line (common/trainer.cpp:105).  Epochs go down in chunks so that output
+   // appears while a long run is in flight.
+   epochLoss_.assign((size_t)std::max(0, args_.maxEpochs), 0.0);
+   const int chunk = 50;
+   for (int first = 0; first < args_.maxEpochs; first += chunk) {
+      int n = std::min(chunk, args_.maxEpochs - first);
+      if (kb2e_train_epochs(ctx_, first, n, epochLoss_.data() + first)) die("kb2e_train_epochs");
+      for (int e = first; e < first + n; e++) printf("Epoch: %d, Loss: %f\n", e, epochLoss_[e]);
+      fflush(stdout);
+   }
+}
+
+void Trainer::train() {
+   prepTrain();
+   bfgs();
+}
+
+void Trainer::write() {
+   const std::string suffix = std::string(".") + methodName(args_.method);
+   const int64_t D = args_.embeddingSize;
+   std::vector<double> table((size_t)numRelations_ * D);
+   if (kb2e_download(ctx_, KB2E_TABLE_RELATION, table.data(), numRelations_, D)) die("kb2e_download");
+   if (!writeTable(args_.outputDir + "/relation2vec" + suffix, (size_t)numRelations_, (size_t)D, table.data())) {
+      printf("Could not write to: %s\n", args_.outputDir.c_str());
+      exit(2);
+   }
+   table.resize((size_t)numEntities_ * D);
+   if (kb2e_download(ctx_, KB2E_TABLE_ENTITY, table.data(), numEntities_, D)) die("kb2e_download");
+   writeTable(args_.outputDir + "/entity2vec" + suffix, (size_t)numEntities_, (size_t)D, table.data());
+   if (model_ != KB2E_MODEL_TRANSE) {
+      // transh/trainer.cpp:94-105: one row per relation; transr/trainer.cpp:128-142: D rows per relation
+      const int64_t rows = model_ == KB2E_MODEL_TRANSH ? numRelations_ : (int64_t)numRelations_ * D;
+      table.resize((size_t)rows * D);
+      if (kb2e_download(ctx_, KB2E_TABLE_WEIGHTS, table.data(), rows, D)) die("kb2e_download");
+      writeTable(args_.outputDir + "/weights" + suffix, (size_t)rows, (size_t)D, table.data());
+   }
+}
+
+}  // namespace kb2e_host
