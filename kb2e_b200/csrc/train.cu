@@ -34,15 +34,15 @@
 
 namespace kb2e {
 
-constexpr int kTrainThreads = 1024;
+constexpr int kMaxTrainThreads = 1024;
+constexpr int kTraceSlots = 64;
 
 struct TrainArgs {
    float* tab;
    float* dtab;
    float* w;
    float* dw;
-   uint8_t* flagE;   // [nE]
-   uint8_t* flagR;   // [2][nR], indexed by global-batch parity
+   uint8_t* flag;    // [nE + nR] batch stamp (1..255) of the last batch that touched the row; 0 = never
    int* rmin;
    int* rmax;
    const int4* triples;
@@ -60,6 +60,7 @@ struct TrainArgs {
    int batches, first_epoch, n_epochs, distance;
    float lr, margin;
    uint32_t seed_lo, seed_hi, flags;
+   unsigned long long* trace;     // tuning aid (KB2E_TRAIN_TRACE): per-CTA clock stamps of the first batches
 };
 
 // ---- small float4 helpers ----------------------------------------------------------------------
@@ -158,17 +159,35 @@ __device__ __forceinline__ int soft_orth_loop(float4 (&a)[NV], float4 (&b)[NV], 
 }
 
 // ---- grid-wide barrier (all CTAs are co-resident: cooperative launch) ---------------------------
-__device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& target) {
+// bar.sync orders the CTA's writes before thread 0's gpu-scope release; pollers use relaxed loads and
+// one acquire fence at the end.  Measured on B200 (tools/microbench.cu): ~1.3 us per barrier.
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+   uint32_t v;
+   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+   return v;
+}
+
+// Split in two so that work which does not depend on other CTAs can run between arrive and wait.
+__device__ __forceinline__ void grid_arrive(uint32_t* counter, uint32_t& target) {
    __syncthreads();
    if (threadIdx.x == 0) {
       target += gridDim.x;
-      __threadfence();
       red_release_add_u32(counter, 1u);
-      while ((int32_t)(ld_acquire_u32(counter) - target) < 0) {
+   }
+}
+
+__device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t target) {
+   if (threadIdx.x == 0) {
+      while ((int32_t)(ld_relaxed_u32(counter) - target) < 0) {
       }
-      __threadfence();
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
    }
    __syncthreads();
+}
+
+__device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& target) {
+   grid_arrive(counter, target);
+   grid_wait(counter, target);
 }
 
 // ---- the sampler: common/trainer.cpp:78-98 with a counter RNG -----------------------------------
@@ -207,7 +226,7 @@ __device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32
 
 // ---- phase 1: one (positive, negative) pair, TransE and TransH -----------------------------------
 template <int MODEL, int LPS, int NV>
-__device__ __forceinline__ void process_pair(const TrainArgs& a, const Pair s, int gl, uint32_t gmask, uint32_t par,
+__device__ __forceinline__ void process_pair(const TrainArgs& a, const Pair s, int gl, uint32_t gmask, uint8_t stamp,
                                              double& loss_acc, uint32_t& active_acc) {
    const int P = a.P, D = a.D;
    const float* eh = a.tab + (size_t)s.h * P;
@@ -328,29 +347,32 @@ __device__ __forceinline__ void process_pair(const TrainArgs& a, const Pair s, i
    // flag the touched rows (+ relation range per entity for the TransH/TransR constraints)
    if (gl < 3) {
       int e = gl == 0 ? s.h : (gl == 1 ? s.t : s.c);
-      a.flagE[e] = 1;
+      a.flag[e] = stamp;
       if (MODEL != KB2E_MODEL_TRANSE) {
          atomicMin(a.rmin + e, s.r);
          atomicMax(a.rmax + e, s.r);
       }
    } else if (gl == 3) {
-      a.flagR[(size_t)par * a.nR + s.r] = 1;
+      a.flag[(size_t)a.nE + s.r] = stamp;
    }
 }
 
 // ---- phase 2 -------------------------------------------------------------------------------------
-// Relation-side row r: d_r (and w_r).  transe/trainer.cpp:43, transh/trainer.cpp:48,52,56.
-template <int MODEL, int LPS, int NV>
-__device__ __forceinline__ void publish_relation(const TrainArgs& a, int r, int gl, uint32_t gmask) {
-   const int P = a.P;
-   float* cur = a.tab + ((size_t)a.nE + r) * P;
-   float* del = a.dtab + ((size_t)a.nE + r) * P;
-   float4 x[NV], d[NV];
-   load_row<LPS, NV>(cur, P, gl, x);
-   load_row<LPS, NV>(del, P, gl, d);
+// Common head of every publish: x = cur + delta, delta = 0 (rows arrive preloaded so that the loads of
+// two rows are in flight together).
+template <int LPS, int NV>
+__device__ __forceinline__ void apply_delta(float* del, int P, int gl, float4 (&x)[NV], float4 (&d)[NV]) {
 #pragma unroll
    for (int q = 0; q < NV; q++) { x[q] = x[q] + d[q]; d[q] = f4(0.f); }
    store_row<LPS, NV>(del, P, gl, d);
+}
+
+// Relation-side row r: d_r (and w_r).  transe/trainer.cpp:43, transh/trainer.cpp:48,52,56.
+template <int MODEL, int LPS, int NV>
+__device__ __forceinline__ void finish_relation(const TrainArgs& a, int r, int gl, uint32_t gmask, float4 (&x)[NV], float4 (&d)[NV]) {
+   const int P = a.P;
+   float* cur = a.tab + ((size_t)a.nE + r) * P;
+   apply_delta<LPS, NV>(a.dtab + ((size_t)a.nE + r) * P, P, gl, x, d);
    norm_row<LPS, NV>(x, true, gmask);
    if (MODEL == KB2E_MODEL_TRANSH) {
       float* wc = a.w + (size_t)r * P;
@@ -358,9 +380,7 @@ __device__ __forceinline__ void publish_relation(const TrainArgs& a, int r, int 
       float4 b[NV], db[NV];
       load_row<LPS, NV>(wc, P, gl, b);
       load_row<LPS, NV>(wd, P, gl, db);
-#pragma unroll
-      for (int q = 0; q < NV; q++) { b[q] = b[q] + db[q]; db[q] = f4(0.f); }
-      store_row<LPS, NV>(wd, P, gl, db);
+      apply_delta<LPS, NV>(wd, P, gl, b, db);
       norm_row<LPS, NV>(b, false, gmask);          // transh/trainer.cpp:52
       norm_row<LPS, NV>(b, false, gmask);          // common/utils.cpp:82
       soft_orth_loop<LPS, NV>(x, b, a.lr, gmask);  // common/utils.cpp:83-108
@@ -372,21 +392,16 @@ __device__ __forceinline__ void publish_relation(const TrainArgs& a, int r, int 
 
 // Entity row e.  transe/trainer.cpp:44-45, transh/trainer.cpp:49-50,57-58.
 template <int MODEL, int LPS, int NV>
-__device__ __forceinline__ void publish_entity(const TrainArgs& a, int e, int gl, uint32_t gmask, uint32_t next_par) {
+__device__ __forceinline__ void finish_entity(const TrainArgs& a, int e, int gl, uint32_t gmask, uint8_t next_stamp,
+                                              float4 (&x)[NV], float4 (&d)[NV]) {
    const int P = a.P;
    float* cur = a.tab + (size_t)e * P;
-   float* del = a.dtab + (size_t)e * P;
-   float4 x[NV], d[NV];
-   load_row<LPS, NV>(cur, P, gl, x);
-   load_row<LPS, NV>(del, P, gl, d);
-#pragma unroll
-   for (int q = 0; q < NV; q++) { x[q] = x[q] + d[q]; d[q] = f4(0.f); }
-   store_row<LPS, NV>(del, P, gl, d);
+   apply_delta<LPS, NV>(a.dtab + (size_t)e * P, P, gl, x, d);
    norm_row<LPS, NV>(x, true, gmask);
    if (MODEL == KB2E_MODEL_TRANSH) {
       int r0 = __ldcg(a.rmin + e), r1 = __ldcg(a.rmax + e);
       if (gl == 0) { a.rmin[e] = 0x7fffffff; a.rmax[e] = -1; }
-      for (int pass = 0; pass < 2; pass++) {
+      for (int pass = 0; pass < 2 && r1 >= 0; pass++) {
          int r = pass == 0 ? r0 : r1;
          if (pass == 1 && r1 == r0) break;
          float4 b[NV], b0[NV];
@@ -401,16 +416,268 @@ __device__ __forceinline__ void publish_entity(const TrainArgs& a, int e, int gl
 #pragma unroll
             for (int q = 0; q < NV; q++) b[q] = b[q] - b0[q];
             red_row<LPS, NV>(a.dw + (size_t)r * P, P, gl, b);
-            if (gl == 0) a.flagR[(size_t)next_par * a.nR + r] = 1;
+            if (gl == 0) a.flag[(size_t)a.nE + r] = next_stamp;
          }
       }
    }
    store_row<LPS, NV>(cur, P, gl, x);
 }
 
+
+// ================================ TransR =========================================================
+// One warp per sample, rows in the float4 layout (lane owns elements 4*lane .. 4*lane+3; D <= 128).
+// M_r is [D][P] = M[j = input dim][i = output dim] (transr/trainer.h:31): row j is contiguous in i, so
+// the projection M_r^T e streams the matrix row by row with coalesced 16-byte loads while e_j is
+// broadcast by shuffle (transr/transr.cpp:20-25, work vectors zeroed -- SURVEY.md 8c).
+__device__ __forceinline__ float comp4(const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
+__device__ __forceinline__ float4 fma4(float s, float4 m, float4 acc) {
+   return make_float4(fmaf(s, m.x, acc.x), fmaf(s, m.y, acc.y), fmaf(s, m.z, acc.z), fmaf(s, m.w, acc.w));
+}
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+   return v;
+}
+__device__ __forceinline__ void red_add1(float* p, float v) {
+   asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+// y = M^T a for up to three vectors at once (lane owns output dims 4*lane..)
+template <int NVEC>
+__device__ __forceinline__ void project3(const float* M, int D, int P, int lane, const float4 (&v)[NVEC], float4 (&y)[NVEC]) {
+   const bool on = lane * 4 < P;
+#pragma unroll
+   for (int k = 0; k < NVEC; k++) y[k] = f4(0.f);
+#pragma unroll 4
+   for (int j = 0; j < D; j++) {
+      const float4 m = on ? ld_cg4(M + (size_t)j * P + lane * 4) : f4(0.f);
+#pragma unroll
+      for (int k = 0; k < NVEC; k++) {
+         const float e = __shfl_sync(0xffffffffu, comp4(v[k], j & 3), j >> 2);
+         y[k] = fma4(e, m, y[k]);
+      }
+   }
+}
+
+__device__ __forceinline__ void process_pair_transr(const TrainArgs& a, const Pair s, int lane, uint8_t stamp,
+                                                    double& loss_acc, uint32_t& active_acc) {
+   const int P = a.P, D = a.D;
+   const bool on = lane * 4 < P;
+   float4 v[3];  // h, t, c
+   v[0] = on ? ld_cg4(a.tab + (size_t)s.h * P + lane * 4) : f4(0.f);
+   v[1] = on ? ld_cg4(a.tab + (size_t)s.t * P + lane * 4) : f4(0.f);
+   v[2] = on ? ld_cg4(a.tab + (size_t)s.c * P + lane * 4) : f4(0.f);
+   const float4 vr = on ? ld_cg4(a.tab + ((size_t)a.nE + s.r) * P + lane * 4) : f4(0.f);
+   const float* M = a.w + (size_t)s.r * a.w_row;
+   float4 y[3];
+   project3<3>(M, D, P, lane, v, y);
+   const bool l1 = a.distance == KB2E_DISTANCE_L1;
+   const float4 rp = (y[1] - y[0]) - vr;
+   const float4 rn = s.corruptTail ? (y[2] - y[0]) - vr : (y[1] - y[2]) - vr;
+   float ep = l1 ? abs4(rp) : dot4(rp, rp);
+   float en = l1 ? abs4(rn) : dot4(rn, rn);
+   ep = wsum(ep);
+   en = wsum(en);
+   if (!(ep + a.margin > en)) return;  // common/trainer.cpp:138
+   if (lane == 0) {
+      loss_acc += (double)(a.margin + ep - en);
+      active_acc++;
+   }
+   const float lr = a.lr;
+   const float4 gp = l1 ? lr * sign4(rp, lane * 4, D) : (2.f * lr) * rp;
+   const float4 gn = l1 ? lr * sign4(rn, lane * 4, D) : (2.f * lr) * rn;
+   // transr/trainer.cpp:171: r -= beta*lr*x
+   if (on) red_add4(a.dtab + ((size_t)a.nE + s.r) * P + lane * 4, gp - gn);
+   // negative triple's head / tail
+   const float4 nh = s.corruptTail ? v[0] : v[2];
+   const float4 nt = s.corruptTail ? v[2] : v[1];
+   const float4 dpos = v[0] - v[1];  // h - t   (positive)
+   const float4 dneg = nh - nt;      // h' - t' (negative)
+   float* dM = a.dw + (size_t)s.r * a.w_row;
+   float4 sp = f4(0.f), sn = f4(0.f);  // S_j = sum_i g_i M[j][i] for j = 4*lane + c
+#pragma unroll 2
+   for (int j = 0; j < D; j++) {
+      const float4 m = on ? ld_cg4(M + (size_t)j * P + lane * 4) : f4(0.f);
+      // transr/trainer.cpp:167: M[j][i] -= beta*lr*x_i*(h_j - t_j)
+      const float pj = __shfl_sync(0xffffffffu, comp4(dpos, j & 3), j >> 2);
+      const float nj = __shfl_sync(0xffffffffu, comp4(dneg, j & 3), j >> 2);
+      if (on) red_add4(dM + (size_t)j * P + lane * 4, pj * gp - nj * gn);
+      // transr/trainer.cpp:168-169: e[j] -/+= beta*lr*x_i*M[j][i], summed over i
+      const float a_p = wsum(dot4(gp, m));
+      const float a_n = wsum(dot4(gn, m));
+      if ((j >> 2) == lane) {
+         const int c = j & 3;
+         if (c == 0) { sp.x = a_p; sn.x = a_n; } else if (c == 1) { sp.y = a_p; sn.y = a_n; }
+         else if (c == 2) { sp.z = a_p; sn.z = a_n; } else { sp.w = a_p; sn.w = a_n; }
+      }
+   }
+   if (on) {
+      float* dh = a.dtab + (size_t)s.h * P + lane * 4;
+      float* dt = a.dtab + (size_t)s.t * P + lane * 4;
+      float* dc = a.dtab + (size_t)s.c * P + lane * 4;
+      if (s.corruptTail) {
+         red_add4(dh, sp - sn);        // head is shared by both triples
+         red_add4(dt, -1.f * sp);
+         red_add4(dc, sn);
+      } else {
+         red_add4(dh, sp);
+         red_add4(dt, sn - sp);        // tail is shared
+         red_add4(dc, -1.f * sn);
+      }
+   }
+   if (lane < 3) {
+      int e = lane == 0 ? s.h : (lane == 1 ? s.t : s.c);
+      a.flag[e] = stamp;
+      atomicMin(a.rmin + e, s.r);
+      atomicMax(a.rmax + e, s.r);
+   } else if (lane == 3) {
+      a.flag[(size_t)a.nE + s.r] = stamp;
+   }
+}
+
+// transr/trainer.cpp:174,178-180: r unit length; every row M_r[j][.] unit length (after the delta).
+__device__ __forceinline__ void finish_relation_transr(const TrainArgs& a, int r, int lane, float4 x, float4 d) {
+   const int P = a.P, D = a.D;
+   const bool on = lane * 4 < P;
+   float* cur = a.tab + ((size_t)a.nE + r) * P + lane * 4;
+   float* del = a.dtab + ((size_t)a.nE + r) * P + lane * 4;
+   x = x + d;
+   float len = sqrtf(wsum(dot4(x, x)));
+   if (on) {
+      st_cg4(del, f4(0.f));
+      st_cg4(cur, make_float4(x.x / len, x.y / len, x.z / len, x.w / len));
+   }
+   float* M = a.w + (size_t)r * a.w_row;
+   float* dM = a.dw + (size_t)r * a.w_row;
+#pragma unroll 4
+   for (int j = 0; j < D; j++) {
+      float4 m = on ? ld_cg4(M + (size_t)j * P + lane * 4) : f4(0.f);
+      float4 dm = on ? ld_cg4(dM + (size_t)j * P + lane * 4) : f4(0.f);
+      m = m + dm;
+      float l = sqrtf(wsum(dot4(m, m)));
+      if (on) {
+         st_cg4(dM + (size_t)j * P + lane * 4, f4(0.f));
+         st_cg4(M + (size_t)j * P + lane * 4, make_float4(m.x / l, m.y / l, m.z / l, m.w / l));
+      }
+   }
+}
+
+// transRNorm (transr/trainer.cpp:35-64) of entity row x against the published, read-only M_r; the
+// perturbation the reference applies to M_r goes to the NEXT batch's delta.
+__device__ __forceinline__ void transr_constraint(const TrainArgs& a, int r, int lane, uint8_t next_stamp, float4& x) {
+   const int P = a.P, D = a.D;
+   const float* M = a.w + (size_t)r * a.w_row;
+   float* dM = a.dw + (size_t)r * a.w_row;
+   bool touched = false;
+   for (int iter = 0; iter < 64; iter++) {
+      float4 v[1] = {x}, y[1];
+      project3<1>(M, D, P, lane, v, y);
+      if (wsum(dot4(y[0], y[0])) <= 1.f) break;
+      touched = true;
+      for (int i = 0; i < D; i++) {
+         // lane owns input dims j = 4*lane + c: column i of M for those rows
+         float m[4], part = 0.f;
+#pragma unroll
+         for (int c = 0; c < 4; c++) {
+            int j = lane * 4 + c;
+            m[c] = j < D ? __ldcg(M + (size_t)j * P + i) : 0.f;
+            part += m[c] * comp4(x, c);
+         }
+         const float tmp = 2.f * wsum(part);
+         float nx[4];
+#pragma unroll
+         for (int c = 0; c < 4; c++) {
+            int j = lane * 4 + c;
+            float aj = comp4(x, c);
+            float delta = -(a.lr * tmp * aj);
+            if (j < D) red_add1(dM + (size_t)j * P + i, delta);
+            nx[c] = aj - a.lr * tmp * (m[c] + delta);
+         }
+         x = make_float4(nx[0], nx[1], nx[2], nx[3]);
+      }
+   }
+   if (touched && lane == 0) a.flag[(size_t)a.nE + r] = next_stamp;
+}
+
+// Entity row: unit length (transr/trainer.cpp:175-176), then transRNorm against the lowest / highest
+// relation that touched it, and -- the reference's quirk at :187 -- against M_e when relation e was
+// touched (the reference indexes the ENTITY table with the relation id there).
+__device__ __forceinline__ void finish_entity_transr(const TrainArgs& a, int e, int lane, uint8_t stamp, uint8_t next_stamp,
+                                                     bool own, float4 x, float4 d) {
+   const int P = a.P;
+   const bool on = lane * 4 < P;
+   float* cur = a.tab + (size_t)e * P + lane * 4;
+   int r0 = 0x7fffffff, r1 = -1;
+   if (own) {
+      x = x + d;
+      float len = sqrtf(wsum(dot4(x, x)));
+      x = make_float4(x.x / len, x.y / len, x.z / len, x.w / len);
+      if (on) st_cg4(a.dtab + (size_t)e * P + lane * 4, f4(0.f));
+      r0 = __ldcg(a.rmin + e);
+      r1 = __ldcg(a.rmax + e);
+      if (lane == 0) { a.rmin[e] = 0x7fffffff; a.rmax[e] = -1; }
+      if (r1 >= 0) {
+         transr_constraint(a, r0, lane, next_stamp, x);
+         if (r1 != r0) transr_constraint(a, r1, lane, next_stamp, x);
+      }
+   }
+   const bool quirk = !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK) && e < a.nR && __ldcg(a.flag + a.nE + e) == stamp;
+   if (quirk && !(own && (r0 == e || r1 == e))) transr_constraint(a, e, lane, next_stamp, x);
+   if (on) st_cg4(cur, x);
+}
+
+// Rows [row_begin, row_end) of the unified row space (entities, then relations) whose stamp says
+// "touched in this batch".  Two rows per group are examined per step, flags first, then both rows'
+// loads, then the arithmetic, so that the L2 round trips overlap.
 template <int MODEL, int LPS, int NV>
-__global__ void __launch_bounds__(kTrainThreads, 1) train_kernel(const __grid_constant__ TrainArgs a) {
-   __shared__ double s_loss[kTrainThreads / 32];
+__device__ __forceinline__ void publish_rows(const TrainArgs& a, long long row_begin, long long row_end, long long g0, long long G,
+                                             uint8_t stamp, uint8_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel) {
+   const int P = a.P;
+   for (long long base = row_begin + g0; base < row_end; base += 2 * G) {
+      const long long r0 = base, r1 = base + G;
+      bool f0 = __ldcg(a.flag + r0) == stamp;
+      bool f1 = r1 < row_end && __ldcg(a.flag + r1) == stamp;
+      bool own0 = f0, own1 = f1;
+      if (MODEL == KB2E_MODEL_TRANSR && !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK)) {
+         // transr/trainer.cpp:187: entity row e is also visited when RELATION e was touched
+         if (r0 < a.nE && r0 < a.nR) f0 = f0 || __ldcg(a.flag + a.nE + r0) == stamp;
+         if (r1 < row_end && r1 < a.nE && r1 < a.nR) f1 = f1 || __ldcg(a.flag + a.nE + r1) == stamp;
+      }
+      float4 x0[NV], d0[NV], x1[NV], d1[NV];
+      if (f0) {
+         load_row<LPS, NV>(a.tab + (size_t)r0 * P, P, gl, x0);
+         load_row<LPS, NV>(a.dtab + (size_t)r0 * P, P, gl, d0);
+      }
+      if (f1) {
+         load_row<LPS, NV>(a.tab + (size_t)r1 * P, P, gl, x1);
+         load_row<LPS, NV>(a.dtab + (size_t)r1 * P, P, gl, d1);
+      }
+      if constexpr (MODEL == KB2E_MODEL_TRANSR) {
+         if (f0) {
+            if (r0 >= a.nE) { finish_relation_transr(a, (int)(r0 - a.nE), gl, x0[0], d0[0]); trel += (gl == 0); }
+            else { finish_entity_transr(a, (int)r0, gl, stamp, next_stamp, own0, x0[0], d0[0]); tent += (gl == 0 && own0); }
+         }
+         if (f1) {
+            if (r1 >= a.nE) { finish_relation_transr(a, (int)(r1 - a.nE), gl, x1[0], d1[0]); trel += (gl == 0); }
+            else { finish_entity_transr(a, (int)r1, gl, stamp, next_stamp, own1, x1[0], d1[0]); tent += (gl == 0 && own1); }
+         }
+      } else {
+         (void)own0; (void)own1;
+         if (f0) {
+            if (r0 >= a.nE) { finish_relation<MODEL, LPS, NV>(a, (int)(r0 - a.nE), gl, gmask, x0, d0); trel += (gl == 0); }
+            else { finish_entity<MODEL, LPS, NV>(a, (int)r0, gl, gmask, next_stamp, x0, d0); tent += (gl == 0); }
+         }
+         if (f1) {
+            if (r1 >= a.nE) { finish_relation<MODEL, LPS, NV>(a, (int)(r1 - a.nE), gl, gmask, x1, d1); trel += (gl == 0); }
+            else { finish_entity<MODEL, LPS, NV>(a, (int)r1, gl, gmask, next_stamp, x1, d1); tent += (gl == 0); }
+         }
+      }
+   }
+}
+
+template <int MODEL, int LPS, int NV, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant__ TrainArgs a) {
+   __shared__ double s_loss[THREADS / 32];
    const int lane = threadIdx.x & 31;
    const int gl = lane % LPS;
    const uint32_t gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << ((lane / LPS) * LPS));
@@ -418,40 +685,63 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_kernel(const __grid_co
    const long long G = (long long)gridDim.x * groups_per_block;
    // Samples (and rows) are dealt round-robin over CTAs so every SM gets an equal share.
    const long long g0 = (long long)(threadIdx.x / LPS) * gridDim.x + blockIdx.x;
-   const long long tid_global = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-   const long long nthreads = (long long)gridDim.x * blockDim.x;
+   const long long R = (long long)a.nE + a.nR;
    uint32_t bar_target = 0;
    uint32_t active_acc = 0, tent_acc = 0, trel_acc = 0;
+   int trace_slot = 0;
+#define KB2E_TRACE()                                                                                  \
+   if (a.trace != nullptr && threadIdx.x == 0 && trace_slot < kTraceSlots) {                          \
+      unsigned long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+      a.trace[(size_t)blockIdx.x * kTraceSlots + trace_slot++] = t_;                                  \
+   }
+   const uint32_t gb_first = (uint32_t)a.first_epoch * (uint32_t)a.batches;
+   // The sampler does not depend on the embeddings, so each group draws its first sample of the
+   // NEXT batch (triple fetch + rejection probes) before waiting at the end-of-batch barrier.
+   Pair pre;
+   const bool has_first = g0 < a.batchsize;
+   if (has_first) pre = draw_pair(a, (uint32_t)g0, gb_first);
 
    for (int ep = 0; ep < a.n_epochs; ep++) {
       double loss_acc = 0.0;
       for (int batch = 0; batch < a.batches; batch++) {
-         const uint32_t gb = (uint32_t)(a.first_epoch + ep) * (uint32_t)a.batches + (uint32_t)batch;
-         const uint32_t par = gb & 1u;
+         const uint32_t gb = gb_first + (uint32_t)ep * (uint32_t)a.batches + (uint32_t)batch;
+         const uint8_t stamp = (uint8_t)(gb % 255u + 1u);
+         const uint8_t next_stamp = (uint8_t)((gb + 1u) % 255u + 1u);
+         KB2E_TRACE();
          // ---- phase 1 ----
-         // The relation flags of the previous batch (other parity) are dead by now: clear them.
-         for (long long i = tid_global; i < a.nR; i += nthreads) a.flagR[(size_t)(par ^ 1u) * a.nR + i] = 0;
-         for (long long k = g0; k < a.batchsize; k += G) {
-            Pair s = draw_pair(a, (uint32_t)k, gb);
-            process_pair<MODEL, LPS, NV>(a, s, gl, gmask, par, loss_acc, active_acc);
-         }
-         grid_barrier(a.barrier, bar_target);
-         // ---- phase 2a: relation-side rows ----
-         for (long long r = g0; r < a.nR; r += G) {
-            if (__ldcg(a.flagR + (size_t)par * a.nR + r)) {
-               publish_relation<MODEL, LPS, NV>(a, (int)r, gl, gmask);
-               if (gl == 0) trel_acc++;
+         if constexpr (MODEL == KB2E_MODEL_TRANSR) {
+            if (has_first) process_pair_transr(a, pre, gl, stamp, loss_acc, active_acc);
+            for (long long k = g0 + G; k < a.batchsize; k += G) {
+               Pair s = draw_pair(a, (uint32_t)k, gb);
+               process_pair_transr(a, s, gl, stamp, loss_acc, active_acc);
+            }
+         } else {
+            if (has_first) process_pair<MODEL, LPS, NV>(a, pre, gl, gmask, stamp, loss_acc, active_acc);
+            for (long long k = g0 + G; k < a.batchsize; k += G) {
+               Pair s = draw_pair(a, (uint32_t)k, gb);
+               process_pair<MODEL, LPS, NV>(a, s, gl, gmask, stamp, loss_acc, active_acc);
             }
          }
-         if (MODEL != KB2E_MODEL_TRANSE) grid_barrier(a.barrier, bar_target);
-         // ---- phase 2b: entity rows ----
-         for (long long e = g0; e < a.nE; e += G) {
-            if (__ldcg(a.flagE + e)) {
-               publish_entity<MODEL, LPS, NV>(a, (int)e, gl, gmask, par ^ 1u);
-               if (gl == 0) { a.flagE[e] = 0; tent_acc++; }
-            }
-         }
+         KB2E_TRACE();
          grid_barrier(a.barrier, bar_target);
+         KB2E_TRACE();
+         // ---- phase 2 ----
+         if (MODEL == KB2E_MODEL_TRANSE) {
+            // no coupling between relation and entity rows: one pass over the whole row space
+            publish_rows<MODEL, LPS, NV>(a, 0, R, g0, G, stamp, next_stamp, gl, gmask, tent_acc, trel_acc);
+            KB2E_TRACE();
+         } else {
+            publish_rows<MODEL, LPS, NV>(a, a.nE, R, g0, G, stamp, next_stamp, gl, gmask, tent_acc, trel_acc);
+            grid_barrier(a.barrier, bar_target);
+            KB2E_TRACE();
+            publish_rows<MODEL, LPS, NV>(a, 0, a.nE, g0, G, stamp, next_stamp, gl, gmask, tent_acc, trel_acc);
+         }
+         KB2E_TRACE();
+         grid_arrive(a.barrier, bar_target);
+         // the next batch's first sample is drawn while the other CTAs arrive
+         if (has_first && !(ep == a.n_epochs - 1 && batch == a.batches - 1)) pre = draw_pair(a, (uint32_t)g0, gb + 1u);
+         grid_wait(a.barrier, bar_target);
       }
       // epoch loss: group leaders -> warp -> block -> one atomic per CTA
       double v = (gl == 0) ? loss_acc : 0.0;
@@ -467,7 +757,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_kernel(const __grid_co
       __syncthreads();
    }
    // counters
-   uint32_t c0 = (gl == 0) ? active_acc : 0u, c1 = (gl == 0) ? tent_acc : 0u, c2 = (gl == 0) ? trel_acc : 0u;
+   uint32_t c0 = (gl == 0) ? active_acc : 0u, c1 = tent_acc, c2 = trel_acc;
 #pragma unroll
    for (int o = 16; o > 0; o >>= 1) {
       c0 += __shfl_xor_sync(0xffffffffu, c0, o);
@@ -525,6 +815,24 @@ __global__ void score32_kernel(const float* tab, const float* w, int nE, int D, 
       e += l1 ? abs4(res) : dot4(res, res);
    }
    e = gsum<32>(e, 0xffffffffu);
+   if (lane == 0) out[k] = (double)e;
+}
+
+// TransR fp32 energies with the arithmetic of process_pair_transr (one warp per triple).
+__global__ void score32_transr_kernel(const float* tab, const float* w, size_t w_row, int nE, int D, int P, int distance,
+                                      const int32_t* h, const int32_t* t, const int32_t* r, long long n, double* out) {
+   long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   int lane = threadIdx.x & 31;
+   if (k >= n) return;
+   const bool on = lane * 4 < P;
+   float4 v[2], y[2];
+   v[0] = on ? ld_cg4(tab + (size_t)h[k] * P + lane * 4) : f4(0.f);
+   v[1] = on ? ld_cg4(tab + (size_t)t[k] * P + lane * 4) : f4(0.f);
+   const float4 vr = on ? ld_cg4(tab + ((size_t)nE + r[k]) * P + lane * 4) : f4(0.f);
+   project3<2>(w + (size_t)r[k] * w_row, D, P, lane, v, y);
+   const float4 res = (y[1] - y[0]) - vr;
+   float e = distance == KB2E_DISTANCE_L1 ? abs4(res) : dot4(res, res);
+   e = wsum(e);
    if (lane == 0) out[k] = (double)e;
 }
 
@@ -740,7 +1048,7 @@ int tables_64_to_32(kb2e_ctx* c) {
 static void fill_args(kb2e_ctx* c, TrainArgs& a) {
    memset(&a, 0, sizeof(a));
    a.tab = c->tab; a.dtab = c->dtab; a.w = c->w; a.dw = c->dw;
-   a.flagE = c->flag; a.flagR = c->flag + c->nE;
+   a.flag = c->flag;
    a.rmin = c->rmin; a.rmax = c->rmax;
    a.triples = c->triples; a.hash = c->hash; a.hash_mask = c->hash_mask; a.pr = c->pr;
    a.barrier = c->barrier; a.loss = c->loss_dev; a.counters = c->counters;
@@ -758,9 +1066,11 @@ static void fill_args(kb2e_ctx* c, TrainArgs& a) {
 
 typedef void (*TrainKernel)(const TrainArgs);
 
-template <int MODEL>
-static TrainKernel pick_kernel(int lps, int nv) {
-#define KB2E_PICK(L, N) if (lps == L && nv == N) return train_kernel<MODEL, L, N>;
+// One persistent CTA per SM; fewer threads per CTA buy registers (65536 / THREADS per thread) for the
+// shapes that keep more vectors per lane in flight.
+template <int MODEL, int THREADS>
+static TrainKernel pick_kernel_t(int lps, int nv) {
+#define KB2E_PICK(L, N) if (lps == L && nv == N) return train_kernel<MODEL, L, N, THREADS>;
    KB2E_PICK(8, 1) KB2E_PICK(8, 2) KB2E_PICK(8, 4)
    KB2E_PICK(16, 1) KB2E_PICK(16, 2) KB2E_PICK(16, 4)
    KB2E_PICK(32, 1) KB2E_PICK(32, 2) KB2E_PICK(32, 4)
@@ -768,39 +1078,54 @@ static TrainKernel pick_kernel(int lps, int nv) {
    return nullptr;
 }
 
+template <int MODEL>
+static TrainKernel pick_kernel(int lps, int nv, int threads) {
+   if (threads == 1024) return pick_kernel_t<MODEL, 1024>(lps, nv);
+   if (threads == 768) return pick_kernel_t<MODEL, 768>(lps, nv);
+   if (threads == 512) return pick_kernel_t<MODEL, 512>(lps, nv);
+   return nullptr;
+}
+
+static int threads_for(int model, int nv) {
+   const char* env = getenv("KB2E_TRAIN_THREADS");
+   if (env) return atoi(env);
+   if (nv >= 4) return 512;
+   if (nv == 2 || model != KB2E_MODEL_TRANSE) return 768;
+   return 1024;
+}
+
 // Choose lanes-per-sample (LPS) / float4-vectors-per-lane (NV): among the shapes that waste the
 // fewest lanes on padding, take the widest group whose group count still covers the whole batch in
 // one pass over the resident groups; KB2E_TRAIN_LPS overrides (tuning aid).
-static void choose_shape(const kb2e_ctx* c, long long batchsize, int& lps, int& nv) {
+static void choose_shape(const kb2e_ctx* c, long long batchsize, int& lps, int& nv, int& threads_out) {
    const int vecs = (c->P + 3) / 4;
-   const long long threads = (long long)c->num_sms * kTrainThreads;
    const int maxnv = (c->cfg.model == KB2E_MODEL_TRANSH) ? 2 : 4;
    const char* env = getenv("KB2E_TRAIN_LPS");
    const int forced = env ? atoi(env) : 0;
-   int Ls[3] = {32, 16, 8}, Ns[3];
+   int Ls[3] = {32, 16, 8}, Ns[3], Ts[3];
    double eff[3], best = 0.0;
    for (int i = 0; i < 3; i++) {
       int N = (vecs + Ls[i] - 1) / Ls[i];
       Ns[i] = N <= 1 ? 1 : (N <= 2 ? 2 : (N <= 4 ? 4 : 99));
+      Ts[i] = threads_for(c->cfg.model, Ns[i]);
       eff[i] = (Ns[i] <= maxnv || Ls[i] == 32) ? (double)vecs / (Ls[i] * Ns[i]) : 0.0;
       if (Ns[i] > 4) eff[i] = 0.0;
       best = std::max(best, eff[i]);
    }
-   lps = 32; nv = Ns[0];
+   lps = 32; nv = Ns[0]; threads_out = Ts[0];
    if (best == 0.0) { nv = 99; return; }
    int widest = -1, fit = -1;
    for (int i = 0; i < 3; i++) {
-      if (forced == Ls[i] && eff[i] > 0.0) { lps = Ls[i]; nv = Ns[i]; return; }
+      if (forced == Ls[i] && eff[i] > 0.0) { lps = Ls[i]; nv = Ns[i]; threads_out = Ts[i]; return; }
       if (eff[i] < 0.75 * best) continue;
       if (widest < 0) widest = i;
-      if (fit < 0 && threads / Ls[i] >= batchsize) fit = i;
+      if (fit < 0 && (long long)c->num_sms * Ts[i] / Ls[i] >= batchsize) fit = i;
    }
    int pick = fit >= 0 ? fit : widest;
-   lps = Ls[pick]; nv = Ns[pick];
+   lps = Ls[pick]; nv = Ns[pick]; threads_out = Ts[pick];
 }
 
 int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_dev, int64_t n_pairs, double* loss_out) {
-   if (c->cfg.model == KB2E_MODEL_TRANSR) return fail(c, KB2E_ERR_LIMIT, "TransR training kernel not built yet");
    if (!c->have32) return fail(c, KB2E_ERR_ARG, "no embeddings: call kb2e_init_embeddings or kb2e_upload first");
    TrainArgs a;
    if (n_epochs <= 0) return KB2E_OK;
@@ -823,25 +1148,52 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
       a.batchsize = c->n_train / c->cfg.batches;  // common/trainer.cpp:70
    }
    if ((int64_t)a.batchsize >= (1ll << 32)) return fail(c, KB2E_ERR_LIMIT, "batch larger than 2^32 samples");
-   int lps, nv;
-   choose_shape(c, a.batchsize, lps, nv);
+   int lps, nv, threads;
+   choose_shape(c, a.batchsize, lps, nv, threads);
    if (nv > 4) return fail(c, KB2E_ERR_LIMIT, "embedding size above 512 is not supported by the training kernel");
-   TrainKernel k = c->cfg.model == KB2E_MODEL_TRANSE ? pick_kernel<KB2E_MODEL_TRANSE>(lps, nv) : pick_kernel<KB2E_MODEL_TRANSH>(lps, nv);
+   TrainKernel k = nullptr;
+   if (c->cfg.model == KB2E_MODEL_TRANSR) {
+      if (c->P > 128) return fail(c, KB2E_ERR_LIMIT, "TransR training supports embedding sizes up to 128");
+      lps = 32; nv = 1; threads = 768;
+      k = train_kernel<KB2E_MODEL_TRANSR, 32, 1, 768>;
+   } else if (c->cfg.model == KB2E_MODEL_TRANSE) {
+      k = pick_kernel<KB2E_MODEL_TRANSE>(lps, nv, threads);
+   } else {
+      k = pick_kernel<KB2E_MODEL_TRANSH>(lps, nv, threads);
+   }
    if (!k) return fail(c, KB2E_ERR_LIMIT, "no training kernel for this embedding size");
    int per_sm = 0;
-   KB2E_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kTrainThreads, 0));
+   KB2E_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0));
    if (per_sm < 1) return fail(c, KB2E_ERR_CUDA, "training kernel does not fit on an SM");
    KB2E_CUDA(c, cudaMemsetAsync(c->barrier, 0, 64, c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->loss_dev, 0, (size_t)n_epochs * sizeof(double), c->stream));
+   const char* trace_path = getenv("KB2E_TRAIN_TRACE");
+   unsigned long long* trace_dev = nullptr;
+   if (trace_path) {
+      KB2E_CUDA(c, cudaMalloc(&trace_dev, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long)));
+      KB2E_CUDA(c, cudaMemsetAsync(trace_dev, 0, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long), c->stream));
+      a.trace = trace_dev;
+   }
    void* params[] = {&a};
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-   KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(kTrainThreads), params, 0, c->stream));
+   KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(threads), params, 0, c->stream));
    KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
    std::vector<double> loss(n_epochs);
    unsigned long long cnt[3];
    KB2E_CUDA(c, cudaMemcpyAsync(loss.data(), c->loss_dev, (size_t)n_epochs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(cnt, c->counters, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   if (trace_dev) {
+      std::vector<unsigned long long> tr((size_t)c->num_sms * kTraceSlots);
+      cudaMemcpy(tr.data(), trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      cudaFree(trace_dev);
+      if (FILE* f = fopen(trace_path, "w")) {
+         for (int b = 0; b < c->num_sms; b++) {
+            for (int k = 0; k < kTraceSlots; k++) fprintf(f, "%llu%c", tr[(size_t)b * kTraceSlots + k], k + 1 == kTraceSlots ? '\n' : ' ');
+         }
+         fclose(f);
+      }
+   }
    float ms = 0.f;
    KB2E_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
    c->tstats.kernel_ms += ms;
@@ -871,9 +1223,11 @@ int train_score32(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t
       int rc = tables_64_to_32(c);
       if (rc) return rc;
    }
-   if (c->cfg.model == KB2E_MODEL_TRANSR) return fail(c, KB2E_ERR_LIMIT, "fp32 TransR scoring not built yet");
    unsigned blocks = blocks_for(n * 32, 256);
-   if (c->cfg.model == KB2E_MODEL_TRANSE)
+   if (c->cfg.model == KB2E_MODEL_TRANSR) {
+      if (c->P > 128) return fail(c, KB2E_ERR_LIMIT, "TransR fp32 scoring supports embedding sizes up to 128");
+      score32_transr_kernel<<<blocks, 256, 0, c->stream>>>(c->tab, c->w, c->w_row, c->nE, c->D, c->P, c->cfg.distance, h, t, r, n, out);
+   } else if (c->cfg.model == KB2E_MODEL_TRANSE)
       score32_kernel<KB2E_MODEL_TRANSE><<<blocks, 256, 0, c->stream>>>(c->tab, c->w, c->nE, c->D, c->P, c->cfg.distance, h, t, r, n, out);
    else
       score32_kernel<KB2E_MODEL_TRANSH><<<blocks, 256, 0, c->stream>>>(c->tab, c->w, c->nE, c->D, c->P, c->cfg.distance, h, t, r, n, out);

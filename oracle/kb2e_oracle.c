@@ -573,34 +573,32 @@ static int soft_orth_entity(double* a, const double* b0, double* db, int n, doub
    return iters;
 }
 
-/* transRNorm (transr/trainer.cpp:35-64) on an entity row against a FIXED matrix: `a` updated in
- * place, the matrix perturbation accumulated into dM for the next batch. */
-static int transr_norm_entity(double* a, const double* M0, double* dM, int D, double lr, double* M) {
+/* transRNorm (transr/trainer.cpp:35-64) on an entity row against a FIXED matrix: the published M_r is
+ * read-only during the phase, so every sweep reads M0; `a` is updated in place exactly as the
+ * reference does within a sweep (column i of M is perturbed first, then a uses the perturbed
+ * column), and the perturbations of all sweeps are accumulated into dM for the next batch. */
+static int transr_norm_entity(double* a, const double* M0, double* dM, int D, double lr, double* unused) {
+   (void)unused;
    int iters = 0;
-   int copied = 0;
-   const double* Mc = M0;
    while (1) {
       double x = 0;
       for (int i = 0; i < D; i++) {
          double tmp = 0;
-         for (int j = 0; j < D; j++) tmp += Mc[(size_t)j * D + i] * a[j];
+         for (int j = 0; j < D; j++) tmp += M0[(size_t)j * D + i] * a[j];
          x += sqr(tmp);
       }
       if (x <= 1 || iters >= 64) break;
-      if (!copied) { memcpy(M, M0, sizeof(double) * (size_t)D * D); copied = 1; Mc = M; }
       for (int i = 0; i < D; i++) {
          double tmp = 0;
-         for (int j = 0; j < D; j++) tmp += M[(size_t)j * D + i] * a[j];
+         for (int j = 0; j < D; j++) tmp += M0[(size_t)j * D + i] * a[j];
          tmp *= 2;
          for (int j = 0; j < D; j++) {
-            M[(size_t)j * D + i] -= lr * tmp * a[j];
-            a[j] -= lr * tmp * M[(size_t)j * D + i];
+            double delta = -(lr * tmp * a[j]);
+            dM[(size_t)j * D + i] += delta;
+            a[j] -= lr * tmp * (M0[(size_t)j * D + i] + delta);
          }
       }
       iters++;
-   }
-   if (iters) {
-      for (size_t k = 0; k < (size_t)D * D; k++) dM[k] += M[k] - M0[k];
    }
    return iters;
 }
@@ -676,7 +674,7 @@ double orc_train_batch_dfr(int model, int distance, int D, int nE, int nR, doubl
    double* scratch = (double*)malloc(sizeof(double) * (model == 2 ? (size_t)D * D : (size_t)D));
    double* sink = (double*)calloc(wrow, sizeof(double));
    for (int e = 0; e < nE; e++) {
-      int quirk = (model == 2 && e < nR && aR[e]); /* transr/trainer.cpp:187 */
+      int quirk = (model == 2 && e < nR && tR[e]); /* transr/trainer.cpp:187 */
       if (!tE[e] && !quirk) continue;
       double* row = ent + (size_t)e * D;
       if (tE[e]) {

@@ -182,6 +182,11 @@ class Reference:
         L = self.lib = C.CDLL(REF_SO)
         L.ref_vec_len.restype = C.c_double
         L.ref_train_files.restype = C.c_double
+        L.ref_trainer_create.restype = C.c_void_p
+        L.ref_trainer_epochs.restype = C.c_double
+        L.ref_trainer_epochs.argtypes = [C.c_void_p, C.c_int]
+        L.ref_trainer_write.argtypes = [C.c_void_p]
+        L.ref_trainer_destroy.argtypes = [C.c_void_p]
 
     def energy(self, model, distance, ent, rel, w, h, t, r, zero_work=True):
         ent, rel, w = f64(ent), f64(rel), f64(w)
@@ -248,3 +253,26 @@ class Reference:
         return self.lib.ref_train_files(model, datadir.encode(), outdir.encode(), D, C.c_double(lr), C.c_double(margin),
                                         method, distance, batches, epochs, C.c_uint(seed), seeddir.encode(),
                                         seedmethod, int(zero_work), int(write))
+
+
+class ReferenceTrainer:
+    """A live reference trainer (loadFiles + prepTrain done once); ``epochs(n)`` times n more epochs of
+    the reference's own bfgs() loop.  Used by bench.py --impl reference and the statistical-parity runs."""
+
+    def __init__(self, ref, model, datadir, outdir, D, lr, margin, method, distance, batches, seed,
+                 seeddir=".", seedmethod=0, zero_work=True):
+        self.ref = ref
+        self.h = C.c_void_p(ref.lib.ref_trainer_create(model, datadir.encode(), outdir.encode(), D, C.c_double(lr),
+                                                        C.c_double(margin), method, distance, batches, C.c_uint(seed),
+                                                        seeddir.encode(), seedmethod, int(zero_work)))
+
+    def epochs(self, n):
+        return self.ref.lib.ref_trainer_epochs(self.h, int(n))
+
+    def write(self):
+        self.ref.lib.ref_trainer_write(self.h)
+
+    def close(self):
+        if self.h:
+            self.ref.lib.ref_trainer_destroy(self.h)
+            self.h = None

@@ -443,4 +443,60 @@ int ref_bern(const char* datadir, int nR, double* head_mean, double* tail_mean) 
    return 0;
 }
 
+// ---- persistent reference trainer (bench.py --impl reference: load + init once, then time epochs) ----
+struct RefTrainer {
+   int model;
+   ProbeE* e;
+   ProbeH* h;
+   ProbeR* r;
+};
+
+struct EpochsE : ProbeE { using ProbeE::ProbeE; void epochs(int n) { maxEpochs_ = n; bfgs(); } };
+struct EpochsH : ProbeH { using ProbeH::ProbeH; void epochs(int n) { maxEpochs_ = n; bfgs(); } };
+struct EpochsR : ProbeR { using ProbeR::ProbeR; void epochs(int n) { maxEpochs_ = n; bfgs(); } };
+
+void* ref_trainer_create(int model, const char* datadir, const char* outdir, int D, double lr, double margin,
+                         int method, int distance, int batches, unsigned seed, const char* seeddir, int seedmethod,
+                         int zero_work) {
+   common::EmbeddingArguments a = makeArgs(D, lr, margin, method, distance, batches, 1);
+   a.dataDir = datadir;
+   a.outputDir = outdir;
+   a.seedDataDir = seeddir ? seeddir : ".";
+   a.seedMethod = seedmethod;
+   a.seed = seed;
+   srand(seed);
+   RefTrainer* t = new RefTrainer();
+   t->model = model;
+   t->e = NULL; t->h = NULL; t->r = NULL;
+   if (model == 0) { t->e = new EpochsE(a); t->e->loadFiles(); t->e->prep(); }
+   else if (model == 1) { t->h = new EpochsH(a); t->h->loadFiles(); t->h->prep(); }
+   else { t->r = new EpochsR(a, zero_work != 0); t->r->loadFiles(); t->r->prep(); }
+   fflush(stdout);
+   return t;
+}
+
+// Runs n more epochs of the reference's bfgs() (the printed epoch index restarts at 0 every call);
+// returns the wall seconds spent inside bfgs().
+double ref_trainer_epochs(void* handle, int n) {
+   RefTrainer* t = (RefTrainer*)handle;
+   auto t0 = std::chrono::steady_clock::now();
+   if (t->model == 0) static_cast<EpochsE*>(t->e)->epochs(n);
+   else if (t->model == 1) static_cast<EpochsH*>(t->h)->epochs(n);
+   else static_cast<EpochsR*>(t->r)->epochs(n);
+   auto t1 = std::chrono::steady_clock::now();
+   fflush(stdout);
+   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+void ref_trainer_write(void* handle) {
+   RefTrainer* t = (RefTrainer*)handle;
+   if (t->model == 0) t->e->write(); else if (t->model == 1) t->h->write(); else t->r->write();
+}
+
+void ref_trainer_destroy(void* handle) {
+   RefTrainer* t = (RefTrainer*)handle;
+   delete t->e; delete t->h; delete t->r;
+   delete t;
+}
+
 }  // extern "C"

@@ -68,9 +68,8 @@ def test_scores_match_reference(gpu_lib, golden, ci):
         tri = g["pairs"][:, :3]
         e64 = ctx.score(tri, precision=1)
         assert np.array_equal(e64, g["energy"])
-        if g["model"] != 2:
-            e32 = ctx.score(tri, precision=0)
-            assert np.allclose(e32, g["energy"], rtol=1e-5, atol=1e-6)
+        e32 = ctx.score(tri, precision=0)
+        assert np.allclose(e32, g["energy"], rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("ci", [0, 1, 2, 3, 4, 5])
@@ -107,7 +106,8 @@ def reference_free_oracle(oracle):
     return oracle
 
 
-@pytest.mark.parametrize("model,dist,D", [(0, 0, 50), (0, 1, 100), (0, 0, 20), (0, 1, 200), (1, 0, 100), (1, 0, 20)])
+@pytest.mark.parametrize("model,dist,D", [(0, 0, 50), (0, 1, 100), (0, 0, 20), (0, 1, 200), (1, 0, 100), (1, 0, 20),
+                                          (2, 0, 50), (2, 1, 20)])
 def test_batch_matches_deferred_oracle(gpu_lib, oracle, model, dist, D):
     """One batch of 1500 sampled pairs: GPU tables == orc_train_batch_dfr (fp64) on the same pairs.
     fp32 rounding can flip an L1 sign or a hinge decision for a residual within ~1e-7 of zero, so a
@@ -122,6 +122,12 @@ def test_batch_matches_deferred_oracle(gpu_lib, oracle, model, dist, D):
     if model == 1:
         w = rng.normal(0, 1, (nR, D))
         w /= np.linalg.norm(w, axis=1, keepdims=True)
+    if model == 2:
+        # TransR state as training keeps it: unit entity / relation rows, unit rows of M_r near identity
+        ent /= np.linalg.norm(ent, axis=1, keepdims=True)
+        rel /= np.linalg.norm(rel, axis=1, keepdims=True)
+        w = np.tile(np.eye(D), (nR, 1, 1)) + rng.normal(0, 0.02, (nR, D, D))
+        w /= np.linalg.norm(w, axis=2, keepdims=True)
     ent, rel, w = f32(ent), f32(rel), f32(w)
     smp = oracle.sampler(g["train"], nE, nR, 1)
     pairs = smp.sample_batch(99, 0, 1500)
@@ -137,7 +143,9 @@ def test_batch_matches_deferred_oracle(gpu_lib, oracle, model, dist, D):
     assert abs(active - oactive) <= 2
     assert abs(loss - oloss) <= 2e-5 * abs(oloss) + 4 * 1.0 * abs(active - oactive)
     assert st["samples"] == 1500 and st["active"] == active
-    for got, want in ((ge, oe), (gr, orl)) + (((gw, ow),) if model == 1 else ()):
+    if model == 2:
+        gw, ow = gw.reshape(ow.shape), ow
+    for got, want in ((ge, oe), (gr, orl)) + (((gw, ow),) if model != 0 else ()):
         diff = np.abs(got - want)
         assert (diff > 3e-6).mean() < 1e-2, (diff > 3e-6).mean()
         assert diff.max() <= 8 * LR
