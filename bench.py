@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- the KB2E hot path on B200: margin-ranking SGD epochs + filtered link-prediction ranking.
+
+Workload (BASELINE.json configs[1]): TransE, bern, squared-L2, size=100, rate=0.01, margin=1,
+batches=100 on a synthetic planted-translation KG of FB15k shape (14,951 entities / 1,345 relations /
+483,142 train / 50,000 valid / 59,071 test), then filtered MeanRank / Hits@10 over the 59,071 test
+triples (118,142 queries x 14,951 candidates).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A training "step" is one epoch (100 batches x 4,831 sampled (positive, negative) pairs); the
+headline `value` is training pairs ("triples") per second with everything resident in HBM, timed
+per step with CUDA events on the launching stream, L2 flushed before every step, max over ranks.
+`e2e` is the same epoch through the C ABI with HOST buffers: triples and fp64 tables copied in from
+pinned host memory, fp64 tables copied back.  The ranking pass is reported in the `eval` block of the
+same JSON line with its own value / e2e / roofline / cpu_baseline.
+
+Multi-GPU (--gpus N under torchrun): training at FB15k shape does not shard ("replicas only",
+DESIGN.md): every rank trains its own replica (different -seed), value = N x pairs / max time.
+Ranking shards the test triples across ranks (tables + filter replicated) and all-reduces the four
+int64 sums over NCCL.
+
+--impl reference times the UNMODIFIED reference (oracle/_ref, compiled from /root/reference by
+oracle/Makefile) on the host cores of this box: one epoch of its bfgs() per step; evalCorruption on
+a bounded sample of the queries.  The reference is single-threaded.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(model="transe", dim=100, method=1, distance=1, rate=0.01, margin=1.0, batches=100, shape="fb15k")
+WORKLOAD = "TransE bern L2 size=100 rate=0.01 margin=1 batches=100, synthetic FB15k-shape KG (14951/1345/483142/50000/59071) + filtered ranking of 59071 test triples"
+HBM_FALLBACK_GBS = 6650.0
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8:
+                self.rows.append(f)
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        busy = [x for x in sm if x > 0.5 * float(self.rows[0][2])] or sm
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[4 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": reasons, "samples": len(self.rows)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def algorithmic_bytes(n_pairs, active, touched_rows, dim, rows_per_pair=4):
+    """per pair (rows + 2*rows*alpha) * D * 4 + 12 bytes, plus 3*U*D*4 for the publish."""
+    alpha = active / max(n_pairs, 1)
+    return n_pairs * ((rows_per_pair + 2 * rows_per_pair * alpha) * dim * 4 + 12) + 3 * touched_rows * dim * 4, alpha
+
+
+# ------------------------------------------------------------------------------------------ product arm
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+
+    import kb2e_b200
+    from kb2e_b200 import kg, TABLE_ENTITY, TABLE_RELATION
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, peak_src = peaks()
+    nE, nR, n_train, n_valid, n_test, _ = kg.SHAPES[CFG["shape"]]
+
+    # ---- synthetic KG: generated on rank 0 (torch on the GPU for the exact nearest neighbours), broadcast
+    if rank == 0:
+        g = kg.make_kg(CFG["shape"], seed=0)
+        blob = torch.from_numpy(np.concatenate([g["train"], g["valid"], g["test"]]).astype(np.int32)).cuda()
+    else:
+        blob = torch.empty((n_train + n_valid + n_test, 3), dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.broadcast(blob, 0)
+    allt = blob.cpu().numpy()
+    train, valid, test = allt[:n_train], allt[n_train:n_train + n_valid], allt[n_train + n_valid:]
+    head_mean, tail_mean = kg.bern_stats(train, nR)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(a):
+        if world == 1:
+            return a
+        t = torch.from_numpy(np.asarray(a, dtype=np.int64)).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    ctx = kb2e_b200.Context(CFG["model"], CFG["dim"], nE, nR, method=CFG["method"], distance=CFG["distance"],
+                            batches=CFG["batches"], rate=CFG["rate"], margin=CFG["margin"], seed=1 + rank, device=local)
+    ctx.set_train_triples(train)
+    ctx.set_bern(head_mean, tail_mean)
+    ctx.init_embeddings()
+    pairs_per_step = CFG["batches"] * (n_train // CFG["batches"])
+    K, W = args.steps, args.warmup
+
+    clocks = ClockSampler(local)
+    with clocks:
+        # ---- training, device-resident -------------------------------------------------------------
+        for e in range(W):
+            ctx.train_epochs(e, 1)
+        s0 = ctx.train_stats()
+        step_ms, wall_ms = [], []
+        for e in range(W, W + K):
+            flush.fill_(1)          # L2 flush between timed steps
+            barrier()
+            t0 = time.perf_counter()
+            before = ctx.train_stats()["kernel_ms"]
+            ctx.train_epochs(e, 1)  # one persistent launch = 100 batches; events on the launching stream inside
+            torch.cuda.synchronize()
+            wall_ms.append((time.perf_counter() - t0) * 1e3)
+            step_ms.append(max_over_ranks(ctx.train_stats()["kernel_ms"] - before))
+        s1 = ctx.train_stats()
+        total_ms = sum(step_ms)
+        value = world * pairs_per_step * K / (total_ms * 1e-3)
+        n_pairs = s1["samples"] - s0["samples"]
+        touched = (s1["touched_ent"] - s0["touched_ent"]) + (s1["touched_rel"] - s0["touched_rel"])
+        abytes, alpha = algorithmic_bytes(n_pairs, s1["active"] - s0["active"], touched, CFG["dim"])
+        launches = int(s1["launches"] - s0["launches"])
+        local_kernel_ms = s1["kernel_ms"] - s0["kernel_ms"]
+        achieved = abytes / (local_kernel_ms * 1e-3) / 1e9
+
+        # ---- training, end to end through the C ABI with host buffers ---------------------------------
+        def pinned(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return t, t.numpy()
+
+        ent_host = ctx.download(TABLE_ENTITY)
+        rel_host = ctx.download(TABLE_RELATION)
+        keep = [pinned(train[:, 0]), pinned(train[:, 1]), pinned(train[:, 2]), pinned(ent_host), pinned(rel_host),
+                pinned(head_mean), pinned(tail_mean), pinned(np.empty_like(ent_host)), pinned(np.empty_like(rel_host))]
+        p_h, p_t, p_r, p_ent, p_rel, p_hm, p_tm, o_ent, o_rel = (k[1] for k in keep)
+        p_train = (p_h, p_t, p_r)
+        e2e_ms = []
+        with kb2e_b200.Context(CFG["model"], CFG["dim"], nE, nR, method=CFG["method"], distance=CFG["distance"],
+                               batches=CFG["batches"], rate=CFG["rate"], margin=CFG["margin"], seed=101 + rank, device=local) as c2:
+            for it in range(2 + K):
+                barrier()
+                t0 = time.perf_counter()
+                c2.set_train_triples(p_train)           # H2D: triples (+ device hash-set build)
+                c2.set_bern(p_hm, p_tm)                 # H2D: corruption probabilities
+                c2.upload(TABLE_ENTITY, p_ent)          # H2D: fp64 tables
+                c2.upload(TABLE_RELATION, p_rel)
+                loss = c2.train_epochs(it, 1)           # D2H: epoch loss
+                out_e = c2.download(TABLE_ENTITY, out=o_ent)    # D2H: fp64 tables
+                out_r = c2.download(TABLE_RELATION, out=o_rel)
+                dt = (time.perf_counter() - t0) * 1e3
+                if it >= 2:
+                    e2e_ms.append(max_over_ranks(dt))
+        h2d = int(p_h.nbytes * 3 + p_ent.nbytes + p_rel.nbytes + p_hm.nbytes + p_tm.nbytes)
+        d2h = int(out_e.nbytes + out_r.nbytes + 8)
+        e2e_value = world * pairs_per_step * K / (sum(e2e_ms) * 1e-3)
+
+        # ---- filtered ranking: test triples sharded over ranks ------------------------------------------
+        # every rank ranks with rank 0's trained tables
+        ent_t = torch.from_numpy(ctx.download(TABLE_ENTITY)).cuda()
+        rel_t = torch.from_numpy(ctx.download(TABLE_RELATION)).cuda()
+        if world > 1:
+            dist.broadcast(ent_t, 0)
+            dist.broadcast(rel_t, 0)
+        ent_eval, rel_eval = np.round(ent_t.cpu().numpy(), 6), np.round(rel_t.cpu().numpy(), 6)  # what "%.6lf" files hold
+        lo = n_test * rank // world
+        hi = n_test * (rank + 1) // world
+        ev = kb2e_b200.Context(CFG["model"], CFG["dim"], nE, nR, method=CFG["method"], distance=CFG["distance"], device=local)
+        ev.upload(TABLE_ENTITY, ent_eval)
+        ev.upload(TABLE_RELATION, rel_eval)
+        ev.set_test_triples(test)
+        ev.add_filter_triples(train)
+        ev.add_filter_triples(valid)
+        KE, WE = max(1, min(K, 3)), max(1, min(W, 2))
+        for _ in range(WE):
+            ev.rank(lo, hi - lo, want_ranks=False)
+        r0 = ev.rank_stats()
+        ev_ms = []
+        for _ in range(KE):
+            flush.fill_(1)
+            barrier()
+            before = ev.rank_stats()["kernel_ms"]
+            res = ev.rank(lo, hi - lo, want_ranks=False)
+            ev_ms.append(max_over_ranks(ev.rank_stats()["kernel_ms"] - before))
+        r1 = ev.rank_stats()
+        sums = sum_over_ranks(res["sums"])
+        nq = 2 * n_test
+        ev_value = nq * KE / (sum(ev_ms) * 1e-3)
+        main_ms = (r1["main_kernel_ms"] - r0["main_kernel_ms"]) / KE
+        # end to end: host tables + host triples in, per-query ranks out
+        filt_all = np.concatenate([train, valid])
+        keep2 = [pinned(test[:, k]) for k in range(3)] + [pinned(filt_all[:, k]) for k in range(3)] + \
+                [pinned(ent_eval), pinned(rel_eval)] + [pinned(np.empty(2 * (hi - lo), dtype=np.int32)) for _ in range(4)]
+        p_test = tuple(k[1] for k in keep2[0:3])
+        p_filt = tuple(k[1] for k in keep2[3:6])
+        p_ee, p_re = keep2[6][1], keep2[7][1]
+        p_out = [k[1] for k in keep2[8:12]]
+        ev_e2e = []
+        for it in range(1 + KE):
+            barrier()
+            t0 = time.perf_counter()
+            with kb2e_b200.Context(CFG["model"], CFG["dim"], nE, nR, method=CFG["method"], distance=CFG["distance"], device=local) as e2:
+                e2.upload(TABLE_ENTITY, p_ee)
+                e2.upload(TABLE_RELATION, p_re)
+                e2.set_test_triples(p_test)
+                e2.add_filter_triples(p_filt)
+                full = e2.rank(lo, hi - lo, out=p_out)
+            dt = (time.perf_counter() - t0) * 1e3
+            if it >= 1:
+                ev_e2e.append(max_over_ranks(dt))
+        ev_e2e_value = nq * KE / (sum(ev_e2e) * 1e-3)
+        ev_h2d = int(ent_eval.nbytes + rel_eval.nbytes + 3 * p_test[0].nbytes + 3 * p_filt[0].nbytes)
+        ev_d2h = int(4 * 4 * 2 * (hi - lo) + 32)
+        ev_launches = int(r1["launches"] - r0["launches"])
+    clk = clocks.summary()
+
+    if rank != 0:
+        ctx.close(); ev.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference itself on this box's host cores --------------
+    cpu_train = cpu_eval = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_train, cpu_eval = reference_sample(train, valid, test, nE, nR, ent_eval, rel_eval, train_epochs=1, eval_triples=100)
+
+    ranking_flops = 2.0 * nq * nE * CFG["dim"]
+    traffic = profile_traffic("train")
+    line = {
+        "metric": "train_triples_per_s", "value": value, "unit": "triples/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "kb2e_b200",
+        "config": {"workload": WORKLOAD, "step": "one epoch = 100 batches x 4831 sampled (positive, negative) pairs",
+                   "parallelism": "replicas only (training), test triples sharded (ranking)" if world > 1 else "single GPU",
+                   "l2": "flushed before every timed step (256 MiB write); the 13 MB of tables are L2-resident within a step by nature of the workload",
+                   "timing": "CUDA events on the launching stream around each persistent launch, max over ranks"},
+        "wall_ms_per_step": sum(wall_ms) / K,
+        "gpu_launches": launches + ev_launches,
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": sum(e2e_ms) / K,
+                "what": "kb2e_set_train_triples + kb2e_set_bern + kb2e_upload x2 + kb2e_train_epochs(1) + kb2e_download x2, pinned host buffers"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "kb2e::train_kernel<TransE,16,2,768>",
+                     "alpha": alpha, "touched_rows_per_batch": touched / (K * CFG["batches"]),
+                     "algorithmic_bytes_per_launch": abytes / max(launches, 1),
+                     "note": "algorithmic bytes (SURVEY 8d) / CUDA-event time of the persistent launch; tables are L2-resident, so DRAM traffic is far below the algorithmic bytes"},
+        "cpu_baseline": cpu_train,
+        "eval": {
+            "metric": "eval_queries_per_s", "value": ev_value, "unit": "queries/s", "ms_per_step": sum(ev_ms) / KE, "steps": KE,
+            "queries_per_step": nq, "candidates": nE, "scaling": "strong",
+            "raw_mean_rank": float(sums[0]) / nq, "filtered_mean_rank": float(sums[1]) / nq,
+            "raw_hits10": float(sums[2]) / nq, "filtered_hits10": float(sums[3]) / nq,
+            "e2e": {"value": ev_e2e_value, "unit": "queries/s", "h2d_bytes_per_step": ev_h2d, "d2h_bytes_per_step": ev_d2h,
+                    "what": "kb2e_create + kb2e_upload x2 + set_test/add_filter + kb2e_rank with per-query ranks copied back"},
+            "roofline": {"bound": "fp64 CUDA cores (exact reference-order scoring; not a tensor-core kernel yet)",
+                         "achieved": ranking_flops / (main_ms * 1e-3) / 1e12, "unit": "TFLOP/s (2*Q*N*D)",
+                         "main_kernel_ms": main_ms, "kernel": "kb2e::rank_exact_kernel<L2>"},
+            "cpu_baseline": cpu_eval,
+        },
+    }
+    print(json.dumps(line))
+    ctx.close(); ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_traffic(which):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one matches."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(which)
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def reference_sample(train, valid, test, nE, nR, ent_eval, rel_eval, train_epochs, eval_triples, steps=1, warmup=0):
+    """Times the unmodified reference (oracle/_ref) on this box: `train_epochs` epochs of bfgs() per step and
+    evalCorruption over the first `eval_triples` test triples.  Returns (train block, eval block)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from kb2e_oracle import Reference, ReferenceTrainer
+    from kb2e_b200 import kg
+
+    if not Reference.available():
+        return ({"unavailable": "oracle/_ref/libkb2e_ref.so not built"}, None)
+    ref = Reference()
+    tmp = tempfile.mkdtemp(prefix="kb2e_bench_")
+    try:
+        kg.write_kg({"nE": nE, "nR": nR, "train": train, "valid": valid, "test": test}, tmp)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)  # the reference prints its per-epoch line; keep the JSON line clean
+        try:
+            tr = ReferenceTrainer(ref, 0, tmp, tmp, CFG["dim"], CFG["rate"], CFG["margin"], CFG["method"], CFG["distance"],
+                                  CFG["batches"], 1)
+            secs = []
+            for it in range(warmup + steps):
+                s = tr.epochs(train_epochs)
+                if it >= warmup:
+                    secs.append(s)
+            tr.close()
+        finally:
+            os.dup2(saved, 1)
+            os.close(devnull)
+        pairs = train_epochs * CFG["batches"] * (len(train) // CFG["batches"])
+        train_block = {"value": pairs * len(secs) / sum(secs), "unit": "triples/s", "cores": 1, "kind": "reference",
+                       "sample": f"{train_epochs} epoch(s) of the reference's own bfgs() per step ({pairs} pairs), load/init/write excluded; single-threaded program",
+                       "seconds_per_step": sum(secs) / len(secs), "step_seconds": secs}
+        t0 = time.perf_counter()
+        ref.rank(0, CFG["distance"], ent_eval, rel_eval, None, test[:eval_triples], np.concatenate([train, valid]))
+        dt = time.perf_counter() - t0
+        eval_block = {"value": 2 * eval_triples / dt, "unit": "queries/s", "cores": 1, "kind": "reference",
+                      "sample": f"evalCorruption on the first {eval_triples} test triples ({2 * eval_triples} queries x {nE} candidates), "
+                                "including building its filter map; the N_R x N_E^2 cache reset of run() is NOT included (it would add about 0.5 s per relation)",
+                      "seconds": dt}
+        return train_block, eval_block
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return  # the reference is a single-process CPU program: rank 0 alone runs it
+    from kb2e_b200 import kg
+    nE, nR, n_train, n_valid, n_test, _ = kg.SHAPES[CFG["shape"]]
+    g = kg.make_kg(CFG["shape"], seed=0)
+    rng = np.random.default_rng(0)
+    # the ranking sample needs tables; random N(0, 1/D) rows rounded like the "%.6lf" files are enough for timing
+    ent = np.round(rng.normal(0, 1.0 / CFG["dim"], (nE, CFG["dim"])), 6)
+    rel = np.round(rng.normal(0, 1.0 / CFG["dim"], (nR, CFG["dim"])), 6)
+    tb, eb = reference_sample(g["train"], g["valid"], g["test"], nE, nR, ent, rel, train_epochs=1, eval_triples=100,
+                              steps=args.steps, warmup=args.warmup)
+    if "unavailable" in tb:
+        print(json.dumps({"impl": "reference", "unavailable": tb["unavailable"]}))
+        return
+    line = {
+        "metric": "train_triples_per_s", "value": tb["value"], "unit": "triples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": tb["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": WORKLOAD, "step": "one epoch of the reference's bfgs() = 100 batches x 4831 pairs, on the host CPU"},
+        "cpu_baseline": {k: tb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": tb["value"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "eval": {"metric": "eval_queries_per_s", "value": eb["value"], "unit": "queries/s", "cpu_baseline": eb,
+                 "e2e": {"value": eb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kb2e_b200", choices=["kb2e_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3  # timing rule: at least 3 warm-up steps
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

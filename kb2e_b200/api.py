@@ -71,6 +71,16 @@ def _p(a, t):
     return None if a is None else a.ctypes.data_as(C.POINTER(t))
 
 
+def _columns(triples):
+    """(n, 3) array of (head, tail, relation) -> three contiguous int32 columns; a tuple/list of three
+    int32 arrays is passed through untouched (so callers can hand over pinned host buffers)."""
+    if isinstance(triples, (tuple, list)) and len(triples) == 3 and all(isinstance(x, np.ndarray) for x in triples):
+        h, t, r = (_i32(x) for x in triples)
+        return h, t, r, len(h)
+    tr = _i32(triples).reshape(-1, 3)
+    return _i32(tr[:, 0]), _i32(tr[:, 1]), _i32(tr[:, 2]), len(tr)
+
+
 class Context:
     """One kb2e_ctx: one model instance on one GPU."""
 
@@ -122,11 +132,10 @@ class Context:
 
     # ---- training ----
     def set_train_triples(self, triples):
-        """triples: (n, 3) ints (head, tail, relation)."""
-        tr = _i32(triples).reshape(-1, 3)
-        h, t, r = (_i32(tr[:, k]) for k in range(3))
+        """triples: (n, 3) ints (head, tail, relation), or a tuple of three int32 arrays."""
+        h, t, r, n = _columns(triples)
         self._check(self.lib.kb2e_set_train_triples(self.ptr, _p(h, C.c_int32), _p(t, C.c_int32), _p(r, C.c_int32),
-                                                    C.c_int64(len(tr))), "kb2e_set_train_triples")
+                                                    C.c_int64(n)), "kb2e_set_train_triples")
 
     def set_bern(self, head_mean=None, tail_mean=None):
         hm = None if head_mean is None else np.ascontiguousarray(head_mean, dtype=np.float64)
@@ -143,9 +152,11 @@ class Context:
         self._check(self.lib.kb2e_upload(self.ptr, int(table), _p(a, C.c_double), C.c_int64(rows), C.c_int64(cols)),
                     "kb2e_upload")
 
-    def download(self, table):
+    def download(self, table, out=None):
         rows, cols = self.table_shape(table)
-        out = np.empty((rows, cols), dtype=np.float64)
+        if out is None:
+            out = np.empty((rows, cols), dtype=np.float64)
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == rows * cols
         self._check(self.lib.kb2e_download(self.ptr, int(table), _p(out, C.c_double), C.c_int64(rows), C.c_int64(cols)),
                     "kb2e_download")
         return out
@@ -163,34 +174,34 @@ class Context:
 
     # ---- scoring / ranking ----
     def score(self, triples, precision=1):
-        tr = _i32(triples).reshape(-1, 3)
-        h, t, r = (_i32(tr[:, k]) for k in range(3))
-        out = np.empty(len(tr), dtype=np.float64)
-        self._check(self.lib.kb2e_score(self.ptr, _p(h, C.c_int32), _p(t, C.c_int32), _p(r, C.c_int32), C.c_int64(len(tr)),
+        h, t, r, n = _columns(triples)
+        out = np.empty(n, dtype=np.float64)
+        self._check(self.lib.kb2e_score(self.ptr, _p(h, C.c_int32), _p(t, C.c_int32), _p(r, C.c_int32), C.c_int64(n),
                                         int(precision), _p(out, C.c_double)), "kb2e_score")
         return out
 
     def set_test_triples(self, triples):
-        tr = _i32(triples).reshape(-1, 3)
-        h, t, r = (_i32(tr[:, k]) for k in range(3))
-        self.n_test = len(tr)
+        h, t, r, n = _columns(triples)
+        self.n_test = n
         self._check(self.lib.kb2e_set_test_triples(self.ptr, _p(h, C.c_int32), _p(t, C.c_int32), _p(r, C.c_int32),
-                                                   C.c_int64(len(tr))), "kb2e_set_test_triples")
+                                                   C.c_int64(n)), "kb2e_set_test_triples")
 
     def add_filter_triples(self, triples):
-        tr = _i32(triples).reshape(-1, 3)
-        h, t, r = (_i32(tr[:, k]) for k in range(3))
+        h, t, r, n = _columns(triples)
+        if n == 0:
+            return
         self._check(self.lib.kb2e_add_filter_triples(self.ptr, _p(h, C.c_int32), _p(t, C.c_int32), _p(r, C.c_int32),
-                                                     C.c_int64(len(tr))), "kb2e_add_filter_triples")
+                                                     C.c_int64(n)), "kb2e_add_filter_triples")
 
     def clear_filter_triples(self):
         self._check(self.lib.kb2e_add_filter_triples(self.ptr, None, None, None, C.c_int64(0)), "kb2e_add_filter_triples")
 
-    def rank(self, first=0, count=None, want_ranks=True):
-        """Returns dict(raw, filt, raw_ties, filt_ties, sums) for test triples [first, first+count)."""
+    def rank(self, first=0, count=None, want_ranks=True, out=None):
+        """Returns dict(raw, filt, raw_ties, filt_ties, sums) for test triples [first, first+count).
+        out: optional list of four int32 arrays (2*count each) to receive the per-query results."""
         if count is None:
             count = self.n_test - first
-        outs = [np.empty(2 * count, dtype=np.int32) if want_ranks else None for _ in range(4)]
+        outs = out if out is not None else [np.empty(2 * count, dtype=np.int32) if want_ranks else None for _ in range(4)]
         sums = np.zeros(4, dtype=np.int64)
         self._check(self.lib.kb2e_rank(self.ptr, C.c_int64(first), C.c_int64(count), *[_p(o, C.c_int32) for o in outs],
                                        _p(sums, C.c_int64)), "kb2e_rank")
