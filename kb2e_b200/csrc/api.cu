@@ -128,36 +128,30 @@ int kb2e_init_embeddings(kb2e_ctx* c) {
    return train_init_embeddings(c);
 }
 
-static int table_shape(kb2e_ctx* c, int table, int64_t& rows, int64_t& cols, double*& dev64) {
+static int table_shape(kb2e_ctx* c, int table, int64_t& rows, int64_t& cols) {
    cols = c->D;
-   if (table == KB2E_TABLE_ENTITY) { rows = c->nE; dev64 = c->ent64; return KB2E_OK; }
-   if (table == KB2E_TABLE_RELATION) { rows = c->nR; dev64 = c->rel64; return KB2E_OK; }
-   if (table == KB2E_TABLE_WEIGHTS && c->cfg.model == KB2E_MODEL_TRANSH) { rows = c->nR; dev64 = c->w64; return KB2E_OK; }
-   if (table == KB2E_TABLE_WEIGHTS && c->cfg.model == KB2E_MODEL_TRANSR) { rows = (int64_t)c->nR * c->D; dev64 = c->w64; return KB2E_OK; }
+   if (table == KB2E_TABLE_ENTITY) { rows = c->nE; return KB2E_OK; }
+   if (table == KB2E_TABLE_RELATION) { rows = c->nR; return KB2E_OK; }
+   if (table == KB2E_TABLE_WEIGHTS && c->cfg.model == KB2E_MODEL_TRANSH) { rows = c->nR; return KB2E_OK; }
+   if (table == KB2E_TABLE_WEIGHTS && c->cfg.model == KB2E_MODEL_TRANSR) { rows = (int64_t)c->nR * c->D; return KB2E_OK; }
    return fail(c, KB2E_ERR_ARG, "unknown table for this model");
 }
 
 int kb2e_upload(kb2e_ctx* c, int table, const double* host, int64_t rows, int64_t cols) {
    KB2E_ENTER(c);
    if (!host) return fail(c, KB2E_ERR_ARG, "kb2e_upload: null buffer");
-   int rc = train_alloc(c);
-   if (rc) return rc;
-   // make sure the fp64 mirror exists and is current for the tables NOT being replaced
-   if (!c->have64) {
-      if (!c->have32) {
-         // nothing yet: start from zeros
-         c->have32 = true;
-      }
-      rc = tables_32_to_64(c);
-      if (rc) return rc;
-   }
    int64_t er, ec;
-   double* dev = nullptr;
-   rc = table_shape(c, table, er, ec, dev);
+   int rc = table_shape(c, table, er, ec);
    if (rc) return rc;
    if (rows != er || cols != ec) return fail(c, KB2E_ERR_ARG, "kb2e_upload: shape mismatch");
+   rc = train_alloc(c);
+   if (rc) return rc;
+   double* dev = table64(c, table);
+   if (!dev) return fail(c, KB2E_ERR_CUDA, "kb2e_upload: out of device memory");
+   // the exact fp64 values stay on the device for ranking; training gets the fp32 rounding of them
    KB2E_CUDA(c, cudaMemcpyAsync(dev, host, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-   rc = tables_64_to_32(c);
+   c->v64[table] = true;
+   rc = narrow_table(c, table);
    if (rc) return rc;
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
    return KB2E_OK;
@@ -166,14 +160,15 @@ int kb2e_upload(kb2e_ctx* c, int table, const double* host, int64_t rows, int64_
 int kb2e_download(kb2e_ctx* c, int table, double* host, int64_t rows, int64_t cols) {
    KB2E_ENTER(c);
    if (!host) return fail(c, KB2E_ERR_ARG, "kb2e_download: null buffer");
-   int rc = tables_32_to_64(c);
-   if (rc) return rc;
    int64_t er, ec;
-   double* dev = nullptr;
-   rc = table_shape(c, table, er, ec, dev);
+   int rc = table_shape(c, table, er, ec);
    if (rc) return rc;
    if (rows != er || cols != ec) return fail(c, KB2E_ERR_ARG, "kb2e_download: shape mismatch");
-   KB2E_CUDA(c, cudaMemcpyAsync(host, dev, (size_t)rows * cols * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   if (!c->v64[table]) {
+      rc = widen_table(c, table);
+      if (rc) return rc;
+   }
+   KB2E_CUDA(c, cudaMemcpyAsync(host, table64(c, table), (size_t)rows * cols * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
    return KB2E_OK;
 }
@@ -265,7 +260,6 @@ int kb2e_add_filter_triples(kb2e_ctx* c, const int32_t* h, const int32_t* t, con
 int kb2e_rank(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32_t* filt_rank,
               int32_t* raw_ties, int32_t* filt_ties, int64_t sums[4]) {
    KB2E_ENTER(c);
-   if (!c->have32 && !c->have64) return fail(c, KB2E_ERR_ARG, "kb2e_rank: no embeddings uploaded");
    return rank_run(c, first, count, raw_rank, filt_rank, raw_ties, filt_ties, sums);
 }
 

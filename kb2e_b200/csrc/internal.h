@@ -32,10 +32,13 @@ struct kb2e_ctx {
    uint8_t* flag = nullptr;    // [nE + nR] row touched in the current batch
    int* rmin = nullptr;        // [nE] lowest / highest relation id that touched the entity row (TransH/R)
    int* rmax = nullptr;
-   bool have32 = false;        // fp32 tables hold the current parameters
+   bool v32[3] = {false, false, false};  // per table (entity, relation, weights): fp32 copy is current
 
    // ---- training set ---------------------------------------------------------------------------
    int4* triples = nullptr;    // (h, t, r, 0)
+   int32_t* stage = nullptr;   // H2D staging of the three id columns
+   int64_t triples_cap = 0;
+   uint64_t hash_cap = 0;
    int64_t n_train = 0;
    uint64_t* hash = nullptr;   // open-addressing set of packed (h, r, t)
    uint64_t hash_mask = 0;
@@ -56,7 +59,7 @@ struct kb2e_ctx {
    double* ent64 = nullptr;  // [nE][D]
    double* rel64 = nullptr;  // [nR][D]
    double* w64 = nullptr;    // TransH [nR][D]; TransR [nR][D][D]
-   bool have64 = false;
+   bool v64[3] = {false, false, false};  // per table: fp64 copy is current
 
    // ---- evaluation set -------------------------------------------------------------------------
    std::vector<int32_t> test_h, test_t, test_r;
@@ -85,8 +88,12 @@ int train_init_embeddings(kb2e_ctx* ctx);
 int train_run(kb2e_ctx* ctx, int first_epoch, int n_epochs, const int32_t* pairs_dev, int64_t n_pairs, double* loss_out);
 int train_sample(kb2e_ctx* ctx, int epoch, int batch, int64_t count, int32_t* pairs_dev);
 int train_score32(kb2e_ctx* ctx, const int32_t* h_dev, const int32_t* t_dev, const int32_t* r_dev, int64_t n, double* out_dev);
-int tables_32_to_64(kb2e_ctx* ctx);
-int tables_64_to_32(kb2e_ctx* ctx);
+int num_tables(const kb2e_ctx* ctx);
+int widen_table(kb2e_ctx* ctx, int table);    // fp32 -> fp64 copy of one table
+int narrow_table(kb2e_ctx* ctx, int table);   // fp64 -> fp32
+int ensure32(kb2e_ctx* ctx);                  // every table of the model current in fp32 (training)
+int ensure64(kb2e_ctx* ctx);                  // ... in fp64 (ranking)
+double* table64(kb2e_ctx* ctx, int table);
 
 // rank.cu
 int rank_run(kb2e_ctx* ctx, int64_t first, int64_t count, int32_t* raw_rank, int32_t* filt_rank,

@@ -30,15 +30,21 @@
 #include <numeric>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 #include "internal.h"
+#include "rank_tc.h"
 
 struct RankState {
-   // filter CSR + hash
+   // filter set as a hashed CSR, built on the device: entries sorted by (segment key, neighbour);
+   // hash slot -> offset of the segment's first entry
    uint64_t* seg_key = nullptr;   // hash slots: key or kEmptyKey
-   uint2* seg_val = nullptr;      // (offset, count) per slot
-   int32_t* nbr = nullptr;        // neighbour entity ids
+   uint32_t* seg_val = nullptr;   // offset of the segment in ent_key / nbr
+   uint64_t* ent_key = nullptr;   // sorted segment keys, one per entry
+   int32_t* nbr = nullptr;        // neighbour entity ids, sorted within a segment (duplicates adjacent)
    uint64_t seg_mask = 0;
+   uint32_t n_ent = 0;
    // candidate matrices
    double* ct0 = nullptr;         // entity table transposed [D][ld]
    double* pt = nullptr;          // projected slots [slots][D][ld]
@@ -55,6 +61,7 @@ struct RankState {
    unsigned long long* sums = nullptr;
    int32_t* out = nullptr;        // 4 x cap results in original order
    cudaEvent_t m0 = nullptr, m1 = nullptr;
+   kb2e::TcState tc;
 };
 
 namespace kb2e {
@@ -147,9 +154,11 @@ struct RankArgs {
    int32_t* q_cnt;        // [4][nq]: less, eq, known_less, known_eq
    const int4* tiles;
    const uint64_t* seg_key;
-   const uint2* seg_val;
+   const uint32_t* seg_val;
+   const uint64_t* ent_key;
    const int32_t* nbr;
    uint64_t seg_mask;
+   uint32_t n_ent;
    long long nq;        // total queries of this call (row stride of q_cnt)
    long long q_begin;   // window of queries handled by etrue_kernel / filter_kernel
    long long q_end;
@@ -163,6 +172,32 @@ __global__ void etrue_kernel(const RankArgs a) {
    const double* ct = a.ct + (size_t)a.q_slot[q] * a.D * a.ld;
    const double* d = a.rel64 + (size_t)a.q_rel[q] * a.D;
    a.q_etrue[q] = exact_energy<L2>(ct, a.ld, a.D, a.q_fixed[q], a.q_truth[q], d, a.q_side[q] ? -1.0 : 1.0);
+}
+
+// Exact re-score of the (query, candidate) pairs the tensor-core pre-filter could not decide
+// (rank_tc.cu): same arithmetic and order as exact_energy, rows read from the row-major fp64 table.
+template <int L2>
+__global__ void recheck_kernel(const int2* __restrict__ band, unsigned int n, const double* __restrict__ ent64,
+                               const double* __restrict__ rel64, const int32_t* q_fixed, const int32_t* q_truth,
+                               const int32_t* q_rel, const int32_t* q_side, const double* q_etrue,
+                               int32_t* q_cnt, long long nq, int D) {
+   unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k >= n) return;
+   const int q = band[k].x, c = band[k].y;
+   if (c == q_truth[q]) return;
+   const double* v = ent64 + (size_t)q_fixed[q] * D;
+   const double* e = ent64 + (size_t)c * D;
+   const double* d = rel64 + (size_t)q_rel[q] * D;
+   const double dsign = q_side[q] ? -1.0 : 1.0;
+   double acc = 0.0;
+   for (int i = 0; i < D; i++) {
+      double u = __dsub_rn(v[i], e[i]);
+      double w = __dsub_rn(u, dsign * d[i]);
+      acc = L2 ? __dadd_rn(acc, __dmul_rn(w, w)) : __dadd_rn(acc, fabs(w));
+   }
+   const double et = q_etrue[q];
+   if (acc < et) atomicAdd(q_cnt + q, 1);
+   else if (acc == et) atomicAdd(q_cnt + nq + q, 1);
 }
 
 // ---- the all-candidates kernel ---------------------------------------------------------------------
@@ -257,6 +292,32 @@ __global__ void __launch_bounds__(kRankThreads) rank_exact_kernel(const RankArgs
    }
 }
 
+// ---- filter set construction (device) --------------------------------------------------------------
+// Every known triple (h, t, r) contributes two entries: head-corruption segment (0, r, t) -> h and
+// tail-corruption segment (1, r, h) -> t.
+__global__ void filter_entries_kernel(const int32_t* h, const int32_t* t, const int32_t* r, long long n,
+                                      uint64_t* key, int32_t* val) {
+   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   key[2 * i] = seg_key_of(0, r[i], t[i]);
+   val[2 * i] = h[i];
+   key[2 * i + 1] = seg_key_of(1, r[i], h[i]);
+   val[2 * i + 1] = t[i];
+}
+
+__global__ void segment_hash_kernel(const uint64_t* ent_key, uint32_t n, uint64_t* slots, uint32_t* vals, uint64_t mask) {
+   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   uint64_t k = ent_key[i];
+   if (i > 0 && ent_key[i - 1] == k) return;  // not the first entry of its segment
+   uint64_t p = mix64(k) & mask;
+   while (true) {
+      unsigned long long prev = atomicCAS((unsigned long long*)(slots + p), (unsigned long long)kEmptyKey, (unsigned long long)k);
+      if (prev == kEmptyKey) { vals[p] = i; return; }
+      p = (p + 1) & mask;
+   }
+}
+
 // ---- filter adjustment: one warp per query walks the known-true neighbours -------------------------
 template <int L2>
 __global__ void filter_kernel(const RankArgs a) {
@@ -266,10 +327,11 @@ __global__ void filter_kernel(const RankArgs a) {
    int side = a.q_side[q], rel = a.q_rel[q], fixed = a.q_fixed[q], truth = a.q_truth[q];
    uint64_t key = seg_key_of(side, rel, fixed);
    uint64_t slot = mix64(key) & a.seg_mask;
-   uint2 seg = make_uint2(0, 0);
+   uint32_t off = 0;
+   bool found = false;
    while (true) {
       uint64_t k = __ldg(a.seg_key + slot);
-      if (k == key) { seg = __ldg(a.seg_val + slot); break; }
+      if (k == key) { off = __ldg(a.seg_val + slot); found = true; break; }
       if (k == kEmptyKey) break;
       slot = (slot + 1) & a.seg_mask;
    }
@@ -277,12 +339,21 @@ __global__ void filter_kernel(const RankArgs a) {
    const double* d = a.rel64 + (size_t)rel * a.D;
    const double et = a.q_etrue[q];
    int less = 0, eq = 0;
-   for (uint32_t k = lane; k < seg.y; k += 32) {
-      int c = __ldg(a.nbr + seg.x + k);
-      if (c == truth) continue;
-      double e = exact_energy<L2>(ct, a.ld, a.D, fixed, c, d, side ? -1.0 : 1.0);
-      less += e < et;
-      eq += e == et;
+   if (found) {
+      for (uint32_t base = off; base < a.n_ent; base += 32) {
+         uint32_t k = base + lane;
+         bool mine = k < a.n_ent && __ldg(a.ent_key + k) == key;
+         if (mine) {
+            int c = __ldg(a.nbr + k);
+            bool dup = k > off && __ldg(a.nbr + k - 1) == c;  // the same triple listed twice (e.g. in train and valid)
+            if (c != truth && !dup) {
+               double e = exact_energy<L2>(ct, a.ld, a.D, fixed, c, d, side ? -1.0 : 1.0);
+               less += e < et;
+               eq += e == et;
+            }
+         }
+         if (!__all_sync(0xffffffffu, mine)) break;  // the segment ended inside this chunk
+      }
    }
 #pragma unroll
    for (int o = 16; o > 0; o >>= 1) {
@@ -347,49 +418,47 @@ static int ensure_state(kb2e_ctx* c) {
 static int build_filter(kb2e_ctx* c) {
    RankState* s = c->rank;
    if (!c->filter_dirty && s->seg_key) return KB2E_OK;
-   cudaFree(s->seg_key); cudaFree(s->seg_val); cudaFree(s->nbr);
-   s->seg_key = nullptr; s->seg_val = nullptr; s->nbr = nullptr;
-   // known triples = test + filter (common/evaluation.cpp:59-61); two CSRs in one key space
-   size_t n = c->test_h.size() + c->filt_h.size();
-   std::vector<std::pair<uint64_t, int32_t>> ent;
-   ent.reserve(2 * n);
-   auto add = [&](int32_t h, int32_t t, int32_t r) {
-      ent.emplace_back(seg_key_of(0, r, t), h);  // head corruption: fixed tail -> known heads
-      ent.emplace_back(seg_key_of(1, r, h), t);  // tail corruption: fixed head -> known tails
-   };
-   for (size_t i = 0; i < c->test_h.size(); i++) add(c->test_h[i], c->test_t[i], c->test_r[i]);
-   for (size_t i = 0; i < c->filt_h.size(); i++) add(c->filt_h[i], c->filt_t[i], c->filt_r[i]);
-   std::sort(ent.begin(), ent.end());
-   ent.erase(std::unique(ent.begin(), ent.end()), ent.end());
-   std::vector<int32_t> nbr(ent.size());
-   std::vector<uint64_t> keys;
-   std::vector<uint2> vals;
-   for (size_t i = 0; i < ent.size();) {
-      size_t j = i;
-      while (j < ent.size() && ent[j].first == ent[i].first) { nbr[j] = ent[j].second; j++; }
-      keys.push_back(ent[i].first);
-      vals.push_back(make_uint2((unsigned)i, (unsigned)(j - i)));
-      i = j;
-   }
+   cudaFree(s->seg_key); cudaFree(s->seg_val); cudaFree(s->nbr); cudaFree(s->ent_key);
+   s->seg_key = nullptr; s->seg_val = nullptr; s->nbr = nullptr; s->ent_key = nullptr;
+   // known triples = test + filter (common/evaluation.cpp:59-61)
+   const size_t nt = c->test_h.size(), nf = c->filt_h.size(), n = nt + nf;
+   if (2 * n >= (1ull << 32)) return fail(c, KB2E_ERR_LIMIT, "filter set larger than 2^31 triples");
+   s->n_ent = (uint32_t)(2 * n);
    uint64_t slots = 1024;
-   while (slots < 2 * keys.size()) slots <<= 1;
-   std::vector<uint64_t> hk(slots, kEmptyKey);
-   std::vector<uint2> hv(slots, make_uint2(0, 0));
-   for (size_t i = 0; i < keys.size(); i++) {
-      uint64_t p = mix64(keys[i]) & (slots - 1);
-      while (hk[p] != kEmptyKey) p = (p + 1) & (slots - 1);
-      hk[p] = keys[i];
-      hv[p] = vals[i];
-   }
+   while (slots < 4 * n) slots <<= 1;  // <= 2n segments, load <= 0.5
    s->seg_mask = slots - 1;
    KB2E_CUDA(c, cudaMalloc(&s->seg_key, slots * sizeof(uint64_t)));
-   KB2E_CUDA(c, cudaMalloc(&s->seg_val, slots * sizeof(uint2)));
-   KB2E_CUDA(c, cudaMalloc(&s->nbr, std::max<size_t>(1, nbr.size()) * sizeof(int32_t)));
-   KB2E_CUDA(c, cudaMemcpyAsync(s->seg_key, hk.data(), slots * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-   KB2E_CUDA(c, cudaMemcpyAsync(s->seg_val, hv.data(), slots * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
-   if (!nbr.empty())
-      KB2E_CUDA(c, cudaMemcpyAsync(s->nbr, nbr.data(), nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+   KB2E_CUDA(c, cudaMalloc(&s->seg_val, slots * sizeof(uint32_t)));
+   KB2E_CUDA(c, cudaMalloc(&s->ent_key, std::max<size_t>(1, 2 * n) * sizeof(uint64_t)));
+   KB2E_CUDA(c, cudaMalloc(&s->nbr, std::max<size_t>(1, 2 * n) * sizeof(int32_t)));
+   KB2E_CUDA(c, cudaMemsetAsync(s->seg_key, 0xff, slots * sizeof(uint64_t), c->stream));
+   if (n == 0) { c->filter_dirty = false; return KB2E_OK; }
+   int32_t* ids = nullptr;      // h | t | r columns of test then filter triples
+   uint64_t* key_tmp = nullptr;
+   int32_t* val_tmp = nullptr;
+   void* cub_tmp = nullptr;
+   KB2E_CUDA(c, cudaMalloc(&ids, 3 * n * sizeof(int32_t)));
+   KB2E_CUDA(c, cudaMalloc(&key_tmp, 2 * n * sizeof(uint64_t)));
+   KB2E_CUDA(c, cudaMalloc(&val_tmp, 2 * n * sizeof(int32_t)));
+   const std::vector<int32_t>* cols[3][2] = {{&c->test_h, &c->filt_h}, {&c->test_t, &c->filt_t}, {&c->test_r, &c->filt_r}};
+   for (int k = 0; k < 3; k++) {
+      if (nt) KB2E_CUDA(c, cudaMemcpyAsync(ids + k * n, cols[k][0]->data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+      if (nf) KB2E_CUDA(c, cudaMemcpyAsync(ids + k * n + nt, cols[k][1]->data(), nf * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+   }
+   filter_entries_kernel<<<nblk((long long)n, 256), 256, 0, c->stream>>>(ids, ids + n, ids + 2 * n, (long long)n, key_tmp, val_tmp);
+   // stable LSD radix sort: by neighbour (24 bits), then by segment key (41 bits) -> (key, neighbour) order
+   size_t bytes1 = 0, bytes2 = 0;
+   cub::DeviceRadixSort::SortPairs(nullptr, bytes1, val_tmp, s->nbr, key_tmp, s->ent_key, (int)(2 * n), 0, kEntityBits, c->stream);
+   cub::DeviceRadixSort::SortPairs(nullptr, bytes2, s->ent_key, key_tmp, s->nbr, val_tmp, (int)(2 * n), 0, 41, c->stream);
+   KB2E_CUDA(c, cudaMalloc(&cub_tmp, std::max(bytes1, bytes2)));
+   KB2E_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, bytes1, val_tmp, s->nbr, key_tmp, s->ent_key, (int)(2 * n), 0, kEntityBits, c->stream));
+   KB2E_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, bytes2, s->ent_key, key_tmp, s->nbr, val_tmp, (int)(2 * n), 0, 41, c->stream));
+   KB2E_CUDA(c, cudaMemcpyAsync(s->ent_key, key_tmp, 2 * n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+   KB2E_CUDA(c, cudaMemcpyAsync(s->nbr, val_tmp, 2 * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+   segment_hash_kernel<<<nblk((long long)(2 * n), 256), 256, 0, c->stream>>>(s->ent_key, s->n_ent, s->seg_key, s->seg_val, s->seg_mask);
+   KB2E_CUDA(c, cudaGetLastError());
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   cudaFree(ids); cudaFree(key_tmp); cudaFree(val_tmp); cudaFree(cub_tmp);
    c->filter_dirty = false;
    return KB2E_OK;
 }
@@ -441,7 +510,7 @@ static int project(kb2e_ctx* c, const std::vector<int32_t>& rels) {
 static int prepare_tables(kb2e_ctx* c) {
    int rc = ensure_state(c);
    if (rc) return rc;
-   rc = tables_32_to_64(c);
+   rc = ensure64(c);
    if (rc) return rc;
    RankState* s = c->rank;
    dim3 grid(nblk(s->ld, 32), nblk(c->D, 32));
@@ -553,7 +622,8 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    a.q_fixed = s->q_int; a.q_truth = s->q_int + nq; a.q_rel = s->q_int + 2 * nq; a.q_side = s->q_int + 3 * nq;
    a.q_slot = s->q_int + 4 * nq;
    a.q_etrue = s->q_etrue; a.q_cnt = s->q_cnt;
-   a.seg_key = s->seg_key; a.seg_val = s->seg_val; a.nbr = s->nbr; a.seg_mask = s->seg_mask;
+   a.seg_key = s->seg_key; a.seg_val = s->seg_val; a.ent_key = s->ent_key; a.nbr = s->nbr; a.seg_mask = s->seg_mask;
+   a.n_ent = s->n_ent;
    a.nq = nq; a.nE = c->nE; a.D = c->D; a.ld = s->ld;
 
    const size_t smem = (size_t)c->D * kQT * sizeof(double2);
@@ -561,6 +631,13 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    KB2E_CUDA(c, cudaFuncSetAttribute(rank_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
    KB2E_CUDA(c, cudaFuncSetAttribute(rank_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
+   const bool use_tc = tc_supported(c);
+   if (use_tc) {
+      rc = tc_init(c, &s->tc);
+      if (rc) return rc;
+      rc = tc_prepare_candidates(c, &s->tc);
+      if (rc) return rc;
+   }
    float main_ms = 0.f;
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
    for (size_t p = 0; p < passes.size(); p++) {
@@ -587,10 +664,38 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       const long long pq = ps.q_end - ps.q_begin;
       if (l2) etrue_kernel<1><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
       else etrue_kernel<0><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
-      KB2E_CUDA(c, cudaEventRecord(s->m0, c->stream));
-      if (l2) rank_exact_kernel<1><<<dim3(ntiles, (unsigned)splits), kRankThreads, smem, c->stream>>>(a);
-      else rank_exact_kernel<0><<<dim3(ntiles, (unsigned)splits), kRankThreads, smem, c->stream>>>(a);
-      KB2E_CUDA(c, cudaEventRecord(s->m1, c->stream));
+      bool exact_pass = true;
+      if (use_tc) {
+         // tensor-core pre-filter + exact recheck of the undecided band (rank_tc.cu)
+         bool overflow = false;
+         rc = tc_run(c, &s->tc, a.q_fixed + ps.q_begin, a.q_rel + ps.q_begin, a.q_side + ps.q_begin, a.q_etrue + ps.q_begin,
+                     pq, s->q_cnt + ps.q_begin, &overflow);
+         if (rc) return rc;
+         if (!overflow) {
+            exact_pass = false;
+            main_ms += s->tc.last_ms;
+            c->rstats.rechecked += s->tc.last_band;
+            c->rstats.launches += 3;
+            if (s->tc.last_band) {
+               // band entries hold query indices relative to the pass window
+               recheck_kernel<1><<<nblk(s->tc.last_band, 128), 128, 0, c->stream>>>(
+                  s->tc.band, s->tc.last_band, c->ent64, c->rel64, a.q_fixed + ps.q_begin, a.q_truth + ps.q_begin,
+                  a.q_rel + ps.q_begin, a.q_side + ps.q_begin, a.q_etrue + ps.q_begin, s->q_cnt + ps.q_begin, nq, c->D);
+            }
+            KB2E_CUDA(c, cudaEventRecord(s->m0, c->stream));
+            KB2E_CUDA(c, cudaEventRecord(s->m1, c->stream));
+         } else {
+            // band list overflowed (degenerate tables): fall back to the exact kernel for this pass
+            KB2E_CUDA(c, cudaMemsetAsync(s->q_cnt + ps.q_begin, 0, (size_t)pq * sizeof(int32_t), c->stream));
+            KB2E_CUDA(c, cudaMemsetAsync(s->q_cnt + nq + ps.q_begin, 0, (size_t)pq * sizeof(int32_t), c->stream));
+         }
+      }
+      if (exact_pass) {
+         KB2E_CUDA(c, cudaEventRecord(s->m0, c->stream));
+         if (l2) rank_exact_kernel<1><<<dim3(ntiles, (unsigned)splits), kRankThreads, smem, c->stream>>>(a);
+         else rank_exact_kernel<0><<<dim3(ntiles, (unsigned)splits), kRankThreads, smem, c->stream>>>(a);
+         KB2E_CUDA(c, cudaEventRecord(s->m1, c->stream));
+      }
       if (l2) filter_kernel<1><<<nblk(pq * 32, 128), 128, 0, c->stream>>>(a);
       else filter_kernel<0><<<nblk(pq * 32, 128), 128, 0, c->stream>>>(a);
       KB2E_CUDA(c, cudaGetLastError());
@@ -598,7 +703,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       KB2E_CUDA(c, cudaEventSynchronize(s->m1));
       float ms = 0.f;
       KB2E_CUDA(c, cudaEventElapsedTime(&ms, s->m0, s->m1));
-      main_ms += ms;
+      if (exact_pass) main_ms += ms;
       c->rstats.launches += per_rel ? 4 : 3;
    }
    finalize_kernel<<<nblk(nq, 256), 256, 0, c->stream>>>(s->q_cnt, s->q_int + 5 * nq, nq, s->out, s->sums);
@@ -648,10 +753,11 @@ int rank_score64(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t*
 void rank_free(kb2e_ctx* c) {
    RankState* s = c->rank;
    if (!s) return;
-   cudaFree(s->seg_key); cudaFree(s->seg_val); cudaFree(s->nbr); cudaFree(s->ct0); cudaFree(s->pt);
+   cudaFree(s->seg_key); cudaFree(s->seg_val); cudaFree(s->nbr); cudaFree(s->ent_key); cudaFree(s->ct0); cudaFree(s->pt);
    cudaFree(s->q_int); cudaFree(s->q_etrue); cudaFree(s->q_cnt); cudaFree(s->tiles); cudaFree(s->slot_rel);
    cudaFree(s->sums); cudaFree(s->out);
    if (s->m0) { cudaEventDestroy(s->m0); cudaEventDestroy(s->m1); }
+   tc_free(&s->tc);
    delete s;
    c->rank = nullptr;
 }

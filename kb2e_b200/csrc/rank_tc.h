@@ -1,0 +1,57 @@
+// Interface between rank.cu (exact fp64 ranking, filter, finalize) and rank_tc.cu (tcgen05 pre-filter).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct kb2e_ctx;
+
+namespace kb2e {
+
+namespace tc {
+constexpr int kRowChunks = 14;  // operand rows hold 14 x 16 B = 112 bf16 (embedding sizes up to 112)
+}
+
+struct TcArgs {
+   const __nv_bfloat16* u_hi;
+   const __nv_bfloat16* u_lo;
+   const __nv_bfloat16* c_hi;
+   const __nv_bfloat16* c_lo;
+   const float* n_c;
+   const float* thr_lo;
+   const float* thr_hi;
+   int32_t* q_less;
+   int2* band;
+   unsigned int* band_count;
+   unsigned int band_cap;
+   long long nq;
+   int n_pad;
+};
+
+struct TcState {
+   void* c_hi = nullptr;
+   void* c_lo = nullptr;
+   float* n_c = nullptr;
+   int n_pad = 0;
+   void* u_hi = nullptr;
+   void* u_lo = nullptr;
+   float* thr_lo = nullptr;
+   float* thr_hi = nullptr;
+   long long q_cap = 0;
+   int2* band = nullptr;
+   unsigned int band_cap = 0;
+   unsigned int* scalars = nullptr;  // [0] max |c| (float bits), [1] band count
+   cudaEvent_t e0 = nullptr, e1 = nullptr;
+   float last_ms = 0.f;
+   unsigned int last_band = 0;
+};
+
+bool tc_supported(const kb2e_ctx* c);
+int tc_init(kb2e_ctx* c, TcState* s);
+int tc_prepare_candidates(kb2e_ctx* c, TcState* s);
+int tc_run(kb2e_ctx* c, TcState* s, const int32_t* q_fixed, const int32_t* q_rel, const int32_t* q_side, const double* q_etrue,
+           long long nq, int32_t* q_less, bool* overflow);
+void tc_free(TcState* s);
+
+}  // namespace kb2e

@@ -863,9 +863,14 @@ __global__ void hash_insert_kernel(const int4* triples, long long n, uint64_t* t
    }
 }
 
-__global__ void pack_triples_kernel(const int32_t* h, const int32_t* t, const int32_t* r, long long n, int4* out) {
+// (h, t, r) columns -> packed int4 records; ids are validated here (first offending index -> *bad).
+__global__ void pack_triples_kernel(const int32_t* h, const int32_t* t, const int32_t* r, long long n, int nE, int nR,
+                                    int4* out, unsigned long long* bad) {
    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n) out[i] = make_int4(h[i], t[i], r[i], 0);
+   if (i >= n) return;
+   int hh = h[i], tt = t[i], rr = r[i];
+   if (hh < 0 || hh >= nE || tt < 0 || tt >= nE || rr < 0 || rr >= nR) atomicMin(bad, (unsigned long long)i);
+   out[i] = make_int4(hh, tt, rr, 0);
 }
 
 // Initial values: N(0, (1/D)^2) per element (the reference's rejection-sampled truncated normal never
@@ -955,7 +960,7 @@ int train_alloc(kb2e_ctx* c) {
 
 void train_free(kb2e_ctx* c) {
    cudaFree(c->tab); cudaFree(c->dtab); cudaFree(c->w); cudaFree(c->dw); cudaFree(c->flag);
-   cudaFree(c->rmin); cudaFree(c->rmax); cudaFree(c->triples); cudaFree(c->hash); cudaFree(c->pr);
+   cudaFree(c->rmin); cudaFree(c->rmax); cudaFree(c->triples); cudaFree(c->stage); cudaFree(c->hash); cudaFree(c->pr);
    cudaFree(c->barrier); cudaFree(c->loss_dev); cudaFree(c->counters); cudaFree(c->pairs_dev);
    cudaFree(c->ent64); cudaFree(c->rel64); cudaFree(c->w64);
 }
@@ -963,30 +968,39 @@ void train_free(kb2e_ctx* c) {
 int train_set_triples(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t* r, int64_t n) {
    int rc = train_alloc(c);
    if (rc) return rc;
-   for (int64_t i = 0; i < n; i++) {
-      if (h[i] < 0 || h[i] >= c->nE || t[i] < 0 || t[i] >= c->nE || r[i] < 0 || r[i] >= c->nR)
-         return fail(c, KB2E_ERR_ARG, "train triple " + std::to_string(i) + " has an id out of range");
-   }
-   cudaFree(c->triples); c->triples = nullptr;
-   cudaFree(c->hash); c->hash = nullptr;
-   c->n_train = n;
+   c->n_train = 0;
    if (n == 0) return KB2E_OK;
-   int32_t* tmp = nullptr;
-   KB2E_CUDA(c, cudaMalloc(&tmp, 3 * (size_t)n * sizeof(int32_t)));
-   KB2E_CUDA(c, cudaMemcpyAsync(tmp, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-   KB2E_CUDA(c, cudaMemcpyAsync(tmp + n, t, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-   KB2E_CUDA(c, cudaMemcpyAsync(tmp + 2 * n, r, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-   KB2E_CUDA(c, cudaMalloc(&c->triples, (size_t)n * sizeof(int4)));
-   pack_triples_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(tmp, tmp + n, tmp + 2 * n, n, c->triples);
+   // device buffers are kept across calls (capacity only grows): no allocation on the steady path
+   if (n > c->triples_cap) {
+      cudaFree(c->triples); cudaFree(c->stage);
+      c->triples = nullptr; c->stage = nullptr; c->triples_cap = 0;
+      KB2E_CUDA(c, cudaMalloc(&c->stage, 3 * (size_t)n * sizeof(int32_t)));
+      KB2E_CUDA(c, cudaMalloc(&c->triples, (size_t)n * sizeof(int4)));
+      c->triples_cap = n;
+   }
    uint64_t slots = 1024;
    while (slots < 2 * (uint64_t)n) slots <<= 1;
+   if (slots > c->hash_cap) {
+      cudaFree(c->hash);
+      c->hash = nullptr; c->hash_cap = 0;
+      KB2E_CUDA(c, cudaMalloc(&c->hash, slots * sizeof(uint64_t)));
+      c->hash_cap = slots;
+   }
    c->hash_mask = slots - 1;
-   KB2E_CUDA(c, cudaMalloc(&c->hash, slots * sizeof(uint64_t)));
+   int32_t* st = c->stage;
+   KB2E_CUDA(c, cudaMemcpyAsync(st, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+   KB2E_CUDA(c, cudaMemcpyAsync(st + n, t, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+   KB2E_CUDA(c, cudaMemcpyAsync(st + 2 * n, r, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+   KB2E_CUDA(c, cudaMemsetAsync(c->counters + 7, 0xff, sizeof(unsigned long long), c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->hash, 0xff, slots * sizeof(uint64_t), c->stream));
+   pack_triples_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(st, st + n, st + 2 * n, n, c->nE, c->nR, c->triples, c->counters + 7);
    hash_insert_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->triples, n, c->hash, c->hash_mask);
    KB2E_CUDA(c, cudaGetLastError());
+   unsigned long long bad = 0;
+   KB2E_CUDA(c, cudaMemcpyAsync(&bad, c->counters + 7, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
-   cudaFree(tmp);
+   if (bad != ~0ull) return fail(c, KB2E_ERR_ARG, "train triple " + std::to_string(bad) + " has an id out of range");
+   c->n_train = n;
    return KB2E_OK;
 }
 
@@ -1002,46 +1016,73 @@ int train_init_embeddings(kb2e_ctx* c) {
       identity_kernel<<<blocks_for((long long)c->nR * c->D * c->P, 256), 256, 0, c->stream>>>(c->w, c->nR, c->D, c->P);
    }
    KB2E_CUDA(c, cudaGetLastError());
-   c->have32 = true;
-   c->have64 = false;
+   for (int t = 0; t < 3; t++) { c->v32[t] = true; c->v64[t] = false; }
    return KB2E_OK;
 }
 
-int tables_32_to_64(kb2e_ctx* c) {
-   if (c->have64) return KB2E_OK;
-   if (!c->have32) return fail(c, KB2E_ERR_ARG, "no embeddings: call kb2e_init_embeddings or kb2e_upload first");
-   if (!c->ent64) {
-      KB2E_CUDA(c, cudaMalloc(&c->ent64, (size_t)c->nE * c->D * sizeof(double)));
-      KB2E_CUDA(c, cudaMalloc(&c->rel64, (size_t)c->nR * c->D * sizeof(double)));
-      if (c->cfg.model != KB2E_MODEL_TRANSE) {
-         size_t per = c->cfg.model == KB2E_MODEL_TRANSH ? (size_t)c->D : (size_t)c->D * c->D;
-         KB2E_CUDA(c, cudaMalloc(&c->w64, (size_t)c->nR * per * sizeof(double)));
-      }
+int num_tables(const kb2e_ctx* c) { return c->cfg.model == KB2E_MODEL_TRANSE ? 2 : 3; }
+
+static long long table_rows(const kb2e_ctx* c, int t) {
+   if (t == KB2E_TABLE_ENTITY) return c->nE;
+   if (t == KB2E_TABLE_RELATION) return c->nR;
+   return c->cfg.model == KB2E_MODEL_TRANSH ? (long long)c->nR : (long long)c->nR * c->D;
+}
+
+static float* table32(kb2e_ctx* c, int t) {
+   if (t == KB2E_TABLE_ENTITY) return c->tab;
+   if (t == KB2E_TABLE_RELATION) return c->tab + (size_t)c->nE * c->P;
+   return c->w;
+}
+
+static double** table64_slot(kb2e_ctx* c, int t) {
+   return t == KB2E_TABLE_ENTITY ? &c->ent64 : (t == KB2E_TABLE_RELATION ? &c->rel64 : &c->w64);
+}
+
+double* table64(kb2e_ctx* c, int t) {
+   double** slot = table64_slot(c, t);
+   if (!*slot) {
+      if (cudaMalloc(slot, (size_t)table_rows(c, t) * c->D * sizeof(double)) != cudaSuccess) return nullptr;
    }
-   widen_kernel<<<blocks_for((long long)c->nE * c->D, 256), 256, 0, c->stream>>>(c->tab, c->ent64, c->nE, c->D, c->P);
-   widen_kernel<<<blocks_for((long long)c->nR * c->D, 256), 256, 0, c->stream>>>(c->tab + (size_t)c->nE * c->P, c->rel64, c->nR, c->D, c->P);
-   if (c->cfg.model == KB2E_MODEL_TRANSH) {
-      widen_kernel<<<blocks_for((long long)c->nR * c->D, 256), 256, 0, c->stream>>>(c->w, c->w64, c->nR, c->D, c->P);
-   } else if (c->cfg.model == KB2E_MODEL_TRANSR) {
-      widen_kernel<<<blocks_for((long long)c->nR * c->D * c->D, 256), 256, 0, c->stream>>>(c->w, c->w64, (long long)c->nR * c->D, c->D, c->P);
-   }
+   return *slot;
+}
+
+int widen_table(kb2e_ctx* c, int t) {
+   if (!c->v32[t]) return fail(c, KB2E_ERR_ARG, "table " + std::to_string(t) + " has no values: call kb2e_init_embeddings or kb2e_upload first");
+   double* dst = table64(c, t);
+   if (!dst) return fail(c, KB2E_ERR_CUDA, "out of device memory for the fp64 tables");
+   long long rows = table_rows(c, t);
+   widen_kernel<<<blocks_for(rows * c->D, 256), 256, 0, c->stream>>>(table32(c, t), dst, rows, c->D, c->P);
    KB2E_CUDA(c, cudaGetLastError());
-   c->have64 = true;
+   c->v64[t] = true;
    return KB2E_OK;
 }
 
-int tables_64_to_32(kb2e_ctx* c) {
+int narrow_table(kb2e_ctx* c, int t) {
    int rc = train_alloc(c);
    if (rc) return rc;
-   narrow_kernel<<<blocks_for((long long)c->nE * c->P, 256), 256, 0, c->stream>>>(c->ent64, c->tab, c->nE, c->D, c->P);
-   narrow_kernel<<<blocks_for((long long)c->nR * c->P, 256), 256, 0, c->stream>>>(c->rel64, c->tab + (size_t)c->nE * c->P, c->nR, c->D, c->P);
-   if (c->cfg.model == KB2E_MODEL_TRANSH) {
-      narrow_kernel<<<blocks_for((long long)c->nR * c->P, 256), 256, 0, c->stream>>>(c->w64, c->w, c->nR, c->D, c->P);
-   } else if (c->cfg.model == KB2E_MODEL_TRANSR) {
-      narrow_kernel<<<blocks_for((long long)c->nR * c->D * c->P, 256), 256, 0, c->stream>>>(c->w64, c->w, (long long)c->nR * c->D, c->D, c->P);
-   }
+   if (!c->v64[t]) return fail(c, KB2E_ERR_ARG, "table " + std::to_string(t) + " has no values");
+   long long rows = table_rows(c, t);
+   narrow_kernel<<<blocks_for(rows * c->P, 256), 256, 0, c->stream>>>(*table64_slot(c, t), table32(c, t), rows, c->D, c->P);
    KB2E_CUDA(c, cudaGetLastError());
-   c->have32 = true;
+   c->v32[t] = true;
+   return KB2E_OK;
+}
+
+int ensure32(kb2e_ctx* c) {
+   for (int t = 0; t < num_tables(c); t++) {
+      if (c->v32[t]) continue;
+      int rc = narrow_table(c, t);
+      if (rc) return rc;
+   }
+   return KB2E_OK;
+}
+
+int ensure64(kb2e_ctx* c) {
+   for (int t = 0; t < num_tables(c); t++) {
+      if (c->v64[t]) continue;
+      int rc = widen_table(c, t);
+      if (rc) return rc;
+   }
    return KB2E_OK;
 }
 
@@ -1126,7 +1167,7 @@ static void choose_shape(const kb2e_ctx* c, long long batchsize, int& lps, int& 
 }
 
 int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_dev, int64_t n_pairs, double* loss_out) {
-   if (!c->have32) return fail(c, KB2E_ERR_ARG, "no embeddings: call kb2e_init_embeddings or kb2e_upload first");
+   { int rc = ensure32(c); if (rc) return rc; }
    TrainArgs a;
    if (n_epochs <= 0) return KB2E_OK;
    if (n_epochs > c->loss_cap) {
@@ -1203,7 +1244,7 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    c->tstats.touched_ent = cnt[1];
    c->tstats.touched_rel = cnt[2];
    if (loss_out) memcpy(loss_out, loss.data(), (size_t)n_epochs * sizeof(double));
-   c->have64 = false;
+   for (int t = 0; t < 3; t++) c->v64[t] = false;
    return KB2E_OK;
 }
 
@@ -1218,11 +1259,7 @@ int train_sample(kb2e_ctx* c, int epoch, int batch, int64_t count, int32_t* out_
 }
 
 int train_score32(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t* r, int64_t n, double* out) {
-   if (!c->have32) {
-      if (!c->have64) return fail(c, KB2E_ERR_ARG, "no embeddings");
-      int rc = tables_64_to_32(c);
-      if (rc) return rc;
-   }
+   { int rc = ensure32(c); if (rc) return rc; }
    unsigned blocks = blocks_for(n * 32, 256);
    if (c->cfg.model == KB2E_MODEL_TRANSR) {
       if (c->P > 128) return fail(c, KB2E_ERR_LIMIT, "TransR fp32 scoring supports embedding sizes up to 128");

@@ -722,3 +722,33 @@ void orc_train_epochs_dfr(const orc_sampler* s, int model, int distance, int D, 
    free(carry);
    free(pairs);
 }
+
+/* epochs x batches of orc_sample_batch + orc_train_batch_ref: the REFERENCE's sequential batch semantics
+ * (bitwise-pinned above) driven by the uniform counter sampler instead of the reference's randMax
+ * (common/utils.cpp:113-120, whose int-overflowing product of two rand() values is heavily non-uniform).
+ * Separates "what the sampler changes" from "what the deferred renormalisation changes" in the
+ * trained-model parity study (tools/stat_parity.py). */
+void orc_train_epochs_ref(const orc_sampler* s, int model, int distance, int D, int nE, int nR,
+                          double lr, double margin, int batches, int first_epoch, int epochs, uint64_t seed,
+                          double* ent, double* rel, double* w, double* loss_out) {
+   long batchsize = s->n / batches;
+   int* pairs = (int*)malloc(sizeof(int) * 6 * (size_t)(batchsize > 0 ? batchsize : 1));
+   size_t we = w_elems(model, D, nR);
+   double* entN = (double*)malloc(sizeof(double) * (size_t)nE * D);
+   double* relN = (double*)malloc(sizeof(double) * (size_t)nR * D);
+   double* wN = (double*)malloc(sizeof(double) * (we ? we : 1));
+   for (int e = 0; e < epochs; e++) {
+      double loss = 0;
+      for (int b = 0; b < batches; b++) {
+         uint32_t gb = (uint32_t)(first_epoch + e) * (uint32_t)batches + (uint32_t)b;
+         orc_sample_batch(s, seed, gb, batchsize, pairs);
+         loss += orc_train_batch_ref(model, distance, D, nE, nR, lr, margin, ent, rel, w, batchsize, pairs, entN, relN, wN, NULL);
+         /* postbatch: cur = next (transe/trainer.cpp:48-51) */
+         memcpy(ent, entN, sizeof(double) * (size_t)nE * D);
+         memcpy(rel, relN, sizeof(double) * (size_t)nR * D);
+         if (we) memcpy(w, wN, sizeof(double) * we);
+      }
+      if (loss_out) loss_out[e] = loss;
+   }
+   free(entN); free(relN); free(wN); free(pairs);
+}

@@ -106,6 +106,12 @@ void orc_train_epochs_dfr(const orc_sampler*, int model, int distance, int D, in
                           double lr, double margin, int batches, int first_epoch, int epochs, uint64_t seed,
                           double* ent, double* rel, double* w, double* loss_out);
 
+/* Same loop with the REFERENCE's sequential batch semantics (orc_train_batch_ref) under the uniform
+ * counter sampler: isolates the effect of the reference's non-uniform randMax from everything else. */
+void orc_train_epochs_ref(const orc_sampler*, int model, int distance, int D, int nE, int nR,
+                          double lr, double margin, int batches, int first_epoch, int epochs, uint64_t seed,
+                          double* ent, double* rel, double* w, double* loss_out);
+
 #ifdef __cplusplus
 }
 #endif

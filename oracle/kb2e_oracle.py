@@ -162,6 +162,14 @@ class Sampler:
         self.o.lib.orc_sample_batch(self.ptr, C.c_uint64(seed), C.c_uint32(global_batch), C.c_long(count), _i(out))
         return out
 
+    def train_epochs_ref(self, model, distance, lr, margin, batches, first_epoch, epochs, seed, ent, rel, w):
+        """Reference sequential batch semantics + the uniform counter sampler; in place on ent/rel/w."""
+        loss = np.empty(epochs, dtype=np.float64)
+        self.o.lib.orc_train_epochs_ref(self.ptr, model, distance, ent.shape[1], ent.shape[0], rel.shape[0],
+                                        C.c_double(lr), C.c_double(margin), batches, first_epoch, epochs,
+                                        C.c_uint64(seed), _d(ent), _d(rel), _d(w), _d(loss))
+        return loss
+
     def train_epochs_dfr(self, model, distance, lr, margin, batches, first_epoch, epochs, seed, ent, rel, w):
         loss = np.empty(epochs, dtype=np.float64)
         self.o.lib.orc_train_epochs_dfr(self.ptr, model, distance, ent.shape[1], ent.shape[0], rel.shape[0],

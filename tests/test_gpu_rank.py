@@ -125,3 +125,37 @@ def test_full_shape_properties(gpu_lib):
         assert res["sums"][0] == res["raw"].astype(np.int64).sum() and res["sums"][1] == res["filt"].astype(np.int64).sum()
         st = ctx.rank_stats()
         assert st["queries"] == 2 * n
+
+
+@pytest.mark.parametrize("D,nE,n_test", [(100, 3000, 300), (64, 1500, 130), (112, 700, 50)])
+def test_tensor_core_prefilter_equals_exact_kernel(gpu_lib, oracle, D, nE, n_test):
+    """TransE squared-L2: the tcgen05 pre-filter + exact fp64 recheck band must give the very same
+    integer ranks and tie counts as the exact fp64 kernel (and as the oracle), including on clustered
+    embeddings where many candidates score within the band of the truth."""
+    from kb2e_b200.api import FLAG_RANK_EXACT_ONLY
+    nR = 9
+    rng = np.random.default_rng(D)
+    centers = rng.normal(0, 1 / np.sqrt(D), (40, D))
+    ent = centers[rng.integers(0, 40, nE)] + rng.normal(0, 1e-4, (nE, D))   # tight clusters: near-ties everywhere
+    ent[: nE // 2] = rng.normal(0, 1 / np.sqrt(D), (nE // 2, D))
+    ent = np.round(ent, 6)
+    ent[nE - 1] = ent[1]                                                     # exact ties
+    rel = np.round(rng.normal(0, 0.3 / np.sqrt(D), (nR, D)), 6)
+    tri = np.stack([rng.integers(0, nE, n_test + 500), rng.integers(0, nE, n_test + 500), rng.integers(0, nR, n_test + 500)], 1).astype(np.int32)
+    tri[:5, 0] = 1
+    test, filt = tri[:n_test], tri[n_test:]
+    out = {}
+    for name, flags in (("tc", 0), ("exact", FLAG_RANK_EXACT_ONLY)):
+        with make_ctx("transe", D, nE, nR, distance=1, flags=flags) as ctx:
+            upload_tables(ctx, ent, rel, None)
+            ctx.set_test_triples(test)
+            ctx.add_filter_triples(filt)
+            out[name] = ctx.rank()
+            out[name + "_stats"] = ctx.rank_stats()
+    for k in ("raw", "filt", "raw_ties", "filt_ties", "sums"):
+        assert np.array_equal(out["tc"][k], out["exact"][k]), k
+    assert out["tc_stats"]["rechecked"] > 0 and out["exact_stats"]["rechecked"] == 0
+    assert out["tc_stats"]["rechecked"] < 0.2 * 2 * n_test * nE
+    lo, hi, flo, fhi = oracle.rank(0, 1, ent, rel, None, test[:40], np.concatenate([filt, test[40:]]))
+    assert np.array_equal(out["tc"]["raw"][:80], lo) and np.array_equal(out["tc"]["filt"][:80], flo)
+    assert np.array_equal(out["tc"]["raw_ties"][:80], hi - lo)
