@@ -33,21 +33,28 @@
 namespace kb2e {
 namespace tc {
 
-constexpr int BM = 128;          // queries per CTA (TMEM lanes)
-constexpr int BN = 128;          // candidates per tile (TMEM columns)
+constexpr int BM = 128;          // queries per CTA tile (TMEM lanes)
+constexpr int BN = 128;          // candidates per tile (TMEM columns of one accumulator)
 constexpr int KC = kRowChunks;   // 16-byte chunks per operand row (8 bf16 each)
 constexpr int KSTEPS = KC / 2;   // one MMA consumes K = 16 bf16 = 2 chunks
-constexpr int TILE_BYTES = BM * KC * 16;
-constexpr int SMEM_BYTES = 4 * TILE_BYTES + BN * 4 + 64;
+constexpr int TILE_BYTES = BM * KC * 16;   // one operand tile: [chunk][row][16 B]
+constexpr int STAGES = 2;        // B-tile ring and TMEM accumulator ring
+constexpr int MT = 2;            // 128-query tiles per CTA: every candidate tile fetched from L2 feeds MT accumulators
+constexpr int EPI_WARPS = 4 * MT;
+constexpr int THREADS = 32 * (EPI_WARPS + 2);   // epilogue warps (TMEM lane quarters), + copy producer, + MMA issuer
+constexpr int SMEM_BYTES = (2 * MT + 2 * STAGES) * TILE_BYTES + 128;
+constexpr int TMEM_COLS = STAGES * MT * BN;      // 512: the whole tensor memory of the SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_NONE, version 1.
+// Tile layout [16-byte K chunk][row]: core matrix = 8 rows x 16 B contiguous (128 B),
+// leading byte offset (next K chunk) = 128 rows x 16 B, stride byte offset (next 8 rows) = 128 B.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
    uint64_t d = 0;
    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
-   d |= (uint64_t)((BM * 16) >> 4) << 16;      // leading byte offset: next 16-byte K chunk
-   d |= (uint64_t)(128 >> 4) << 32;            // stride byte offset: next group of 8 rows
+   d |= (uint64_t)((BM * 16) >> 4) << 16;      // leading byte offset
+   d |= (uint64_t)(128 >> 4) << 32;            // stride byte offset
    d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)
    return d;
 }
@@ -62,6 +69,9 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate) : "memory");
 }
 
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
    uint32_t ok;
    do {
@@ -69,129 +79,189 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                    : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
    } while (!ok);
 }
-
-// global [rows][KC*8] bf16 row-major -> shared [chunk][row] (128 rows)
-__device__ __forceinline__ void load_tile(const __nv_bfloat16* __restrict__ g, long long row0, unsigned char* s) {
-   const uint4* src = reinterpret_cast<const uint4*>(g) + row0 * KC;
-   for (int item = threadIdx.x; item < BM * KC; item += blockDim.x) {
-      int row = item / KC, kc = item - row * KC;
-      uint4 v = __ldg(src + item);
-      *reinterpret_cast<uint4*>(s + kc * (BM * 16) + row * 16) = v;
-   }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+   // arrives on the mbarrier once every previously issued MMA has completed (implies fence::before_thread_sync)
+   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(128, 2) rank_l2_tc_kernel(const TcArgs a) {
+// One CTA per work item = (128-query tile, range of candidate tiles).  Warp-specialised, all hand-offs by
+// mbarrier: producer --full--> MMA --tmem_full--> epilogue --tmem_empty--> MMA, MMA --empty--> producer.
+__global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) {
    extern __shared__ __align__(128) unsigned char smem[];
-   unsigned char* sA_hi = smem;
-   unsigned char* sA_lo = smem + TILE_BYTES;
-   unsigned char* sB_hi = smem + 2 * TILE_BYTES;
-   unsigned char* sB_lo = smem + 3 * TILE_BYTES;
-   float* s_nc = reinterpret_cast<float*>(smem + 4 * TILE_BYTES);
-   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + 4 * TILE_BYTES + BN * 4);
-   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + 4 * TILE_BYTES + BN * 4 + 16);
+   unsigned char* sA = smem;                             // MT x [hi | lo]
+   unsigned char* sB = smem + 2 * MT * TILE_BYTES;       // STAGES x [hi | lo]
+   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 * MT + 2 * STAGES) * TILE_BYTES);
+   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
+   const uint32_t bar_a = smem_u32(bars + 0);
+   const uint32_t bar_full = smem_u32(bars + 1);         // + stage
+   const uint32_t bar_empty = smem_u32(bars + 3);        // + stage
+   const uint32_t bar_tfull = smem_u32(bars + 5);        // + accumulator
+   const uint32_t bar_tempty = smem_u32(bars + 7);       // + accumulator
 
    const int warp = threadIdx.x >> 5;
-   const long long q0 = (long long)blockIdx.x * BM;
+   const int lane = threadIdx.x & 31;
+   const long long q0 = (long long)blockIdx.x * (MT * BM);
    const int tiles_total = a.n_pad / BN;
    const int t_begin = (int)((long long)tiles_total * blockIdx.y / gridDim.y);
    const int t_end = (int)((long long)tiles_total * (blockIdx.y + 1) / gridDim.y);
+   const int n_iter = t_end - t_begin;
 
-   if (warp == 0) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"((uint32_t)BN) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-   }
    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(s_bar)), "r"(1u) : "memory");
+      mbar_init(bar_a, 1);
+      for (int s = 0; s < STAGES; s++) {
+         mbar_init(bar_full + 8 * s, 1);
+         mbar_init(bar_empty + 8 * s, 1);
+         mbar_init(bar_tfull + 8 * s, 1);
+         mbar_init(bar_tempty + 8 * s, EPI_WARPS);
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
-   load_tile(a.u_hi, q0, sA_hi);
-   load_tile(a.u_lo, q0, sA_lo);
+   if (warp == EPI_WARPS + 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"((uint32_t)TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+   }
    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
    __syncthreads();
    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
    const uint32_t tmem_base = *s_tmem;
 
-   // this thread's query
-   const long long q = q0 + threadIdx.x;
-   const float thr_lo = a.thr_lo[q];   // s <  thr_lo            -> certainly ranked before the truth
-   const float thr_hi = a.thr_hi[q];   // thr_lo <= s <= thr_hi  -> exact fp64 recheck
-   int less = 0;
-   uint32_t parity = 0;
-
-   for (int t = t_begin; t < t_end; t++) {
-      const long long c0 = (long long)t * BN;
-      load_tile(a.c_hi, c0, sB_hi);
-      load_tile(a.c_lo, c0, sB_lo);
-      if (threadIdx.x < BN) s_nc[threadIdx.x] = __ldg(a.n_c + c0 + threadIdx.x);
-      // generic-proxy shared-memory writes -> visible to the tensor core (async proxy)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      if (threadIdx.x == 0) {
-         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-         const uint32_t ah = smem_u32(sA_hi), al = smem_u32(sA_lo), bh = smem_u32(sB_hi), bl = smem_u32(sB_lo);
-#pragma unroll
-         for (int ks = 0; ks < KSTEPS; ks++) {
-            const uint32_t off = ks * 2 * (BM * 16);
-            mma_bf16(tmem_base, make_desc(ah + off), make_desc(bh + off), ks > 0 ? 1u : 0u);
-            mma_bf16(tmem_base, make_desc(ah + off), make_desc(bl + off), 1u);
-            mma_bf16(tmem_base, make_desc(al + off), make_desc(bh + off), 1u);
+   if (warp == EPI_WARPS) {
+      // ===== copy producer: operand tiles are stored in global memory already in the shared-memory layout =====
+      if (lane == 0) {
+         mbar_expect_tx(bar_a, 2 * MT * TILE_BYTES);
+         for (int m = 0; m < MT; m++) {
+            const size_t aoff = ((size_t)blockIdx.x * MT + m) * TILE_BYTES;
+            bulk_copy(smem_u32(sA + (2 * m) * TILE_BYTES), reinterpret_cast<const unsigned char*>(a.u_hi) + aoff, TILE_BYTES, bar_a);
+            bulk_copy(smem_u32(sA + (2 * m + 1) * TILE_BYTES), reinterpret_cast<const unsigned char*>(a.u_lo) + aoff, TILE_BYTES, bar_a);
          }
-         // arrives on the mbarrier when every MMA above has completed (implies fence::before_thread_sync)
-         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(s_bar)) : "memory");
+         for (int i = 0; i < n_iter; i++) {
+            const int s = i & 1;
+            mbar_wait(bar_empty + 8 * s, ((i >> 1) & 1) ^ 1);   // slot free (passes at once the first time round)
+            const size_t off = (size_t)(t_begin + i) * TILE_BYTES;
+            mbar_expect_tx(bar_full + 8 * s, 2 * TILE_BYTES);
+            bulk_copy(smem_u32(sB + (2 * s) * TILE_BYTES), reinterpret_cast<const unsigned char*>(a.c_hi) + off, TILE_BYTES, bar_full + 8 * s);
+            bulk_copy(smem_u32(sB + (2 * s + 1) * TILE_BYTES), reinterpret_cast<const unsigned char*>(a.c_lo) + off, TILE_BYTES, bar_full + 8 * s);
+         }
       }
-      mbar_wait(smem_u32(s_bar), parity);
-      parity ^= 1u;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // epilogue: warp w owns TMEM lanes 32w .. 32w+31 (= queries), 32 columns (= candidates) per load
-#pragma unroll 1
-      for (int cb = 0; cb < BN; cb += 32) {
-         uint32_t v[32];
-         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
-         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr) : "memory");
-         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+   } else if (warp == EPI_WARPS + 1) {
+      // ===== MMA issuer: a single thread drives the tensor core =====
+      if (lane == 0) {
+         mbar_wait(bar_a, 0);
+         for (int i = 0; i < n_iter; i++) {
+            const int s = i & 1;
+            const uint32_t ph = (i >> 1) & 1;
+            mbar_wait(bar_tempty + 8 * s, ph ^ 1);   // accumulator drained by the epilogue
+            mbar_wait(bar_full + 8 * s, ph);         // operand bytes have landed
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t bh = smem_u32(sB + (2 * s) * TILE_BYTES), bl = smem_u32(sB + (2 * s + 1) * TILE_BYTES);
 #pragma unroll
-         for (int j = 0; j < 32; j++) {
-            const float s = fmaf(-2.f, __uint_as_float(v[j]), s_nc[cb + j]);
-            if (s < thr_lo) {
-               less++;
-            } else if (s <= thr_hi) {
-               unsigned int slot = atomicAdd(a.band_count, 1u);
-               if (slot < a.band_cap) a.band[slot] = make_int2((int)q, (int)(c0 + cb + j));
+            for (int m = 0; m < MT; m++) {
+               const uint32_t ah = smem_u32(sA + (2 * m) * TILE_BYTES), al = smem_u32(sA + (2 * m + 1) * TILE_BYTES);
+               const uint32_t acc = tmem_base + (uint32_t)((s * MT + m) * BN);
+#pragma unroll
+               for (int ks = 0; ks < KSTEPS; ks++) {
+                  const uint32_t off = ks * 2 * (BM * 16);
+                  mma_bf16(acc, make_desc(ah + off), make_desc(bh + off), ks > 0 ? 1u : 0u);   // hi * hi
+                  mma_bf16(acc, make_desc(ah + off), make_desc(bl + off), 1u);                 // hi * lo
+                  mma_bf16(acc, make_desc(al + off), make_desc(bh + off), 1u);                 // lo * hi
+               }
+            }
+            umma_commit(bar_empty + 8 * s);    // shared-memory slot can be refilled
+            umma_commit(bar_tfull + 8 * s);    // accumulator ready for the epilogue
+         }
+      }
+   } else {
+      // ===== epilogue: warp w reads TMEM lanes 32(w%4).. of accumulator w/4; thread = one query =====
+      const int mhalf = warp >> 2;
+      const long long q = q0 + threadIdx.x;
+      const float g_lo = a.thr_lo[q];   // g >  g_lo           -> candidate certainly ranks before the truth
+      const float g_hi = a.thr_hi[q];   // g_hi <= g <= g_lo   -> undecided: exact fp64 recheck
+      int less = 0;
+      for (int i = 0; i < n_iter; i++) {
+         const int s = i & 1;
+         mbar_wait(bar_tfull + 8 * s, (i >> 1) & 1);
+         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+         const long long c0 = (long long)(t_begin + i) * BN;
+#pragma unroll 1
+         for (int cb = 0; cb < BN; cb += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((s * MT + mhalf) * BN + cb);
+            asm volatile(
+               "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            bool any_band = false;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+               const float g = __uint_as_float(v[j]);
+               less += (g > g_lo) ? 1 : 0;
+               any_band |= (g >= g_hi) && !(g > g_lo);
+            }
+            if (any_band) {   // rare: collect the undecided candidates of this 32-column chunk
+#pragma unroll
+               for (int j = 0; j < 32; j++) {
+                  const float g = __uint_as_float(v[j]);
+                  if (g >= g_hi && !(g > g_lo)) {
+                     unsigned int slot = atomicAdd(a.band_count, 1u);
+                     if (slot < a.band_cap) a.band[slot] = make_int2((int)q, (int)(c0 + cb + j));
+                  }
+               }
             }
          }
+         // this warp has finished reading the accumulator
+         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+         __syncwarp();
+         if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
       }
-      // TMEM and the B buffers are overwritten by the next tile
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
+      if (q < a.nq) {
+         if (gridDim.y == 1) a.q_less[q] = less;
+         else if (less) atomicAdd(a.q_less + q, less);
+      }
    }
-   if (q < a.nq) {
-      if (gridDim.y == 1) a.q_less[q] = less;
-      else if (less) atomicAdd(a.q_less + q, less);
-   }
+   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
    __syncthreads();
-   if (warp == 0) {
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)BN) : "memory");
+   if (warp == EPI_WARPS + 1) {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
    }
 }
 
 // ---- operand preparation ---------------------------------------------------------------------------
+// Operand tiles live in global memory in the exact shared-memory layout: tile of 128 rows =
+// [16-byte K chunk (14)][row (128)][8 bf16], so a tile is one contiguous 28,672-byte bulk copy.
+__device__ __forceinline__ size_t tiled_index(long long row, int i) {
+   const long long tile = row / BM;
+   const int r = (int)(row - tile * BM);
+   return (size_t)tile * (TILE_BYTES / 2) + (size_t)(i >> 3) * (BM * 8) + (size_t)r * 8 + (i & 7);
+}
+
 __device__ __forceinline__ void split_bf16(double x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
    float xf = (float)x;
    hi = __float2bfloat16_rn(xf);
    lo = __float2bfloat16_rn(xf - __bfloat162float(hi));
 }
 
-// candidates: C (fp64 [n][D] row-major) -> c_hi, c_lo (bf16 [n_pad][KC*8]), n_c = |c|^2, and max |c|
+// candidates: C (fp64 [n][D] row-major) -> tiled c_hi / c_lo; columns D..D+2 of c_hi carry -|c|^2/2 as three
+// bf16 terms (the query side holds 1.0 there), so the accumulator is g = u.c - |c|^2/2 and
+// "score < T" becomes g > -T/2 with no per-column work in the epilogue.  Also max |c| for the band.
 __global__ void prep_candidates_kernel(const double* __restrict__ c64, int n, int n_pad, int D,
-                                       __nv_bfloat16* c_hi, __nv_bfloat16* c_lo, float* n_c, unsigned int* cmax_bits) {
+                                       __nv_bfloat16* c_hi, __nv_bfloat16* c_lo, unsigned int* cmax_bits) {
    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
    int lane = threadIdx.x & 31;
    if (row >= n_pad) return;
@@ -200,19 +270,28 @@ __global__ void prep_candidates_kernel(const double* __restrict__ c64, int n, in
       double x = (row < n && i < D) ? c64[(size_t)row * D + i] : 0.0;
       __nv_bfloat16 h, l;
       split_bf16(x, h, l);
-      c_hi[(size_t)row * (KC * 8) + i] = h;
-      c_lo[(size_t)row * (KC * 8) + i] = l;
+      c_hi[tiled_index(row, i)] = h;
+      c_lo[tiled_index(row, i)] = l;
       s += x * x;
    }
 #pragma unroll
    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
    if (lane == 0) {
-      n_c[row] = row < n ? (float)s : __int_as_float(0x7f800000);  // padding never counts
+      // padding rows get a huge negative bias: they never rank before anything (finite, so 0 * bias stays 0)
+      float b = row < n ? (float)(-0.5 * s) : -1.0e30f;
+      __nv_bfloat16 b0 = __float2bfloat16_rn(b);
+      float r1 = b - __bfloat162float(b0);
+      __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
+      __nv_bfloat16 b2 = __float2bfloat16_rn(r1 - __bfloat162float(b1));
+      c_hi[tiled_index(row, D + 0)] = b0;
+      c_hi[tiled_index(row, D + 1)] = b1;
+      c_hi[tiled_index(row, D + 2)] = b2;
       if (row < n) atomicMax(cmax_bits, __float_as_uint((float)sqrt(s) * 1.0000002f));
    }
 }
 
-// queries: u = V - d' (exact fp64) -> u_hi, u_lo; thresholds from E_true and |u|^2
+// queries: u = V - d' (exact fp64) -> tiled u_hi / u_lo (+ 1.0 in the three bias columns);
+// thresholds on g from E_true and |u|^2:  E(c) < E_true  <=>  g = u.c - |c|^2/2 > (|u|^2 - E_true) / 2
 __global__ void prep_queries_kernel(const double* __restrict__ c64, const double* __restrict__ rel64,
                                     const int32_t* q_fixed, const int32_t* q_rel, const int32_t* q_side, const double* q_etrue,
                                     long long nq, long long q_pad, int D, const unsigned int* cmax_bits,
@@ -229,25 +308,26 @@ __global__ void prep_queries_kernel(const double* __restrict__ c64, const double
       double x = (real && i < D) ? v[i] - sign * d[i] : 0.0;
       __nv_bfloat16 h, l;
       split_bf16(x, h, l);
-      u_hi[(size_t)q * (KC * 8) + i] = h;
-      u_lo[(size_t)q * (KC * 8) + i] = l;
+      if (real && i >= D && i < D + 3) h = __float2bfloat16_rn(1.0f);
+      u_hi[tiled_index(q, i)] = h;
+      u_lo[tiled_index(q, i)] = l;
       s += x * x;
    }
 #pragma unroll
    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
    if (lane == 0) {
       if (!real) {
-         thr_lo[q] = __int_as_float(0xff800000);  // -inf: padding rows never count, never recheck
-         thr_hi[q] = __int_as_float(0xff800000);
+         thr_lo[q] = __int_as_float(0x7f800000);  // +inf: padding rows never count ...
+         thr_hi[q] = __int_as_float(0x7f800000);  // ... and never recheck (g >= +inf is false for finite g)
       } else {
          const double cmax = (double)__uint_as_float(*cmax_bits);
-         const double T = q_etrue[q] - s;
-         // |s~ - s| <= 2 * 1.9e-5 * |u| |c| (three-product bf16 split) + ~4e-5 |u| |c| (fp32 accumulation of
-         // 336 products) + fp32 rounding of n_c and of the final fma; the band 2^-12 |u| |c|max is > 2x that.
+         const double G = 0.5 * (s - q_etrue[q]);
+         // |g~ - g| <= 1.9e-5 |u||c| (three-product bf16 split) + ~2e-5 |u||c| (fp32 accumulation of 336
+         // products) + 3 bf16 terms of |c|^2/2 (<= 2^-25 |c|^2) ; the band 2^-13 |u||c|max + eps is > 2x that.
          const double unorm = sqrt(s);
-         const double delta = 8.0 * (1.0 / 32768.0) * unorm * cmax + 6e-6 * (1.0 + unorm * cmax + cmax * cmax);
-         thr_lo[q] = __double2float_rd(T - delta);
-         thr_hi[q] = __double2float_ru(T + delta);
+         const double delta = 4.0 * (1.0 / 32768.0) * unorm * cmax + 3e-6 * (1.0 + unorm * cmax + cmax * cmax);
+         thr_lo[q] = __double2float_ru(G + delta);
+         thr_hi[q] = __double2float_rd(G - delta);
       }
    }
 }
@@ -258,31 +338,30 @@ __global__ void prep_queries_kernel(const double* __restrict__ c64, const double
 static inline unsigned nblk2(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 bool tc_supported(const kb2e_ctx* c) {
-   return c->cfg.model == KB2E_MODEL_TRANSE && c->cfg.distance == KB2E_DISTANCE_L2 && c->D <= tc::kRowChunks * 8 &&
+   return c->cfg.model == KB2E_MODEL_TRANSE && c->cfg.distance == KB2E_DISTANCE_L2 && c->D + 3 <= tc::kRowChunks * 8 &&
           !(c->cfg.flags & KB2E_FLAG_RANK_EXACT_ONLY);
 }
 
 int tc_prepare_candidates(kb2e_ctx* c, TcState* s) {
    const int n_pad = ((c->nE + tc::BN - 1) / tc::BN) * tc::BN;
    if (n_pad != s->n_pad) {
-      cudaFree(s->c_hi); cudaFree(s->c_lo); cudaFree(s->n_c);
-      s->c_hi = s->c_lo = nullptr; s->n_c = nullptr;
+      cudaFree(s->c_hi); cudaFree(s->c_lo);
+      s->c_hi = s->c_lo = nullptr;
       KB2E_CUDA(c, cudaMalloc(&s->c_hi, (size_t)n_pad * tc::kRowChunks * 16));
       KB2E_CUDA(c, cudaMalloc(&s->c_lo, (size_t)n_pad * tc::kRowChunks * 16));
-      KB2E_CUDA(c, cudaMalloc(&s->n_c, (size_t)n_pad * sizeof(float)));
       s->n_pad = n_pad;
    }
    if (!s->scalars) KB2E_CUDA(c, cudaMalloc(&s->scalars, 4 * sizeof(unsigned int)));
    KB2E_CUDA(c, cudaMemsetAsync(s->scalars, 0, 4 * sizeof(unsigned int), c->stream));
    tc::prep_candidates_kernel<<<nblk2((long long)n_pad * 32, 256), 256, 0, c->stream>>>(
-      c->ent64, c->nE, n_pad, c->D, (__nv_bfloat16*)s->c_hi, (__nv_bfloat16*)s->c_lo, s->n_c, s->scalars);
+      c->ent64, c->nE, n_pad, c->D, (__nv_bfloat16*)s->c_hi, (__nv_bfloat16*)s->c_lo, s->scalars);
    KB2E_CUDA(c, cudaGetLastError());
    return KB2E_OK;
 }
 
 int tc_run(kb2e_ctx* c, TcState* s, const int32_t* q_fixed, const int32_t* q_rel, const int32_t* q_side, const double* q_etrue,
            long long nq, int32_t* q_less, bool* overflow) {
-   const long long q_pad = ((nq + tc::BM - 1) / tc::BM) * tc::BM;
+   const long long q_pad = ((nq + tc::MT * tc::BM - 1) / (tc::MT * tc::BM)) * (tc::MT * tc::BM);
    if (q_pad > s->q_cap) {
       cudaFree(s->u_hi); cudaFree(s->u_lo); cudaFree(s->thr_lo); cudaFree(s->thr_hi); cudaFree(s->band);
       s->u_hi = s->u_lo = nullptr; s->thr_lo = s->thr_hi = nullptr; s->band = nullptr;
@@ -303,17 +382,24 @@ int tc_run(kb2e_ctx* c, TcState* s, const int32_t* q_fixed, const int32_t* q_rel
    TcArgs a;
    a.u_hi = (const __nv_bfloat16*)s->u_hi; a.u_lo = (const __nv_bfloat16*)s->u_lo;
    a.c_hi = (const __nv_bfloat16*)s->c_hi; a.c_lo = (const __nv_bfloat16*)s->c_lo;
-   a.n_c = s->n_c; a.thr_lo = s->thr_lo; a.thr_hi = s->thr_hi;
+   a.thr_lo = s->thr_lo; a.thr_hi = s->thr_hi;
    a.q_less = q_less; a.band = s->band; a.band_count = band_count; a.band_cap = s->band_cap;
    a.nq = nq; a.n_pad = s->n_pad;
-   const unsigned mtiles = (unsigned)(q_pad / tc::BM);
+   const unsigned mtiles = (unsigned)(q_pad / (tc::MT * tc::BM));
    const int ntiles = s->n_pad / tc::BN;
-   long long splits = std::max<long long>(1, (2ll * 2 * c->num_sms + mtiles - 1) / mtiles);
+   // one CTA per SM: cut the candidate range so that the work items fill whole waves (tail < 5 %)
+   long long splits = 1;
+   while (splits < ntiles) {
+      const long long items = (long long)mtiles * splits;
+      const long long waves = (items + c->num_sms - 1) / c->num_sms;
+      if (items >= 2 * c->num_sms && (double)items / (waves * c->num_sms) > 0.95) break;
+      splits++;
+   }
    splits = std::min<long long>(splits, ntiles);
    KB2E_CUDA(c, cudaFuncSetAttribute(tc::rank_l2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
    if (splits > 1) KB2E_CUDA(c, cudaMemsetAsync(q_less, 0, (size_t)nq * sizeof(int32_t), c->stream));
    KB2E_CUDA(c, cudaEventRecord(s->e0, c->stream));
-   tc::rank_l2_tc_kernel<<<dim3(mtiles, (unsigned)splits), 128, tc::SMEM_BYTES, c->stream>>>(a);
+   tc::rank_l2_tc_kernel<<<dim3(mtiles, (unsigned)splits), tc::THREADS, tc::SMEM_BYTES, c->stream>>>(a);
    KB2E_CUDA(c, cudaEventRecord(s->e1, c->stream));
    KB2E_CUDA(c, cudaGetLastError());
    unsigned int count = 0;
@@ -336,7 +422,7 @@ int tc_init(kb2e_ctx* c, TcState* s) {
 }
 
 void tc_free(TcState* s) {
-   cudaFree(s->c_hi); cudaFree(s->c_lo); cudaFree(s->n_c); cudaFree(s->u_hi); cudaFree(s->u_lo);
+   cudaFree(s->c_hi); cudaFree(s->c_lo); cudaFree(s->u_hi); cudaFree(s->u_lo);
    cudaFree(s->thr_lo); cudaFree(s->thr_hi); cudaFree(s->band); cudaFree(s->scalars);
    if (s->e0) { cudaEventDestroy(s->e0); cudaEventDestroy(s->e1); }
    *s = TcState();

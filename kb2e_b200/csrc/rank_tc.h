@@ -10,7 +10,7 @@ struct kb2e_ctx;
 namespace kb2e {
 
 namespace tc {
-constexpr int kRowChunks = 14;  // operand rows hold 14 x 16 B = 112 bf16 (embedding sizes up to 112)
+constexpr int kRowChunks = 14;  // operand rows hold 14 x 16 B = 112 bf16: embedding sizes up to 109 + 3 bias columns
 }
 
 struct TcArgs {
@@ -18,7 +18,6 @@ struct TcArgs {
    const __nv_bfloat16* u_lo;
    const __nv_bfloat16* c_hi;
    const __nv_bfloat16* c_lo;
-   const float* n_c;
    const float* thr_lo;
    const float* thr_hi;
    int32_t* q_less;
@@ -32,7 +31,6 @@ struct TcArgs {
 struct TcState {
    void* c_hi = nullptr;
    void* c_lo = nullptr;
-   float* n_c = nullptr;
    int n_pad = 0;
    void* u_hi = nullptr;
    void* u_lo = nullptr;
