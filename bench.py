@@ -289,7 +289,7 @@ def run_product(args):
     if world == 1 and not args.no_cpu_baseline:
         cpu_train, cpu_eval = reference_sample(train, valid, test, nE, nR, ent_eval, rel_eval, train_epochs=1, eval_triples=100)
 
-    ranking_flops = 2.0 * nq * nE * CFG["dim"]
+    ranking_flops = 2.0 * (2 * (hi - lo)) * nE * CFG["dim"]  # this rank's shard: the roofline is per GPU
     traffic = profile_traffic("train")
     line = {
         "metric": "train_triples_per_s", "value": value, "unit": "triples/s", "n_gpus": world, "steps": K, "warmup": W,
