@@ -131,6 +131,26 @@ int kb2e_rank(kb2e_ctx* ctx, int64_t first, int64_t count,
               int32_t* raw_rank, int32_t* filt_rank, int32_t* raw_ties, int32_t* filt_ties, int64_t sums[4]);
 int kb2e_get_rank_stats(kb2e_ctx* ctx, kb2e_rank_stats* out);
 
+/* ---- entity-partitioned training across the GPUs of one NVLink box (TransE; BASELINE configs[4]) ----
+ * One context per process per GPU.  Entity row e lives on rank e % world at local index e / world;
+ * relation rows are replicated.  kb2e_dist_setup allocates this rank's arena and returns a 64-byte
+ * CUDA IPC handle; the caller exchanges the handles of all ranks (any transport) and passes the
+ * world x 64 bytes, in rank order, to kb2e_dist_connect.  All ranks must then call
+ * kb2e_dist_train_epochs with the same arguments: the kernels exchange rows and updates with peer
+ * loads / vector REDs over NVLink and synchronise on peer-mapped counters; no host step in between.
+ * Train triples and bern statistics are set per rank with kb2e_set_train_triples / kb2e_set_bern.
+ * loss_per_epoch receives this rank's share of the loss (add across ranks).
+ * Tables: KB2E_TABLE_ENTITY = this rank's rows [ceil((N_E - rank) / world)][dim] (global ids rank,
+ * rank + world, ...); KB2E_TABLE_RELATION = the replica [N_R][dim]. */
+#define KB2E_DIST_HANDLE_BYTES 64
+int kb2e_dist_setup(kb2e_ctx* ctx, int32_t rank, int32_t world, void* handle_out);
+int kb2e_dist_connect(kb2e_ctx* ctx, const void* handles);
+int kb2e_dist_init_embeddings(kb2e_ctx* ctx);
+int kb2e_dist_upload(kb2e_ctx* ctx, int table, const double* host, int64_t rows, int64_t cols);
+int kb2e_dist_download(kb2e_ctx* ctx, int table, double* host, int64_t rows, int64_t cols);
+int kb2e_dist_train_epochs(kb2e_ctx* ctx, int32_t first_epoch, int32_t n_epochs, double* loss_per_epoch);
+void kb2e_dist_teardown(kb2e_ctx* ctx);
+
 /* ---- test hooks ----------------------------------------------------------------------------- */
 /* The device sampler's output for samples [0, count) of (epoch, batch): count x {h,t,r,h',t',r'}. */
 int kb2e_sample_batch(kb2e_ctx* ctx, int32_t epoch, int32_t batch, int64_t count, int32_t* pairs_out);

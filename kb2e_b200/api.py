@@ -17,6 +17,8 @@ SYMBOLS = [
     "kb2e_init_embeddings", "kb2e_upload", "kb2e_download", "kb2e_train_epochs", "kb2e_get_train_stats",
     "kb2e_score", "kb2e_set_test_triples", "kb2e_add_filter_triples", "kb2e_rank", "kb2e_get_rank_stats",
     "kb2e_sample_batch", "kb2e_train_batch_pairs",
+    "kb2e_dist_setup", "kb2e_dist_connect", "kb2e_dist_init_embeddings", "kb2e_dist_upload", "kb2e_dist_download",
+    "kb2e_dist_train_epochs", "kb2e_dist_teardown",
 ]
 
 
@@ -226,3 +228,43 @@ class Context:
         self._check(self.lib.kb2e_train_batch_pairs(self.ptr, _p(p, C.c_int32), C.c_int64(len(p)), C.byref(loss),
                                                     C.byref(active)), "kb2e_train_batch_pairs")
         return loss.value, active.value
+
+
+    # ---- entity-partitioned multi-GPU training (one Context per process per GPU) ----
+    def dist_setup(self, rank, world):
+        """Allocates this rank's arena; returns its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.kb2e_dist_setup(self.ptr, int(rank), int(world), buf), "kb2e_dist_setup")
+        self.dist_rank, self.dist_world = int(rank), int(world)
+        self.rows_local = (self.nE - rank + world - 1) // world
+        return buf.raw
+
+    def dist_connect(self, handles):
+        """handles: the concatenated 64-byte handles of all ranks, in rank order."""
+        blob = b"".join(handles) if not isinstance(handles, (bytes, bytearray)) else bytes(handles)
+        assert len(blob) == 64 * self.dist_world
+        self._check(self.lib.kb2e_dist_connect(self.ptr, C.c_char_p(blob)), "kb2e_dist_connect")
+
+    def dist_init_embeddings(self):
+        self._check(self.lib.kb2e_dist_init_embeddings(self.ptr), "kb2e_dist_init_embeddings")
+
+    def dist_upload(self, table, array):
+        a = np.ascontiguousarray(array, dtype=np.float64)
+        rows = self.rows_local if table == TABLE_ENTITY else self.nR
+        a = a.reshape(rows, self.dim)
+        self._check(self.lib.kb2e_dist_upload(self.ptr, int(table), _p(a, C.c_double), C.c_int64(rows), C.c_int64(self.dim)),
+                    "kb2e_dist_upload")
+
+    def dist_download(self, table):
+        rows = self.rows_local if table == TABLE_ENTITY else self.nR
+        out = np.empty((rows, self.dim), dtype=np.float64)
+        self._check(self.lib.kb2e_dist_download(self.ptr, int(table), _p(out, C.c_double), C.c_int64(rows), C.c_int64(self.dim)),
+                    "kb2e_dist_download")
+        return out
+
+    def dist_train_epochs(self, first_epoch, n_epochs):
+        """Collective: every rank calls it with the same arguments.  Returns this rank's share of the loss."""
+        loss = np.zeros(max(n_epochs, 1), dtype=np.float64)
+        self._check(self.lib.kb2e_dist_train_epochs(self.ptr, int(first_epoch), int(n_epochs), _p(loss, C.c_double)),
+                    "kb2e_dist_train_epochs")
+        return loss[:n_epochs]

@@ -77,6 +77,7 @@ void kb2e_destroy(kb2e_ctx* c) {
    if (!c) return;
    cudaSetDevice(c->device);
    cudaStreamSynchronize(c->stream);
+   kb2e_dist_teardown(c);
    rank_free(c);
    train_free(c);
    cudaEventDestroy(c->ev0);

@@ -9,6 +9,8 @@
 
 #include "../../include/kb2e_b200.h"
 
+struct DistState;
+
 struct kb2e_ctx {
    kb2e_config cfg;
    int D = 0;       // -size
@@ -66,6 +68,7 @@ struct kb2e_ctx {
    std::vector<int32_t> filt_h, filt_t, filt_r;
    bool filter_dirty = true;
    struct RankState* rank = nullptr;
+   DistState* dist = nullptr;  // entity-partitioned multi-GPU training (train_dist.cu)
    kb2e_rank_stats rstats{};
 };
 

@@ -1,0 +1,201 @@
+// Device-side building blocks of the persistent training kernels (train.cu, train_dist.cu):
+// row-vector helpers, normalisations (common/utils.cpp:70-111), the grid-wide barrier and the
+// counter-RNG sampler (common/trainer.cpp:78-98).
+#pragma once
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace kb2e {
+
+constexpr int kMaxTrainThreads = 1024;
+constexpr int kTraceSlots = 64;
+
+struct TrainArgs {
+   float* tab;
+   float* dtab;
+   float* w;
+   float* dw;
+   uint8_t* flag;    // [nE + nR] batch stamp (1..255) of the last batch that touched the row; 0 = never
+   int* rmin;
+   int* rmax;
+   const int4* triples;
+   const uint64_t* hash;
+   uint64_t hash_mask;
+   const double* pr;
+   const int32_t* pairs;  // test hook: explicit (pos,neg) pairs instead of the sampler
+   uint32_t* barrier;
+   double* loss;                  // [n_epochs]
+   unsigned long long* counters;  // [0] active, [1] touched_ent, [2] touched_rel
+   long long n_train;
+   long long batchsize;
+   size_t w_row;
+   int nE, nR, D, P;
+   int batches, first_epoch, n_epochs, distance;
+   float lr, margin;
+   uint32_t seed_lo, seed_hi, flags;
+   unsigned long long* trace;     // tuning aid (KB2E_TRAIN_TRACE): per-CTA clock stamps of the first batches
+};
+
+// ---- small float4 helpers ----------------------------------------------------------------------
+__device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 operator*(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float abs4(float4 a) { return fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(a.w); }
+// L1 direction: x > 0 ? 1 : -1 (zero maps to -1, transe/trainer.cpp:31-35); padding lanes get 0.
+__device__ __forceinline__ float4 sign4(float4 a, int idx, int D) {
+   return make_float4(idx + 0 < D ? (a.x > 0.f ? 1.f : -1.f) : 0.f, idx + 1 < D ? (a.y > 0.f ? 1.f : -1.f) : 0.f,
+                      idx + 2 < D ? (a.z > 0.f ? 1.f : -1.f) : 0.f, idx + 3 < D ? (a.w > 0.f ? 1.f : -1.f) : 0.f);
+}
+
+template <int LPS>
+__device__ __forceinline__ float gsum(float v, uint32_t gmask) {
+#pragma unroll
+   for (int o = LPS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+   return v;
+}
+
+template <int LPS, int NV>
+__device__ __forceinline__ void load_row(const float* base, int P, int gl, float4 (&v)[NV]) {
+#pragma unroll
+   for (int q = 0; q < NV; q++) {
+      int off = (q * LPS + gl) * 4;
+      v[q] = off < P ? ld_cg4(base + off) : f4(0.f);
+   }
+}
+
+template <int LPS, int NV>
+__device__ __forceinline__ void red_row(float* base, int P, int gl, const float4 (&v)[NV]) {
+#pragma unroll
+   for (int q = 0; q < NV; q++) {
+      int off = (q * LPS + gl) * 4;
+      if (off < P) red_add4(base + off, v[q]);
+   }
+}
+
+template <int LPS, int NV>
+__device__ __forceinline__ void store_row(float* base, int P, int gl, const float4 (&v)[NV]) {
+#pragma unroll
+   for (int q = 0; q < NV; q++) {
+      int off = (q * LPS + gl) * 4;
+      if (off < P) st_cg4(base + off, v[q]);
+   }
+}
+
+template <int LPS, int NV>
+__device__ __forceinline__ float len2_row(const float4 (&v)[NV], uint32_t gmask) {
+   float s = 0.f;
+#pragma unroll
+   for (int q = 0; q < NV; q++) s += dot4(v[q], v[q]);
+   return gsum<LPS>(s, gmask);
+}
+
+// common::norm(a, ignoreShort), common/utils.cpp:70-77
+template <int LPS, int NV>
+__device__ __forceinline__ void norm_row(float4 (&v)[NV], bool ignoreShort, uint32_t gmask) {
+   float len = sqrtf(len2_row<LPS, NV>(v, gmask));
+   if (!ignoreShort || len > 1.f) {
+#pragma unroll
+      for (int q = 0; q < NV; q++) v[q] = make_float4(v[q].x / len, v[q].y / len, v[q].z / len, v[q].w / len);
+   }
+}
+
+// The loop of common::norm(a, b, rate), common/utils.cpp:83-108 (`sum` is deliberately not reset
+// between iterations, as in the reference).  b must already be unit length.  Returns #corrective steps.
+template <int LPS, int NV>
+__device__ __forceinline__ int soft_orth_loop(float4 (&a)[NV], float4 (&b)[NV], float rate, uint32_t gmask) {
+   float sum = 0.f;
+   int iters = 0;
+   while (true) {
+      sum += len2_row<LPS, NV>(b, gmask);
+      sum = sqrtf(sum);
+      float x = 0.f;
+#pragma unroll
+      for (int q = 0; q < NV; q++) {
+         b[q] = make_float4(b[q].x / sum, b[q].y / sum, b[q].z / sum, b[q].w / sum);
+         x += dot4(a[q], b[q]);
+      }
+      x = gsum<LPS>(x, gmask);
+      if (x > 0.1f && iters < 1000) {
+#pragma unroll
+         for (int q = 0; q < NV; q++) {
+            a[q] = a[q] - rate * b[q];
+            b[q] = b[q] - rate * a[q];
+         }
+         iters++;
+      } else {
+         break;
+      }
+   }
+   return iters;
+}
+
+// ---- grid-wide barrier (all CTAs are co-resident: cooperative launch) ---------------------------
+// bar.sync orders the CTA's writes before thread 0's gpu-scope release; pollers use relaxed loads and
+// one acquire fence at the end.  Measured on B200 (tools/microbench.cu): ~1.3 us per barrier.
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+   uint32_t v;
+   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+   return v;
+}
+
+// Split in two so that work which does not depend on other CTAs can run between arrive and wait.
+__device__ __forceinline__ void grid_arrive(uint32_t* counter, uint32_t& target) {
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      target += gridDim.x;
+      red_release_add_u32(counter, 1u);
+   }
+}
+
+__device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t target) {
+   if (threadIdx.x == 0) {
+      while ((int32_t)(ld_relaxed_u32(counter) - target) < 0) {
+      }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+   }
+   __syncthreads();
+}
+
+__device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& target) {
+   grid_arrive(counter, target);
+   grid_wait(counter, target);
+}
+
+// ---- the sampler: common/trainer.cpp:78-98 with a counter RNG -----------------------------------
+struct Pair {
+   int h, t, r, c;    // positive triple and the corrupting entity
+   bool corruptTail;  // true: (h, r, c) is the negative; false: (c, r, t)
+};
+
+__device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32_t gb) {
+   Pair s;
+   if (a.pairs != nullptr) {
+      const int32_t* p = a.pairs + 6ll * k;
+      s.h = __ldg(p + 0); s.t = __ldg(p + 1); s.r = __ldg(p + 2);
+      int nh = __ldg(p + 3), nt = __ldg(p + 4);
+      s.corruptTail = (nh == s.h);
+      s.c = s.corruptTail ? nt : nh;
+      return s;
+   }
+   uint32_t x[4];
+   philox4x32(k, gb, 0u, 0u, a.seed_lo, a.seed_hi, x);
+   uint64_t i = mulhi64(((uint64_t)x[0] << 32) | x[1], (uint64_t)a.n_train);
+   int4 tr = __ldg(a.triples + i);
+   s.h = tr.x; s.t = tr.y; s.r = tr.z;
+   int coin = (int)(x[2] % 1000u);
+   int j = (int)mulhi32(x[3], (uint32_t)a.nE);
+   s.corruptTail = (double)coin < __ldg(a.pr + tr.z);
+   for (uint32_t att = 1; att < 64; att++) {
+      uint64_t key = s.corruptTail ? pack_triple(s.h, s.r, j) : pack_triple(j, s.r, s.t);
+      if (!hash_contains(a.hash, a.hash_mask, key)) break;
+      philox4x32(k, gb, att, 0u, a.seed_lo, a.seed_hi, x);
+      j = (int)mulhi32(x[0], (uint32_t)a.nE);
+   }
+   s.c = j;
+   return s;
+}
+
+}  // namespace kb2e

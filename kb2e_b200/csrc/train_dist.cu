@@ -1,0 +1,480 @@
+// Entity-table-partitioned TransE training over the GPUs of one NVLink/NVSwitch box (BASELINE
+// configs[4]: 4 M entities x D=200, 100 M triples; SURVEY.md 8e "Training, scaled shape").
+//
+// One process (context) per GPU.  Entity row e lives on GPU e % G at local index e / G; the relation
+// table is small and replicated.  Every rank maps every peer's arena with CUDA IPC, so the SAME
+// persistent kernel design as train.cu runs on each GPU and simply dereferences peer pointers:
+//   phase 1  rank g takes the samples k = g (mod G) of the batch (the counter RNG makes the sample set
+//            independent of G), gathers h / t / c rows from their owners with ld.global.cg over NVLink,
+//            and pushes the update with red.global.add.v4.f32 into the OWNER's delta table; relation
+//            deltas go to the relation row's owner r % G.  Touched-row stamps are remote byte stores.
+//   barrier  local grid barrier + a cross-GPU barrier on peer-mapped counters (system-scope atomics)
+//   phase 2  every rank publishes its own stamped entity rows locally; the owner of a relation row
+//            normalises it and writes the new row into every replica
+//   barrier
+// No NCCL call and no host round trip inside an epoch: the exchange is peer loads / REDs issued by
+// the compute kernel itself, overlapped with its math.  Loss and counters are per rank (the host
+// adds them).  Semantics are identical to the single-GPU kernel (same samples, same deferred
+// renormalisation), so results agree up to the order of float atomics.
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+#include "train_device.cuh"
+
+namespace kb2e {
+
+constexpr int kMaxPeers = 8;
+constexpr int kDistThreads = 768;
+
+struct DistArgs {
+   TrainArgs base;                     // sampler fields (triples, hash, pr, seeds, nE, n_train) + lr, margin, distance, D, P
+   unsigned char* arena[kMaxPeers];    // arena[g] = rank g's arena as mapped into this process
+   size_t off_tab, off_dtab, off_flag, off_rel, off_drel, off_rflag, off_xbar;
+   uint32_t* local_bar;
+   int rank, world, wshift;
+   int rows_local;
+   uint32_t xbase;                     // value of every rank's cross-GPU counter when this launch starts
+};
+
+__device__ __forceinline__ float* ent_row(const DistArgs& a, size_t off, int e) {
+   const int g = e & (a.world - 1);
+   return reinterpret_cast<float*>(a.arena[g] + off) + (size_t)(e >> a.wshift) * a.base.P;
+}
+__device__ __forceinline__ uint8_t* ent_flag(const DistArgs& a, int e) {
+   return a.arena[e & (a.world - 1)] + a.off_flag + (e >> a.wshift);
+}
+
+// all CTAs of this GPU, then all GPUs, then all CTAs again (release / acquire at system scope)
+__device__ __forceinline__ void cross_barrier(const DistArgs& a, uint32_t& ltarget, uint32_t& xtarget) {
+   __threadfence_system();   // this thread's peer stores / REDs are performed before it arrives
+   grid_barrier(a.local_bar, ltarget);
+   if (blockIdx.x == 0 && threadIdx.x == 0) {
+      xtarget += (uint32_t)a.world;
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      for (int g = 0; g < a.world; g++) {
+         uint32_t* p = reinterpret_cast<uint32_t*>(a.arena[g] + a.off_xbar);
+         asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p), "r"(1u) : "memory");
+      }
+      const uint32_t* mine = reinterpret_cast<const uint32_t*>(a.arena[a.rank] + a.off_xbar);
+      uint32_t v;
+      do {
+         asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      } while ((int32_t)(v - xtarget) < 0);
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+   }
+   grid_barrier(a.local_bar, ltarget);
+}
+
+template <int LPS, int NV>
+__device__ __forceinline__ void dist_process_pair(const DistArgs& a, const Pair s, int gl, uint32_t gmask, uint8_t stamp,
+                                                  double& loss_acc, uint32_t& active_acc) {
+   const TrainArgs& b = a.base;
+   const int P = b.P, D = b.D;
+   float4 vh[NV], vt[NV], vc[NV], vr[NV];
+   load_row<LPS, NV>(ent_row(a, a.off_tab, s.h), P, gl, vh);
+   load_row<LPS, NV>(ent_row(a, a.off_tab, s.t), P, gl, vt);
+   load_row<LPS, NV>(ent_row(a, a.off_tab, s.c), P, gl, vc);
+   load_row<LPS, NV>(reinterpret_cast<float*>(a.arena[a.rank] + a.off_rel) + (size_t)s.r * P, P, gl, vr);   // local replica
+   const bool l1 = b.distance == KB2E_DISTANCE_L1;
+   float4 rp[NV], rn[NV];
+   float ep = 0.f, en = 0.f;
+#pragma unroll
+   for (int q = 0; q < NV; q++) {
+      rp[q] = (vt[q] - vh[q]) - vr[q];
+      rn[q] = s.corruptTail ? (vc[q] - vh[q]) - vr[q] : (vt[q] - vc[q]) - vr[q];
+      if (l1) { ep += abs4(rp[q]); en += abs4(rn[q]); }
+      else { ep += dot4(rp[q], rp[q]); en += dot4(rn[q], rn[q]); }
+   }
+   ep = gsum<LPS>(ep, gmask);
+   en = gsum<LPS>(en, gmask);
+   if (!(ep + b.margin > en)) return;   // common/trainer.cpp:138
+   if (gl == 0) {
+      loss_acc += (double)(b.margin + ep - en);
+      active_acc++;
+   }
+   const float lr = b.lr;
+   float4 gp[NV], gn[NV], u[NV];
+#pragma unroll
+   for (int q = 0; q < NV; q++) {
+      int idx = (q * LPS + gl) * 4;
+      if (l1) { gp[q] = lr * sign4(rp[q], idx, D); gn[q] = lr * sign4(rn[q], idx, D); }
+      else { gp[q] = (2.f * lr) * rp[q]; gn[q] = (2.f * lr) * rn[q]; }
+   }
+   float* dh = ent_row(a, a.off_dtab, s.h);
+   float* dt = ent_row(a, a.off_dtab, s.t);
+   float* dc = ent_row(a, a.off_dtab, s.c);
+   const int rg = s.r & (a.world - 1);   // owner of the relation row
+   float* dr = reinterpret_cast<float*>(a.arena[rg] + a.off_drel) + (size_t)s.r * P;
+#pragma unroll
+   for (int q = 0; q < NV; q++) u[q] = gp[q] - gn[q];
+   red_row<LPS, NV>(dr, P, gl, u);
+   if (s.corruptTail) {
+      red_row<LPS, NV>(dh, P, gl, u);
+#pragma unroll
+      for (int q = 0; q < NV; q++) u[q] = -1.f * gp[q];
+      red_row<LPS, NV>(dt, P, gl, u);
+      red_row<LPS, NV>(dc, P, gl, gn);
+   } else {
+      red_row<LPS, NV>(dh, P, gl, gp);
+#pragma unroll
+      for (int q = 0; q < NV; q++) u[q] = gn[q] - gp[q];
+      red_row<LPS, NV>(dt, P, gl, u);
+#pragma unroll
+      for (int q = 0; q < NV; q++) u[q] = -1.f * gn[q];
+      red_row<LPS, NV>(dc, P, gl, u);
+   }
+   if (gl < 3) {
+      int e = gl == 0 ? s.h : (gl == 1 ? s.t : s.c);
+      *ent_flag(a, e) = stamp;
+   } else if (gl == 3) {
+      *(a.arena[rg] + a.off_rflag + s.r) = stamp;
+   }
+}
+
+template <int LPS, int NV>
+__global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __grid_constant__ DistArgs a) {
+   __shared__ double s_loss[kDistThreads / 32];
+   const TrainArgs& b = a.base;
+   const int lane = threadIdx.x & 31;
+   const int gl = lane % LPS;
+   const uint32_t gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << ((lane / LPS) * LPS));
+   const int groups_per_block = blockDim.x / LPS;
+   const long long G = (long long)gridDim.x * groups_per_block;
+   const long long g0 = (long long)(threadIdx.x / LPS) * gridDim.x + blockIdx.x;
+   const int P = b.P;
+   unsigned char* me = a.arena[a.rank];
+   float* tab = reinterpret_cast<float*>(me + a.off_tab);
+   float* dtab = reinterpret_cast<float*>(me + a.off_dtab);
+   uint8_t* flag = me + a.off_flag;
+   float* drel = reinterpret_cast<float*>(me + a.off_drel);
+   uint8_t* rflag = me + a.off_rflag;
+   // this rank's share of a batch: global samples k = rank, rank + world, ...
+   const long long my_count = (b.batchsize - a.rank + a.world - 1) >> a.wshift;
+   uint32_t ltarget = 0, xtarget = a.xbase;
+   uint32_t active_acc = 0, tent_acc = 0, trel_acc = 0;
+   const uint32_t gb_first = (uint32_t)b.first_epoch * (uint32_t)b.batches;
+   Pair pre;
+   const bool has_first = g0 < my_count;
+   if (has_first) pre = draw_pair(b, (uint32_t)(g0 * a.world + a.rank), gb_first);
+   // peers may still be zeroing / publishing from the previous launch
+   cross_barrier(a, ltarget, xtarget);
+
+   for (int ep = 0; ep < b.n_epochs; ep++) {
+      double loss_acc = 0.0;
+      for (int batch = 0; batch < b.batches; batch++) {
+         const uint32_t gb = gb_first + (uint32_t)ep * (uint32_t)b.batches + (uint32_t)batch;
+         const uint8_t stamp = (uint8_t)(gb % 255u + 1u);
+         // ---- phase 1 ----
+         if (has_first) dist_process_pair<LPS, NV>(a, pre, gl, gmask, stamp, loss_acc, active_acc);
+         for (long long j = g0 + G; j < my_count; j += G) {
+            Pair s = draw_pair(b, (uint32_t)(j * a.world + a.rank), gb);
+            dist_process_pair<LPS, NV>(a, s, gl, gmask, stamp, loss_acc, active_acc);
+         }
+         cross_barrier(a, ltarget, xtarget);
+         // ---- phase 2: own entity rows ----
+         for (long long row = g0; row < a.rows_local; row += G) {
+            if (__ldcg(flag + row) != stamp) continue;
+            float4 x[NV], d[NV];
+            load_row<LPS, NV>(tab + (size_t)row * P, P, gl, x);
+            load_row<LPS, NV>(dtab + (size_t)row * P, P, gl, d);
+#pragma unroll
+            for (int q = 0; q < NV; q++) { x[q] = x[q] + d[q]; d[q] = f4(0.f); }
+            store_row<LPS, NV>(dtab + (size_t)row * P, P, gl, d);
+            norm_row<LPS, NV>(x, true, gmask);   // transe/trainer.cpp:44-45
+            store_row<LPS, NV>(tab + (size_t)row * P, P, gl, x);
+            tent_acc += (gl == 0);
+         }
+         // ---- phase 2: relation rows owned by this rank -> every replica ----
+         for (long long r = (long long)a.rank + g0 * a.world; r < b.nR; r += G * a.world) {
+            if (__ldcg(rflag + r) != stamp) continue;
+            float4 x[NV], d[NV];
+            load_row<LPS, NV>(reinterpret_cast<float*>(me + a.off_rel) + (size_t)r * P, P, gl, x);
+            load_row<LPS, NV>(drel + (size_t)r * P, P, gl, d);
+#pragma unroll
+            for (int q = 0; q < NV; q++) { x[q] = x[q] + d[q]; d[q] = f4(0.f); }
+            store_row<LPS, NV>(drel + (size_t)r * P, P, gl, d);
+            norm_row<LPS, NV>(x, true, gmask);   // transe/trainer.cpp:43
+            for (int g = 0; g < a.world; g++)
+               store_row<LPS, NV>(reinterpret_cast<float*>(a.arena[g] + a.off_rel) + (size_t)r * P, P, gl, x);
+            trel_acc += (gl == 0);
+         }
+         if (has_first && !(ep == b.n_epochs - 1 && batch == b.batches - 1))
+            pre = draw_pair(b, (uint32_t)(g0 * a.world + a.rank), gb + 1u);
+         cross_barrier(a, ltarget, xtarget);
+      }
+      double v = (gl == 0) ? loss_acc : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_loss[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+         double t = 0.0;
+         for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += s_loss[i];
+         if (t != 0.0) atomicAdd(b.loss + ep, t);
+      }
+      __syncthreads();
+   }
+   uint32_t c0 = (gl == 0) ? active_acc : 0u, c1 = tent_acc, c2 = trel_acc;
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+   }
+   if (lane == 0) {
+      if (c0) atomicAdd(b.counters + 0, (unsigned long long)c0);
+      if (c1) atomicAdd(b.counters + 1, (unsigned long long)c1);
+      if (c2) atomicAdd(b.counters + 2, (unsigned long long)c2);
+   }
+}
+
+// init: N(0, (1/D)^2) keyed by the GLOBAL row id, so every world size starts from the same tables
+__global__ void dist_init_kernel(float* tab, long long rows_local, int rank, int world, int D, int P, uint32_t k0, uint32_t k1) {
+   long long lrow = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   int lane = threadIdx.x & 31;
+   if (lrow >= rows_local) return;
+   long long row = lrow * world + rank;
+   float* p = tab + lrow * P;
+   float s2 = 0.f;
+   const float sigma = 1.0f / (float)D;
+   for (int base = lane * 4; base < P; base += 128) {
+      uint32_t x[4];
+      philox4x32((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)base, 1u, k0, k1, x);
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+         float u1 = ((float)x[2 * q] + 1.0f) * 2.3283064e-10f;
+         float u2 = (float)x[2 * q + 1] * 2.3283064e-10f;
+         float rad = sqrtf(-2.0f * logf(u1));
+         v[2 * q] = rad * cospif(2.0f * u2) * sigma;
+         v[2 * q + 1] = rad * sinpif(2.0f * u2) * sigma;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+         if (base + q >= D) v[q] = 0.f;
+         s2 += v[q] * v[q];
+      }
+      *reinterpret_cast<float4*>(p + base) = make_float4(v[0], v[1], v[2], v[3]);
+   }
+   s2 = gsum<32>(s2, 0xffffffffu);
+   float len = sqrtf(s2);
+   __syncwarp();
+   if (len > 1.f) {
+      for (int base = lane * 4; base < P; base += 128) {
+         float4 v = *reinterpret_cast<float4*>(p + base);
+         *reinterpret_cast<float4*>(p + base) = make_float4(v.x / len, v.y / len, v.z / len, v.w / len);
+      }
+   }
+}
+
+__global__ void dist_widen_kernel(const float* src, double* dst, long long rows, int D, int P) {
+   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < rows * D) dst[i] = (double)src[(i / D) * P + (i % D)];
+}
+__global__ void dist_narrow_kernel(const double* src, float* dst, long long rows, int D, int P) {
+   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= rows * P) return;
+   int c = (int)(i % P);
+   dst[i] = c < D ? (float)src[(i / P) * D + c] : 0.f;
+}
+
+}  // namespace kb2e
+
+using namespace kb2e;
+
+struct DistState {
+   int rank = 0, world = 1, wshift = 0;
+   long long rows_local = 0;
+   unsigned char* arena = nullptr;
+   size_t arena_bytes = 0;
+   size_t off_tab = 0, off_dtab = 0, off_flag = 0, off_rel = 0, off_drel = 0, off_rflag = 0, off_xbar = 0;
+   unsigned char* peers[kMaxPeers] = {};
+   bool connected = false;
+   uint32_t xcount = 0;   // cross-GPU barrier arrivals so far (identical on every rank: the counters are never reset)
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline unsigned dblocks(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+extern "C" {
+
+int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) {
+   if (!c || !handle_out) return KB2E_ERR_ARG;
+   KB2E_CUDA(c, cudaSetDevice(c->device));
+   if (c->cfg.model != KB2E_MODEL_TRANSE) return fail(c, KB2E_ERR_LIMIT, "partitioned training is built for TransE");
+   if (world < 1 || world > kMaxPeers || (world & (world - 1)) || rank < 0 || rank >= world)
+      return fail(c, KB2E_ERR_ARG, "kb2e_dist_setup: world must be 1, 2, 4 or 8 and 0 <= rank < world");
+   int rc = train_alloc(c);   // barrier counter, counters, pr
+   if (rc) return rc;
+   DistState* d = new DistState();
+   d->rank = rank; d->world = world;
+   while ((1 << d->wshift) < world) d->wshift++;
+   d->rows_local = ((long long)c->nE - rank + world - 1) / world;
+   const size_t tab_bytes = (size_t)d->rows_local * c->P * sizeof(float);
+   const size_t rel_bytes = (size_t)c->nR * c->P * sizeof(float);
+   size_t off = 0;
+   d->off_tab = off; off = align_up(off + tab_bytes, 256);
+   d->off_dtab = off; off = align_up(off + tab_bytes, 256);
+   d->off_flag = off; off = align_up(off + (size_t)d->rows_local, 256);
+   d->off_rel = off; off = align_up(off + rel_bytes, 256);
+   d->off_drel = off; off = align_up(off + rel_bytes, 256);
+   d->off_rflag = off; off = align_up(off + (size_t)c->nR, 256);
+   d->off_xbar = off; off = align_up(off + 64, 256);
+   d->arena_bytes = off;
+   KB2E_CUDA(c, cudaMalloc(&d->arena, d->arena_bytes));
+   KB2E_CUDA(c, cudaMemset(d->arena, 0, d->arena_bytes));
+   cudaIpcMemHandle_t h;
+   KB2E_CUDA(c, cudaIpcGetMemHandle(&h, d->arena));
+   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+   memcpy(handle_out, &h, sizeof(h));
+   delete c->dist;
+   c->dist = d;
+   return KB2E_OK;
+}
+
+int kb2e_dist_connect(kb2e_ctx* c, const void* handles) {
+   if (!c || !c->dist || !handles) return KB2E_ERR_ARG;
+   KB2E_CUDA(c, cudaSetDevice(c->device));
+   DistState* d = c->dist;
+   for (int g = 0; g < d->world; g++) {
+      if (g == d->rank) { d->peers[g] = d->arena; continue; }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const unsigned char*)handles + 64 * g, sizeof(h));
+      void* p = nullptr;
+      KB2E_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      d->peers[g] = (unsigned char*)p;
+   }
+   d->connected = true;
+   return KB2E_OK;
+}
+
+int kb2e_dist_init_embeddings(kb2e_ctx* c) {
+   if (!c || !c->dist) return KB2E_ERR_ARG;
+   KB2E_CUDA(c, cudaSetDevice(c->device));
+   DistState* d = c->dist;
+   uint32_t k0 = (uint32_t)c->cfg.seed, k1 = (uint32_t)(c->cfg.seed >> 32);
+   dist_init_kernel<<<dblocks(d->rows_local * 32, 256), 256, 0, c->stream>>>(
+      reinterpret_cast<float*>(d->arena + d->off_tab), d->rows_local, d->rank, d->world, c->D, c->P, k0, k1);
+   // relation replica: rows nE .. nE+nR-1 of the global row space, identical on every rank
+   dist_init_kernel<<<dblocks((long long)c->nR * 32, 256), 256, 0, c->stream>>>(
+      reinterpret_cast<float*>(d->arena + d->off_rel) - (size_t)0, c->nR, 0, 1, c->D, c->P, k0 ^ 0x9e3779b9u, k1);
+   KB2E_CUDA(c, cudaGetLastError());
+   KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   return KB2E_OK;
+}
+
+// table: KB2E_TABLE_ENTITY -> this rank's rows (global ids rank, rank+world, ...), [rows_local][dim];
+//        KB2E_TABLE_RELATION -> the replica, [num_relations][dim]
+static int dist_copy(kb2e_ctx* c, int table, double* host, const double* host_in, int64_t rows, int64_t cols) {
+   if (!c || !c->dist) return KB2E_ERR_ARG;
+   KB2E_CUDA(c, cudaSetDevice(c->device));
+   DistState* d = c->dist;
+   const long long want = table == KB2E_TABLE_ENTITY ? d->rows_local : c->nR;
+   if (table != KB2E_TABLE_ENTITY && table != KB2E_TABLE_RELATION) return fail(c, KB2E_ERR_ARG, "kb2e_dist: unknown table");
+   if (rows != want || cols != c->D) return fail(c, KB2E_ERR_ARG, "kb2e_dist: shape mismatch");
+   float* dev32 = reinterpret_cast<float*>(d->arena + (table == KB2E_TABLE_ENTITY ? d->off_tab : d->off_rel));
+   double* tmp = nullptr;
+   KB2E_CUDA(c, cudaMalloc(&tmp, (size_t)rows * cols * sizeof(double)));
+   if (host_in) {
+      KB2E_CUDA(c, cudaMemcpyAsync(tmp, host_in, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      dist_narrow_kernel<<<dblocks(rows * c->P, 256), 256, 0, c->stream>>>(tmp, dev32, rows, c->D, c->P);
+   } else {
+      dist_widen_kernel<<<dblocks(rows * c->D, 256), 256, 0, c->stream>>>(dev32, tmp, rows, c->D, c->P);
+      KB2E_CUDA(c, cudaMemcpyAsync(host, tmp, (size_t)rows * cols * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   }
+   KB2E_CUDA(c, cudaGetLastError());
+   KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   cudaFree(tmp);
+   return KB2E_OK;
+}
+
+int kb2e_dist_upload(kb2e_ctx* c, int table, const double* host, int64_t rows, int64_t cols) {
+   return host ? dist_copy(c, table, nullptr, host, rows, cols) : KB2E_ERR_ARG;
+}
+int kb2e_dist_download(kb2e_ctx* c, int table, double* host, int64_t rows, int64_t cols) {
+   return host ? dist_copy(c, table, host, nullptr, rows, cols) : KB2E_ERR_ARG;
+}
+
+int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, double* loss_per_epoch) {
+   if (!c || !c->dist) return KB2E_ERR_ARG;
+   KB2E_CUDA(c, cudaSetDevice(c->device));
+   DistState* d = c->dist;
+   if (!d->connected) return fail(c, KB2E_ERR_ARG, "kb2e_dist_train_epochs: call kb2e_dist_connect first");
+   if (!c->triples || c->n_train == 0 || !c->have_pr) return fail(c, KB2E_ERR_ARG, "kb2e_dist_train_epochs: set the train triples and bern statistics first");
+   if (n_epochs <= 0) return KB2E_OK;
+   if (n_epochs > c->loss_cap) {
+      cudaFree(c->loss_dev);
+      KB2E_CUDA(c, cudaMalloc(&c->loss_dev, (size_t)n_epochs * sizeof(double)));
+      c->loss_cap = n_epochs;
+   }
+   DistArgs a;
+   memset(&a, 0, sizeof(a));
+   TrainArgs& b = a.base;
+   b.triples = c->triples; b.hash = c->hash; b.hash_mask = c->hash_mask; b.pr = c->pr;
+   b.loss = c->loss_dev; b.counters = c->counters;
+   b.n_train = c->n_train;
+   b.batchsize = c->n_train / c->cfg.batches;
+   b.nE = c->nE; b.nR = c->nR; b.D = c->D; b.P = c->P;
+   b.batches = c->cfg.batches; b.first_epoch = first_epoch; b.n_epochs = n_epochs; b.distance = c->cfg.distance;
+   b.lr = (float)c->cfg.rate; b.margin = (float)c->cfg.margin;
+   b.seed_lo = (uint32_t)c->cfg.seed; b.seed_hi = (uint32_t)(c->cfg.seed >> 32);
+   for (int g = 0; g < d->world; g++) a.arena[g] = d->peers[g];
+   a.off_tab = d->off_tab; a.off_dtab = d->off_dtab; a.off_flag = d->off_flag; a.off_rel = d->off_rel;
+   a.off_drel = d->off_drel; a.off_rflag = d->off_rflag; a.off_xbar = d->off_xbar;
+   a.local_bar = c->barrier;
+   a.rank = d->rank; a.world = d->world; a.wshift = d->wshift; a.rows_local = (int)d->rows_local;
+   // shape: same rule as the single-GPU kernel, on this rank's share of the batch
+   const int vecs = (c->P + 3) / 4;
+   int lps = vecs <= 16 ? 16 : 32;
+   int nv = (vecs + lps - 1) / lps;
+   nv = nv <= 1 ? 1 : (nv <= 2 ? 2 : 99);
+   void (*k)(const DistArgs) = nullptr;
+   if (lps == 16 && nv == 1) k = train_dist_kernel<16, 1>;
+   else if (lps == 32 && nv == 1) k = train_dist_kernel<32, 1>;
+   else if (lps == 32 && nv == 2) k = train_dist_kernel<32, 2>;
+   if (!k) return fail(c, KB2E_ERR_LIMIT, "partitioned training supports embedding sizes up to 256");
+   // the peer-mapped cross-GPU counters are monotonic across launches (a reset could wipe a fast peer's
+   // arrival); every rank runs the same barrier sequence, so the start value is known on the host
+   a.xbase = d->xcount;
+   d->xcount += (uint32_t)d->world * (1u + 2u * (uint32_t)c->cfg.batches * (uint32_t)n_epochs);
+   KB2E_CUDA(c, cudaMemsetAsync(c->barrier, 0, 64, c->stream));
+   KB2E_CUDA(c, cudaMemsetAsync(c->loss_dev, 0, (size_t)n_epochs * sizeof(double), c->stream));
+   KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   void* params[] = {&a};
+   KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+   KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(kDistThreads), params, 0, c->stream));
+   KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+   std::vector<double> loss(n_epochs);
+   unsigned long long cnt[3];
+   KB2E_CUDA(c, cudaMemcpyAsync(loss.data(), c->loss_dev, (size_t)n_epochs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   KB2E_CUDA(c, cudaMemcpyAsync(cnt, c->counters, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+   KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   float ms = 0.f;
+   KB2E_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+   c->tstats.kernel_ms += ms;
+   c->tstats.launches += 1;
+   const long long my = (b.batchsize - d->rank + d->world - 1) / d->world;
+   c->tstats.samples += (uint64_t)my * (uint64_t)b.batches * (uint64_t)n_epochs;
+   c->tstats.active = cnt[0];
+   c->tstats.touched_ent = cnt[1];
+   c->tstats.touched_rel = cnt[2];
+   if (loss_per_epoch) memcpy(loss_per_epoch, loss.data(), (size_t)n_epochs * sizeof(double));
+   return KB2E_OK;
+}
+
+void kb2e_dist_teardown(kb2e_ctx* c) {
+   if (!c || !c->dist) return;
+   cudaSetDevice(c->device);
+   DistState* d = c->dist;
+   for (int g = 0; g < d->world; g++)
+      if (g != d->rank && d->peers[g]) cudaIpcCloseMemHandle(d->peers[g]);
+   cudaFree(d->arena);
+   delete d;
+   c->dist = nullptr;
+}
+
+}  // extern "C"

@@ -17,6 +17,8 @@ SHAPES = {
     # name: (entities, relations, train, valid, test, zipf)
     "fb15k": (14951, 1345, 483142, 50000, 59071, True),
     "wn18": (40943, 18, 141442, 5000, 5000, False),
+    # throughput-only shape of BASELINE configs[4]; the reference cannot run it
+    "scaled": (4_000_000, 1345, 100_000_000, 10_000, 10_000, True),
     "tiny": (500, 12, 6000, 300, 300, True),
     "small": (2000, 20, 40000, 1000, 1000, True),
 }

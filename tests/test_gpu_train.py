@@ -206,3 +206,34 @@ def test_error_paths(gpu_lib):
         ctx.init_embeddings()
         with pytest.raises(kb2e_b200.Kb2eError):
             ctx.train_epochs(0, 1)  # no triples
+
+
+def test_partitioned_kernel_world1_matches_single_gpu_kernel(gpu_lib):
+    """The entity-partitioned kernel (train_dist.cu) run with world = 1 -- every "peer" pointer is the local
+    arena -- must reproduce the single-GPU kernel: same sampler, same deferred semantics.  (The 2-GPU run of
+    the same check is tools/dist_check.py under torchrun; its output is kept in profiles/.)"""
+    from kb2e_b200 import kg, TABLE_ENTITY, TABLE_RELATION
+    from kb2e_b200.partitioned import PartitionedTrainer
+    g = kg.make_kg("tiny", seed=9)
+    nE, nR, D, batches, seed = g["nE"], g["nR"], 24, 10, 31
+    rng = np.random.default_rng(0)
+    ent = f32(rng.normal(0, 1.0 / D, (nE, D)))
+    rel = f32(rng.normal(0, 1.0 / D, (nR, D)))
+    hm, tm = kg.bern_stats(g["train"], nR)
+    cfg = dict(method=1, distance=1, batches=batches, rate=LR, margin=1.0, seed=seed)
+    with make_ctx("transe", D, nE, nR, **cfg) as ctx:
+        ctx.set_train_triples(g["train"])
+        ctx.set_bern(hm, tm)
+        upload_tables(ctx, ent, rel, None)
+        loss1 = ctx.train_epochs(0, 3)
+        e1, r1, _ = download_tables(ctx)
+    pt = PartitionedTrainer(D, nE, nR, 0, 1, 0, **cfg)
+    pt.set_training_set(g["train"], hm, tm)
+    pt.upload_global(ent, rel)
+    loss2 = pt.train_epochs(0, 2)
+    loss2 = np.concatenate([loss2, pt.train_epochs(2, 1)])   # a second launch continues the barrier counters
+    e2, r2 = pt.gather_global()
+    pt.close()
+    assert np.allclose(loss1, loss2, rtol=1e-4)
+    assert np.abs(e1 - e2).max() < 5e-3 and np.abs(e1 - e2).mean() < 2e-5
+    assert np.abs(r1 - r2).max() < 5e-3

@@ -27,7 +27,8 @@ nE, nR, ntr, nva, nte, _ = kg.SHAPES[args.shape]
 t0 = time.time()
 if args.random:
     rng = np.random.default_rng(0)
-    mk = lambda n: np.stack([rng.integers(0, nE, n), rng.integers(0, nE, n), rng.integers(0, nR, n)], 1).astype(np.int32)
+    mk = lambda n: np.stack([rng.integers(0, nE, n, dtype=np.int32), rng.integers(0, nE, n, dtype=np.int32),
+                             rng.integers(0, nR, n, dtype=np.int32)], 1)
     g = {"nE": nE, "nR": nR, "train": mk(ntr), "valid": mk(nva), "test": mk(nte)}
 else:
     g = kg.make_kg(args.shape, seed=0)
@@ -36,11 +37,11 @@ with kb2e_b200.Context(args.model, args.dim, nE, nR, method=args.method, distanc
                        rate=0.01, margin=1.0, seed=1) as ctx:
     t0 = time.time()
     ctx.set_train_triples(g["train"])
-    ctx.set_bern(*kg.bern_stats(g["train"], nR))
+    ctx.set_bern(*(kg.bern_stats(g["train"], nR) if args.method == 1 else (None, None)))
     ctx.init_embeddings()
     print("setup %.3fs" % (time.time() - t0), flush=True)
     done = 0
-    for chunk in (1, 1, args.epochs, args.epochs):
+    for chunk in ((1, 1, args.epochs, args.epochs) if args.shape != "scaled" else (1, args.epochs)):
         s0 = ctx.train_stats()
         t0 = time.time()
         loss = ctx.train_epochs(done, chunk)
