@@ -444,46 +444,40 @@ template <int MODEL, int LPS, int NV>
 __device__ __forceinline__ void publish_rows(const TrainArgs& a, long long row_begin, long long row_end, long long g0, long long G,
                                              uint8_t stamp, uint8_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel) {
    const int P = a.P;
-   for (long long base = row_begin + g0; base < row_end; base += 2 * G) {
-      const long long r0 = base, r1 = base + G;
-      bool f0 = __ldcg(a.flag + r0) == stamp;
-      bool f1 = r1 < row_end && __ldcg(a.flag + r1) == stamp;
-      bool own0 = f0, own1 = f1;
-      if (MODEL == KB2E_MODEL_TRANSR && !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK)) {
-         // transr/trainer.cpp:187: entity row e is also visited when RELATION e was touched
-         if (r0 < a.nE && r0 < a.nR) f0 = f0 || __ldcg(a.flag + a.nE + r0) == stamp;
-         if (r1 < row_end && r1 < a.nE && r1 < a.nR) f1 = f1 || __ldcg(a.flag + a.nE + r1) == stamp;
+   const int lane = threadIdx.x & 31;
+   const bool quirk = MODEL == KB2E_MODEL_TRANSR && !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK);
+   long long first, end;
+   group_range(row_begin, row_end, g0, G, first, end);
+   auto stamped = [&](long long r) {
+      bool f = __ldcg(a.flag + r) == stamp;
+      // transr/trainer.cpp:187: entity row e is also visited when RELATION e was touched
+      if (quirk && r < a.nE && r < a.nR) f = f || __ldcg(a.flag + a.nE + r) == stamp;
+      return f;
+   };
+   auto finish = [&](long long r, float4 (&x)[NV], float4 (&d)[NV]) {
+      if constexpr (MODEL == KB2E_MODEL_TRANSR) {
+         if (r >= a.nE) { finish_relation_transr(a, (int)(r - a.nE), gl, x[0], d[0]); trel += (gl == 0); }
+         else {
+            const bool own = __ldcg(a.flag + r) == stamp;
+            finish_entity_transr(a, (int)r, gl, stamp, next_stamp, own, x[0], d[0]);
+            tent += (gl == 0 && own);
+         }
+      } else {
+         if (r >= a.nE) { finish_relation<MODEL, LPS, NV>(a, (int)(r - a.nE), gl, gmask, x, d); trel += (gl == 0); }
+         else { finish_entity<MODEL, LPS, NV>(a, (int)r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
       }
+   };
+   for_stamped_rows<LPS>(first, end, gl, gmask, lane, stamped, [&](long long r0, long long r1) {
       float4 x0[NV], d0[NV], x1[NV], d1[NV];
-      if (f0) {
-         load_row<LPS, NV>(a.tab + (size_t)r0 * P, P, gl, x0);
-         load_row<LPS, NV>(a.dtab + (size_t)r0 * P, P, gl, d0);
-      }
-      if (f1) {
+      load_row<LPS, NV>(a.tab + (size_t)r0 * P, P, gl, x0);
+      load_row<LPS, NV>(a.dtab + (size_t)r0 * P, P, gl, d0);
+      if (r1 >= 0) {
          load_row<LPS, NV>(a.tab + (size_t)r1 * P, P, gl, x1);
          load_row<LPS, NV>(a.dtab + (size_t)r1 * P, P, gl, d1);
       }
-      if constexpr (MODEL == KB2E_MODEL_TRANSR) {
-         if (f0) {
-            if (r0 >= a.nE) { finish_relation_transr(a, (int)(r0 - a.nE), gl, x0[0], d0[0]); trel += (gl == 0); }
-            else { finish_entity_transr(a, (int)r0, gl, stamp, next_stamp, own0, x0[0], d0[0]); tent += (gl == 0 && own0); }
-         }
-         if (f1) {
-            if (r1 >= a.nE) { finish_relation_transr(a, (int)(r1 - a.nE), gl, x1[0], d1[0]); trel += (gl == 0); }
-            else { finish_entity_transr(a, (int)r1, gl, stamp, next_stamp, own1, x1[0], d1[0]); tent += (gl == 0 && own1); }
-         }
-      } else {
-         (void)own0; (void)own1;
-         if (f0) {
-            if (r0 >= a.nE) { finish_relation<MODEL, LPS, NV>(a, (int)(r0 - a.nE), gl, gmask, x0, d0); trel += (gl == 0); }
-            else { finish_entity<MODEL, LPS, NV>(a, (int)r0, gl, gmask, next_stamp, x0, d0); tent += (gl == 0); }
-         }
-         if (f1) {
-            if (r1 >= a.nE) { finish_relation<MODEL, LPS, NV>(a, (int)(r1 - a.nE), gl, gmask, x1, d1); trel += (gl == 0); }
-            else { finish_entity<MODEL, LPS, NV>(a, (int)r1, gl, gmask, next_stamp, x1, d1); tent += (gl == 0); }
-         }
-      }
-   }
+      finish(r0, x0, d0);
+      if (r1 >= 0) finish(r1, x1, d1);
+   });
 }
 
 template <int MODEL, int LPS, int NV, int THREADS>

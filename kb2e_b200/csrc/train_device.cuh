@@ -198,4 +198,37 @@ __device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32
    return s;
 }
 
+
+// ---- phase-2 row walk ------------------------------------------------------------------------------
+// Every group owns a contiguous range of rows.  The stamps of LPS rows are fetched with one coalesced
+// load per lane and turned into a bit mask by a ballot, then the stamped rows are handed to `body` two
+// at a time (r1 = -1 when only one is left) so that the loads of both rows are in flight together and
+// no row waits on its own stamp load.  `stamped(row)` decides whether a row was touched in this batch.
+template <int LPS, typename Pred, typename Body>
+__device__ __forceinline__ void for_stamped_rows(long long first, long long end, int gl, uint32_t gmask, int lane,
+                                                 Pred&& stamped, Body&& body) {
+   const int gshift = (lane / LPS) * LPS;
+   for (long long base = first; base < end; base += LPS) {
+      const long long r = base + gl;
+      const bool f = r < end && stamped(r);
+      uint32_t m = (__ballot_sync(gmask, f) >> gshift) & (LPS == 32 ? 0xffffffffu : ((1u << LPS) - 1u));
+      while (m) {
+         const int b0 = __ffs(m) - 1;
+         m &= m - 1;
+         int b1 = -1;
+         if (m) { b1 = __ffs(m) - 1; m &= m - 1; }
+         body(base + b0, b1 >= 0 ? base + b1 : -1ll);
+      }
+   }
+}
+
+// this group's contiguous share of [row_begin, row_end) when the rows are dealt to G groups
+__device__ __forceinline__ void group_range(long long row_begin, long long row_end, long long g0, long long G,
+                                            long long& first, long long& end) {
+   const long long per = (row_end - row_begin + G - 1) / G;
+   first = row_begin + g0 * per;
+   end = first + per < row_end ? first + per : row_end;
+   if (first > row_end) first = row_end;
+}
+
 }  // namespace kb2e

@@ -18,7 +18,9 @@
 // renormalisation), so results agree up to the order of float atomics.
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -38,13 +40,16 @@ struct DistArgs {
    int rank, world, wshift;
    int rows_local;
    uint32_t xbase;                     // value of every rank's cross-GPU counter when this launch starts
+   int debug;                          // tuning aid (KB2E_DIST_DEBUG bits): 1 entity REDs local, 2 entity loads local, 4 relation REDs local, 8 flags local
 };
 
 __device__ __forceinline__ float* ent_row(const DistArgs& a, size_t off, int e) {
-   const int g = e & (a.world - 1);
+   int g = e & (a.world - 1);
+   if (((a.debug & 1) && off == a.off_dtab) || ((a.debug & 2) && off == a.off_tab)) g = a.rank;   // tuning aid only
    return reinterpret_cast<float*>(a.arena[g] + off) + (size_t)(e >> a.wshift) * a.base.P;
 }
 __device__ __forceinline__ uint8_t* ent_flag(const DistArgs& a, int e) {
+   if (a.debug & 8) return a.arena[a.rank] + a.off_flag + (e >> a.wshift);
    return a.arena[e & (a.world - 1)] + a.off_flag + (e >> a.wshift);
 }
 
@@ -107,7 +112,7 @@ __device__ __forceinline__ void dist_process_pair(const DistArgs& a, const Pair 
    float* dh = ent_row(a, a.off_dtab, s.h);
    float* dt = ent_row(a, a.off_dtab, s.t);
    float* dc = ent_row(a, a.off_dtab, s.c);
-   const int rg = s.r & (a.world - 1);   // owner of the relation row
+   const int rg = (a.debug & 4) ? a.rank : (s.r & (a.world - 1));   // owner of the relation row
    float* dr = reinterpret_cast<float*>(a.arena[rg] + a.off_drel) + (size_t)s.r * P;
 #pragma unroll
    for (int q = 0; q < NV; q++) u[q] = gp[q] - gn[q];
@@ -156,6 +161,13 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
    const long long my_count = (b.batchsize - a.rank + a.world - 1) >> a.wshift;
    uint32_t ltarget = 0, xtarget = a.xbase;
    uint32_t active_acc = 0, tent_acc = 0, trel_acc = 0;
+   int trace_slot = 0;
+#define KB2E_DTRACE()                                                                                 \
+   if (b.trace != nullptr && threadIdx.x == 0 && trace_slot < kTraceSlots) {                          \
+      unsigned long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+      b.trace[(size_t)blockIdx.x * kTraceSlots + trace_slot++] = t_;                                  \
+   }
    const uint32_t gb_first = (uint32_t)b.first_epoch * (uint32_t)b.batches;
    Pair pre;
    const bool has_first = g0 < my_count;
@@ -168,26 +180,46 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
       for (int batch = 0; batch < b.batches; batch++) {
          const uint32_t gb = gb_first + (uint32_t)ep * (uint32_t)b.batches + (uint32_t)batch;
          const uint8_t stamp = (uint8_t)(gb % 255u + 1u);
+         KB2E_DTRACE();
          // ---- phase 1 ----
          if (has_first) dist_process_pair<LPS, NV>(a, pre, gl, gmask, stamp, loss_acc, active_acc);
          for (long long j = g0 + G; j < my_count; j += G) {
             Pair s = draw_pair(b, (uint32_t)(j * a.world + a.rank), gb);
             dist_process_pair<LPS, NV>(a, s, gl, gmask, stamp, loss_acc, active_acc);
          }
+         KB2E_DTRACE();
          cross_barrier(a, ltarget, xtarget);
+         KB2E_DTRACE();
          // ---- phase 2: own entity rows ----
-         for (long long row = g0; row < a.rows_local; row += G) {
-            if (__ldcg(flag + row) != stamp) continue;
-            float4 x[NV], d[NV];
-            load_row<LPS, NV>(tab + (size_t)row * P, P, gl, x);
-            load_row<LPS, NV>(dtab + (size_t)row * P, P, gl, d);
+         {
+            long long first, end;
+            group_range(0, a.rows_local, g0, G, first, end);
+            for_stamped_rows<LPS>(first, end, gl, gmask, lane, [&](long long r) { return __ldcg(flag + r) == stamp; },
+                                  [&](long long r0, long long r1) {
+               float4 x0[NV], d0[NV], x1[NV], d1[NV];
+               load_row<LPS, NV>(tab + (size_t)r0 * P, P, gl, x0);
+               load_row<LPS, NV>(dtab + (size_t)r0 * P, P, gl, d0);
+               if (r1 >= 0) {
+                  load_row<LPS, NV>(tab + (size_t)r1 * P, P, gl, x1);
+                  load_row<LPS, NV>(dtab + (size_t)r1 * P, P, gl, d1);
+               }
 #pragma unroll
-            for (int q = 0; q < NV; q++) { x[q] = x[q] + d[q]; d[q] = f4(0.f); }
-            store_row<LPS, NV>(dtab + (size_t)row * P, P, gl, d);
-            norm_row<LPS, NV>(x, true, gmask);   // transe/trainer.cpp:44-45
-            store_row<LPS, NV>(tab + (size_t)row * P, P, gl, x);
-            tent_acc += (gl == 0);
+               for (int q = 0; q < NV; q++) { x0[q] = x0[q] + d0[q]; d0[q] = f4(0.f); }
+               store_row<LPS, NV>(dtab + (size_t)r0 * P, P, gl, d0);
+               norm_row<LPS, NV>(x0, true, gmask);   // transe/trainer.cpp:44-45
+               store_row<LPS, NV>(tab + (size_t)r0 * P, P, gl, x0);
+               tent_acc += (gl == 0);
+               if (r1 >= 0) {
+#pragma unroll
+                  for (int q = 0; q < NV; q++) { x1[q] = x1[q] + d1[q]; d1[q] = f4(0.f); }
+                  store_row<LPS, NV>(dtab + (size_t)r1 * P, P, gl, d1);
+                  norm_row<LPS, NV>(x1, true, gmask);
+                  store_row<LPS, NV>(tab + (size_t)r1 * P, P, gl, x1);
+                  tent_acc += (gl == 0);
+               }
+            });
          }
+         KB2E_DTRACE();
          // ---- phase 2: relation rows owned by this rank -> every replica ----
          for (long long r = (long long)a.rank + g0 * a.world; r < b.nR; r += G * a.world) {
             if (__ldcg(rflag + r) != stamp) continue;
@@ -204,6 +236,7 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
          }
          if (has_first && !(ep == b.n_epochs - 1 && batch == b.batches - 1))
             pre = draw_pair(b, (uint32_t)(g0 * a.world + a.rank), gb + 1u);
+         KB2E_DTRACE();
          cross_barrier(a, ltarget, xtarget);
       }
       double v = (gl == 0) ? loss_acc : 0.0;
@@ -427,6 +460,7 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    a.off_drel = d->off_drel; a.off_rflag = d->off_rflag; a.off_xbar = d->off_xbar;
    a.local_bar = c->barrier;
    a.rank = d->rank; a.world = d->world; a.wshift = d->wshift; a.rows_local = (int)d->rows_local;
+   a.debug = getenv("KB2E_DIST_DEBUG") ? atoi(getenv("KB2E_DIST_DEBUG")) : 0;
    // shape: same rule as the single-GPU kernel, on this rank's share of the batch
    const int vecs = (c->P + 3) / 4;
    int lps = vecs <= 16 ? 16 : 32;
@@ -444,6 +478,13 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    KB2E_CUDA(c, cudaMemsetAsync(c->barrier, 0, 64, c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->loss_dev, 0, (size_t)n_epochs * sizeof(double), c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   const char* trace_path = getenv("KB2E_TRAIN_TRACE");
+   unsigned long long* trace_dev = nullptr;
+   if (trace_path) {
+      KB2E_CUDA(c, cudaMalloc(&trace_dev, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long)));
+      KB2E_CUDA(c, cudaMemset(trace_dev, 0, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long)));
+      a.base.trace = trace_dev;
+   }
    void* params[] = {&a};
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
    KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(kDistThreads), params, 0, c->stream));
@@ -453,6 +494,17 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    KB2E_CUDA(c, cudaMemcpyAsync(loss.data(), c->loss_dev, (size_t)n_epochs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(cnt, c->counters, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   if (trace_dev) {
+      std::vector<unsigned long long> tr((size_t)c->num_sms * kTraceSlots);
+      cudaMemcpy(tr.data(), trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      cudaFree(trace_dev);
+      std::string path = std::string(trace_path) + "." + std::to_string(d->rank);
+      if (FILE* f = fopen(path.c_str(), "w")) {
+         for (int bb = 0; bb < c->num_sms; bb++)
+            for (int kk = 0; kk < kTraceSlots; kk++) fprintf(f, "%llu%c", tr[(size_t)bb * kTraceSlots + kk], kk + 1 == kTraceSlots ? '\n' : ' ');
+         fclose(f);
+      }
+   }
    float ms = 0.f;
    KB2E_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
    c->tstats.kernel_ms += ms;

@@ -144,8 +144,11 @@ def stage_gpu(out_path):
             trained[name] = (ent, rel, w)
             # both sides ranked by the same exact kernel from 6-decimal values (what the eval programs read)
             mine = rank_tables(model, dist, nE, nR, np.round(ent, 6), np.round(rel, 6), None if w is None else np.round(w, 6), g)
-            rw = gold[f"s{s}_{name}_w"] if model != 0 else None
-            theirs = rank_tables(model, dist, nE, nR, gold[f"s{s}_{name}_ent"], gold[f"s{s}_{name}_rel"], rw, g)
+            # the fixture keeps the reference's 6-decimal file values as float32; round(x * 1e6) / 1e6 recovers the
+            # exact doubles the reference's fscanf("%lf") produced (float32 error * 1e6 < 0.1)
+            exact = lambda a: np.round(np.asarray(a, dtype=np.float64) * 1e6) / 1e6
+            rw = exact(gold[f"s{s}_{name}_w"]) if model != 0 else None
+            theirs = rank_tables(model, dist, nE, nR, exact(gold[f"s{s}_{name}_ent"]), exact(gold[f"s{s}_{name}_rel"]), rw, g)
             rr = ref_report[f"s{s}_{name}"]
             ru = ref_report.get(f"s{s}_{name}_uniform")
             rows.append({"seed": s, "model": name, "gpu": mine, "reference": theirs, "reference_cpu_eval": rr,
