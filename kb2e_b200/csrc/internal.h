@@ -10,6 +10,7 @@
 #include "../../include/kb2e_b200.h"
 
 struct DistState;
+namespace kb2e { struct LazyBuffers; struct TrainArgs; }
 
 struct kb2e_ctx {
    kb2e_config cfg;
@@ -69,6 +70,7 @@ struct kb2e_ctx {
    bool filter_dirty = true;
    struct RankState* rank = nullptr;
    DistState* dist = nullptr;  // entity-partitioned multi-GPU training (train_dist.cu)
+   kb2e::LazyBuffers* lazy = nullptr;  // second value buffer, extra delta buffers, stamps (train_lazy.cu)
    kb2e_rank_stats rstats{};
 };
 
@@ -97,6 +99,14 @@ int narrow_table(kb2e_ctx* ctx, int table);   // fp64 -> fp32
 int ensure32(kb2e_ctx* ctx);                  // every table of the model current in fp32 (training)
 int ensure64(kb2e_ctx* ctx);                  // ... in fp64 (ranking)
 double* table64(kb2e_ctx* ctx, int table);
+
+// train_lazy.cu
+bool train_lazy_wanted(const kb2e_ctx* ctx, long long batchsize, int lps, int nv);
+int train_lazy_launch(kb2e_ctx* ctx, const TrainArgs& base, int lps, int nv, int* threads_out);
+void train_lazy_free(kb2e_ctx* ctx);
+
+// train_transr.cu
+int train_transr_launch(kb2e_ctx* ctx, const TrainArgs& base, int* threads_out);
 
 // rank.cu
 int rank_run(kb2e_ctx* ctx, int64_t first, int64_t count, int32_t* raw_rank, int32_t* filt_rank,

@@ -26,6 +26,9 @@
 // re-scored and those ranked before the truth are subtracted from the raw rank.
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -318,14 +321,23 @@ __global__ void segment_hash_kernel(const uint64_t* ent_key, uint32_t n, uint64_
    }
 }
 
-// ---- filter adjustment: one warp per query walks the known-true neighbours -------------------------
-template <int L2>
-__global__ void filter_kernel(const RankArgs a) {
-   long long q = a.q_begin + (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-   int lane = threadIdx.x & 31;
+// ---- filter adjustment: a group of 8 lanes per query walks the known-true neighbours ---------------
+// (planted / FB15k-like graphs have a handful of known answers per query, so a whole warp per query
+// leaves most lanes idle).  ROWS = true (TransE): the candidate matrix IS the entity table, so the
+// energies are taken from the row-major fp64 table (contiguous 8*D-byte rows, every fetched sector is
+// used) instead of the transposed copy (one 8-byte word per sector); the arithmetic and its order are
+// those of exact_energy either way.
+constexpr int kFilterLanes = 8;
+
+template <int L2, bool ROWS>
+__global__ void filter_kernel(const RankArgs a, const double* __restrict__ ent64) {
+   const long long q = a.q_begin + (((long long)blockIdx.x * blockDim.x + threadIdx.x) / kFilterLanes);
+   const int lane = threadIdx.x & 31;
+   const int sub = lane & (kFilterLanes - 1);
+   const uint32_t gmask = ((1u << kFilterLanes) - 1u) << (lane & ~(kFilterLanes - 1));
    if (q >= a.q_end) return;
-   int side = a.q_side[q], rel = a.q_rel[q], fixed = a.q_fixed[q], truth = a.q_truth[q];
-   uint64_t key = seg_key_of(side, rel, fixed);
+   const int side = a.q_side[q], rel = a.q_rel[q], fixed = a.q_fixed[q], truth = a.q_truth[q];
+   const uint64_t key = seg_key_of(side, rel, fixed);
    uint64_t slot = mix64(key) & a.seg_mask;
    uint32_t off = 0;
    bool found = false;
@@ -337,30 +349,42 @@ __global__ void filter_kernel(const RankArgs a) {
    }
    const double* ct = a.ct + (size_t)a.q_slot[q] * a.D * a.ld;
    const double* d = a.rel64 + (size_t)rel * a.D;
+   const double dsign = side ? -1.0 : 1.0;
    const double et = a.q_etrue[q];
    int less = 0, eq = 0;
    if (found) {
-      for (uint32_t base = off; base < a.n_ent; base += 32) {
-         uint32_t k = base + lane;
-         bool mine = k < a.n_ent && __ldg(a.ent_key + k) == key;
+      for (uint32_t base = off; base < a.n_ent; base += kFilterLanes) {
+         const uint32_t k = base + sub;
+         const bool mine = k < a.n_ent && __ldg(a.ent_key + k) == key;
          if (mine) {
-            int c = __ldg(a.nbr + k);
-            bool dup = k > off && __ldg(a.nbr + k - 1) == c;  // the same triple listed twice (e.g. in train and valid)
+            const int c = __ldg(a.nbr + k);
+            const bool dup = k > off && __ldg(a.nbr + k - 1) == c;  // the same triple listed twice (e.g. in train and valid)
             if (c != truth && !dup) {
-               double e = exact_energy<L2>(ct, a.ld, a.D, fixed, c, d, side ? -1.0 : 1.0);
+               double e;
+               if (ROWS) {
+                  const double* v = ent64 + (size_t)fixed * a.D;
+                  const double* x = ent64 + (size_t)c * a.D;
+                  e = 0.0;
+                  for (int i = 0; i < a.D; i++) {
+                     const double w = __dsub_rn(__dsub_rn(__ldg(v + i), __ldg(x + i)), dsign * __ldg(d + i));
+                     e = L2 ? __dadd_rn(e, __dmul_rn(w, w)) : __dadd_rn(e, fabs(w));
+                  }
+               } else {
+                  e = exact_energy<L2>(ct, a.ld, a.D, fixed, c, d, dsign);
+               }
                less += e < et;
                eq += e == et;
             }
          }
-         if (!__all_sync(0xffffffffu, mine)) break;  // the segment ended inside this chunk
+         if (__ballot_sync(gmask, mine) != gmask) break;  // the segment ended inside this chunk
       }
    }
 #pragma unroll
-   for (int o = 16; o > 0; o >>= 1) {
-      less += __shfl_xor_sync(0xffffffffu, less, o);
-      eq += __shfl_xor_sync(0xffffffffu, eq, o);
+   for (int o = kFilterLanes / 2; o > 0; o >>= 1) {
+      less += __shfl_xor_sync(gmask, less, o);
+      eq += __shfl_xor_sync(gmask, eq, o);
    }
-   if (lane == 0) {
+   if (sub == 0) {
       a.q_cnt[2 * a.nq + q] = less;
       a.q_cnt[3 * a.nq + q] = eq;
    }
@@ -525,10 +549,22 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       return fail(c, KB2E_ERR_ARG, "rank window outside the test triples");
    if (sums) sums[0] = sums[1] = sums[2] = sums[3] = 0;
    if (count == 0) return KB2E_OK;
+   // KB2E_RANK_TIMING=1: host-side phase times of this call on stderr (tuning aid; adds stream synchronisations)
+   const bool timing = getenv("KB2E_RANK_TIMING") != nullptr;
+   auto t_last = std::chrono::steady_clock::now();
+   auto lap = [&](const char* what) {
+      if (!timing) return;
+      cudaStreamSynchronize(c->stream);
+      auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[kb2e_rank] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+      t_last = now;
+   };
    int rc = prepare_tables(c);
    if (rc) return rc;
+   lap("fp64 tables + transpose");
    rc = build_filter(c);
    if (rc) return rc;
+   lap("filter CSR build");
    RankState* s = c->rank;
    const bool per_rel = c->cfg.model != KB2E_MODEL_TRANSE;
    const bool l2 = c->cfg.model != KB2E_MODEL_TRANSH && c->cfg.distance == KB2E_DISTANCE_L2;
@@ -615,6 +651,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       s->tile_cap = (int64_t)tiles.size();
    }
    KB2E_CUDA(c, cudaMemcpyAsync(s->tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+   lap("query arrays (host) + H2D");
 
    RankArgs a;
    memset(&a, 0, sizeof(a));
@@ -639,6 +676,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       if (rc) return rc;
    }
    float main_ms = 0.f;
+   lap("tensor-core operand prep");
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
    for (size_t p = 0; p < passes.size(); p++) {
       const Pass& ps = passes[p];
@@ -696,8 +734,16 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
          else rank_exact_kernel<0><<<dim3(ntiles, (unsigned)splits), kRankThreads, smem, c->stream>>>(a);
          KB2E_CUDA(c, cudaEventRecord(s->m1, c->stream));
       }
-      if (l2) filter_kernel<1><<<nblk(pq * 32, 128), 128, 0, c->stream>>>(a);
-      else filter_kernel<0><<<nblk(pq * 32, 128), 128, 0, c->stream>>>(a);
+      {
+         const unsigned fb = nblk(pq * kFilterLanes, 128);
+         if (per_rel) {
+            if (l2) filter_kernel<1, false><<<fb, 128, 0, c->stream>>>(a, c->ent64);
+            else filter_kernel<0, false><<<fb, 128, 0, c->stream>>>(a, c->ent64);
+         } else {
+            if (l2) filter_kernel<1, true><<<fb, 128, 0, c->stream>>>(a, c->ent64);
+            else filter_kernel<0, true><<<fb, 128, 0, c->stream>>>(a, c->ent64);
+         }
+      }
       KB2E_CUDA(c, cudaGetLastError());
       // the projected slots are reused by the next pass
       KB2E_CUDA(c, cudaEventSynchronize(s->m1));
@@ -714,6 +760,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    KB2E_CUDA(c, cudaMemcpyAsync(out.data(), s->out, out.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(hs, s->sums, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   lap("kernels + D2H");
    float ms = 0.f;
    KB2E_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
    c->rstats.kernel_ms += ms;

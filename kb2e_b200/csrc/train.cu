@@ -235,8 +235,8 @@ __device__ __forceinline__ void finish_entity(const TrainArgs& a, int e, int gl,
 }
 
 
-// ================================ TransR =========================================================
-// One warp per sample, rows in the float4 layout (lane owns elements 4*lane .. 4*lane+3; D <= 128).
+// ================================ TransR (fp32 scoring hook; training lives in train_transr.cu) ====
+// One warp per triple, rows in the float4 layout (lane owns elements 4*lane .. 4*lane+3; D <= 128).
 // M_r is [D][P] = M[j = input dim][i = output dim] (transr/trainer.h:31): row j is contiguous in i, so
 // the projection M_r^T e streams the matrix row by row with coalesced 16-byte loads while e_j is
 // broadcast by shuffle (transr/transr.cpp:20-25, work vectors zeroed -- SURVEY.md 8c).
@@ -248,9 +248,6 @@ __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
    return v;
-}
-__device__ __forceinline__ void red_add1(float* p, float v) {
-   asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
 }
 
 // y = M^T a for up to three vectors at once (lane owns output dims 4*lane..)
@@ -270,173 +267,6 @@ __device__ __forceinline__ void project3(const float* M, int D, int P, int lane,
    }
 }
 
-__device__ __forceinline__ void process_pair_transr(const TrainArgs& a, const Pair s, int lane, uint8_t stamp,
-                                                    double& loss_acc, uint32_t& active_acc) {
-   const int P = a.P, D = a.D;
-   const bool on = lane * 4 < P;
-   float4 v[3];  // h, t, c
-   v[0] = on ? ld_cg4(a.tab + (size_t)s.h * P + lane * 4) : f4(0.f);
-   v[1] = on ? ld_cg4(a.tab + (size_t)s.t * P + lane * 4) : f4(0.f);
-   v[2] = on ? ld_cg4(a.tab + (size_t)s.c * P + lane * 4) : f4(0.f);
-   const float4 vr = on ? ld_cg4(a.tab + ((size_t)a.nE + s.r) * P + lane * 4) : f4(0.f);
-   const float* M = a.w + (size_t)s.r * a.w_row;
-   float4 y[3];
-   project3<3>(M, D, P, lane, v, y);
-   const bool l1 = a.distance == KB2E_DISTANCE_L1;
-   const float4 rp = (y[1] - y[0]) - vr;
-   const float4 rn = s.corruptTail ? (y[2] - y[0]) - vr : (y[1] - y[2]) - vr;
-   float ep = l1 ? abs4(rp) : dot4(rp, rp);
-   float en = l1 ? abs4(rn) : dot4(rn, rn);
-   ep = wsum(ep);
-   en = wsum(en);
-   if (!(ep + a.margin > en)) return;  // common/trainer.cpp:138
-   if (lane == 0) {
-      loss_acc += (double)(a.margin + ep - en);
-      active_acc++;
-   }
-   const float lr = a.lr;
-   const float4 gp = l1 ? lr * sign4(rp, lane * 4, D) : (2.f * lr) * rp;
-   const float4 gn = l1 ? lr * sign4(rn, lane * 4, D) : (2.f * lr) * rn;
-   // transr/trainer.cpp:171: r -= beta*lr*x
-   if (on) red_add4(a.dtab + ((size_t)a.nE + s.r) * P + lane * 4, gp - gn);
-   // negative triple's head / tail
-   const float4 nh = s.corruptTail ? v[0] : v[2];
-   const float4 nt = s.corruptTail ? v[2] : v[1];
-   const float4 dpos = v[0] - v[1];  // h - t   (positive)
-   const float4 dneg = nh - nt;      // h' - t' (negative)
-   float* dM = a.dw + (size_t)s.r * a.w_row;
-   float4 sp = f4(0.f), sn = f4(0.f);  // S_j = sum_i g_i M[j][i] for j = 4*lane + c
-#pragma unroll 2
-   for (int j = 0; j < D; j++) {
-      const float4 m = on ? ld_cg4(M + (size_t)j * P + lane * 4) : f4(0.f);
-      // transr/trainer.cpp:167: M[j][i] -= beta*lr*x_i*(h_j - t_j)
-      const float pj = __shfl_sync(0xffffffffu, comp4(dpos, j & 3), j >> 2);
-      const float nj = __shfl_sync(0xffffffffu, comp4(dneg, j & 3), j >> 2);
-      if (on) red_add4(dM + (size_t)j * P + lane * 4, pj * gp - nj * gn);
-      // transr/trainer.cpp:168-169: e[j] -/+= beta*lr*x_i*M[j][i], summed over i
-      const float a_p = wsum(dot4(gp, m));
-      const float a_n = wsum(dot4(gn, m));
-      if ((j >> 2) == lane) {
-         const int c = j & 3;
-         if (c == 0) { sp.x = a_p; sn.x = a_n; } else if (c == 1) { sp.y = a_p; sn.y = a_n; }
-         else if (c == 2) { sp.z = a_p; sn.z = a_n; } else { sp.w = a_p; sn.w = a_n; }
-      }
-   }
-   if (on) {
-      float* dh = a.dtab + (size_t)s.h * P + lane * 4;
-      float* dt = a.dtab + (size_t)s.t * P + lane * 4;
-      float* dc = a.dtab + (size_t)s.c * P + lane * 4;
-      if (s.corruptTail) {
-         red_add4(dh, sp - sn);        // head is shared by both triples
-         red_add4(dt, -1.f * sp);
-         red_add4(dc, sn);
-      } else {
-         red_add4(dh, sp);
-         red_add4(dt, sn - sp);        // tail is shared
-         red_add4(dc, -1.f * sn);
-      }
-   }
-   if (lane < 3) {
-      int e = lane == 0 ? s.h : (lane == 1 ? s.t : s.c);
-      a.flag[e] = stamp;
-      atomicMin(a.rmin + e, s.r);
-      atomicMax(a.rmax + e, s.r);
-   } else if (lane == 3) {
-      a.flag[(size_t)a.nE + s.r] = stamp;
-   }
-}
-
-// transr/trainer.cpp:174,178-180: r unit length; every row M_r[j][.] unit length (after the delta).
-__device__ __forceinline__ void finish_relation_transr(const TrainArgs& a, int r, int lane, float4 x, float4 d) {
-   const int P = a.P, D = a.D;
-   const bool on = lane * 4 < P;
-   float* cur = a.tab + ((size_t)a.nE + r) * P + lane * 4;
-   float* del = a.dtab + ((size_t)a.nE + r) * P + lane * 4;
-   x = x + d;
-   float len = sqrtf(wsum(dot4(x, x)));
-   if (on) {
-      st_cg4(del, f4(0.f));
-      st_cg4(cur, make_float4(x.x / len, x.y / len, x.z / len, x.w / len));
-   }
-   float* M = a.w + (size_t)r * a.w_row;
-   float* dM = a.dw + (size_t)r * a.w_row;
-#pragma unroll 4
-   for (int j = 0; j < D; j++) {
-      float4 m = on ? ld_cg4(M + (size_t)j * P + lane * 4) : f4(0.f);
-      float4 dm = on ? ld_cg4(dM + (size_t)j * P + lane * 4) : f4(0.f);
-      m = m + dm;
-      float l = sqrtf(wsum(dot4(m, m)));
-      if (on) {
-         st_cg4(dM + (size_t)j * P + lane * 4, f4(0.f));
-         st_cg4(M + (size_t)j * P + lane * 4, make_float4(m.x / l, m.y / l, m.z / l, m.w / l));
-      }
-   }
-}
-
-// transRNorm (transr/trainer.cpp:35-64) of entity row x against the published, read-only M_r; the
-// perturbation the reference applies to M_r goes to the NEXT batch's delta.
-__device__ __forceinline__ void transr_constraint(const TrainArgs& a, int r, int lane, uint8_t next_stamp, float4& x) {
-   const int P = a.P, D = a.D;
-   const float* M = a.w + (size_t)r * a.w_row;
-   float* dM = a.dw + (size_t)r * a.w_row;
-   bool touched = false;
-   for (int iter = 0; iter < 64; iter++) {
-      float4 v[1] = {x}, y[1];
-      project3<1>(M, D, P, lane, v, y);
-      if (wsum(dot4(y[0], y[0])) <= 1.f) break;
-      touched = true;
-      for (int i = 0; i < D; i++) {
-         // lane owns input dims j = 4*lane + c: column i of M for those rows
-         float m[4], part = 0.f;
-#pragma unroll
-         for (int c = 0; c < 4; c++) {
-            int j = lane * 4 + c;
-            m[c] = j < D ? __ldcg(M + (size_t)j * P + i) : 0.f;
-            part += m[c] * comp4(x, c);
-         }
-         const float tmp = 2.f * wsum(part);
-         float nx[4];
-#pragma unroll
-         for (int c = 0; c < 4; c++) {
-            int j = lane * 4 + c;
-            float aj = comp4(x, c);
-            float delta = -(a.lr * tmp * aj);
-            if (j < D) red_add1(dM + (size_t)j * P + i, delta);
-            nx[c] = aj - a.lr * tmp * (m[c] + delta);
-         }
-         x = make_float4(nx[0], nx[1], nx[2], nx[3]);
-      }
-   }
-   if (touched && lane == 0) a.flag[(size_t)a.nE + r] = next_stamp;
-}
-
-// Entity row: unit length (transr/trainer.cpp:175-176), then transRNorm against the lowest / highest
-// relation that touched it, and -- the reference's quirk at :187 -- against M_e when relation e was
-// touched (the reference indexes the ENTITY table with the relation id there).
-__device__ __forceinline__ void finish_entity_transr(const TrainArgs& a, int e, int lane, uint8_t stamp, uint8_t next_stamp,
-                                                     bool own, float4 x, float4 d) {
-   const int P = a.P;
-   const bool on = lane * 4 < P;
-   float* cur = a.tab + (size_t)e * P + lane * 4;
-   int r0 = 0x7fffffff, r1 = -1;
-   if (own) {
-      x = x + d;
-      float len = sqrtf(wsum(dot4(x, x)));
-      x = make_float4(x.x / len, x.y / len, x.z / len, x.w / len);
-      if (on) st_cg4(a.dtab + (size_t)e * P + lane * 4, f4(0.f));
-      r0 = __ldcg(a.rmin + e);
-      r1 = __ldcg(a.rmax + e);
-      if (lane == 0) { a.rmin[e] = 0x7fffffff; a.rmax[e] = -1; }
-      if (r1 >= 0) {
-         transr_constraint(a, r0, lane, next_stamp, x);
-         if (r1 != r0) transr_constraint(a, r1, lane, next_stamp, x);
-      }
-   }
-   const bool quirk = !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK) && e < a.nR && __ldcg(a.flag + a.nE + e) == stamp;
-   if (quirk && !(own && (r0 == e || r1 == e))) transr_constraint(a, e, lane, next_stamp, x);
-   if (on) st_cg4(cur, x);
-}
-
 // Rows [row_begin, row_end) of the unified row space (entities, then relations) whose stamp says
 // "touched in this batch".  Two rows per group are examined per step, flags first, then both rows'
 // loads, then the arithmetic, so that the L2 round trips overlap.
@@ -445,27 +275,12 @@ __device__ __forceinline__ void publish_rows(const TrainArgs& a, long long row_b
                                              uint8_t stamp, uint8_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel) {
    const int P = a.P;
    const int lane = threadIdx.x & 31;
-   const bool quirk = MODEL == KB2E_MODEL_TRANSR && !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK);
    long long first, end;
    group_range(row_begin, row_end, g0, G, first, end);
-   auto stamped = [&](long long r) {
-      bool f = __ldcg(a.flag + r) == stamp;
-      // transr/trainer.cpp:187: entity row e is also visited when RELATION e was touched
-      if (quirk && r < a.nE && r < a.nR) f = f || __ldcg(a.flag + a.nE + r) == stamp;
-      return f;
-   };
+   auto stamped = [&](long long r) { return __ldcg(a.flag + r) == stamp; };
    auto finish = [&](long long r, float4 (&x)[NV], float4 (&d)[NV]) {
-      if constexpr (MODEL == KB2E_MODEL_TRANSR) {
-         if (r >= a.nE) { finish_relation_transr(a, (int)(r - a.nE), gl, x[0], d[0]); trel += (gl == 0); }
-         else {
-            const bool own = __ldcg(a.flag + r) == stamp;
-            finish_entity_transr(a, (int)r, gl, stamp, next_stamp, own, x[0], d[0]);
-            tent += (gl == 0 && own);
-         }
-      } else {
-         if (r >= a.nE) { finish_relation<MODEL, LPS, NV>(a, (int)(r - a.nE), gl, gmask, x, d); trel += (gl == 0); }
-         else { finish_entity<MODEL, LPS, NV>(a, (int)r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
-      }
+      if (r >= a.nE) { finish_relation<MODEL, LPS, NV>(a, (int)(r - a.nE), gl, gmask, x, d); trel += (gl == 0); }
+      else { finish_entity<MODEL, LPS, NV>(a, (int)r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
    };
    for_stamped_rows<LPS>(first, end, gl, gmask, lane, stamped, [&](long long r0, long long r1) {
       float4 x0[NV], d0[NV], x1[NV], d1[NV];
@@ -515,18 +330,10 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
          const uint8_t next_stamp = (uint8_t)((gb + 1u) % 255u + 1u);
          KB2E_TRACE();
          // ---- phase 1 ----
-         if constexpr (MODEL == KB2E_MODEL_TRANSR) {
-            if (has_first) process_pair_transr(a, pre, gl, stamp, loss_acc, active_acc);
-            for (long long k = g0 + G; k < a.batchsize; k += G) {
-               Pair s = draw_pair(a, (uint32_t)k, gb);
-               process_pair_transr(a, s, gl, stamp, loss_acc, active_acc);
-            }
-         } else {
-            if (has_first) process_pair<MODEL, LPS, NV>(a, pre, gl, gmask, stamp, loss_acc, active_acc);
-            for (long long k = g0 + G; k < a.batchsize; k += G) {
-               Pair s = draw_pair(a, (uint32_t)k, gb);
-               process_pair<MODEL, LPS, NV>(a, s, gl, gmask, stamp, loss_acc, active_acc);
-            }
+         if (has_first) process_pair<MODEL, LPS, NV>(a, pre, gl, gmask, stamp, loss_acc, active_acc);
+         for (long long k = g0 + G; k < a.batchsize; k += G) {
+            Pair s = draw_pair(a, (uint32_t)k, gb);
+            process_pair<MODEL, LPS, NV>(a, s, gl, gmask, stamp, loss_acc, active_acc);
          }
          KB2E_TRACE();
          grid_barrier(a.barrier, bar_target);
@@ -768,6 +575,7 @@ void train_free(kb2e_ctx* c) {
    cudaFree(c->rmin); cudaFree(c->rmax); cudaFree(c->triples); cudaFree(c->stage); cudaFree(c->hash); cudaFree(c->pr);
    cudaFree(c->barrier); cudaFree(c->loss_dev); cudaFree(c->counters); cudaFree(c->pairs_dev);
    cudaFree(c->ent64); cudaFree(c->rel64); cudaFree(c->w64);
+   train_lazy_free(c);
 }
 
 int train_set_triples(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t* r, int64_t n) {
@@ -998,22 +806,27 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    choose_shape(c, a.batchsize, lps, nv, threads);
    if (nv > 4) return fail(c, KB2E_ERR_LIMIT, "embedding size above 512 is not supported by the training kernel");
    TrainKernel k = nullptr;
-   if (c->cfg.model == KB2E_MODEL_TRANSR) {
+   const bool transr = c->cfg.model == KB2E_MODEL_TRANSR;   // own kernel: train_transr.cu
+   if (transr) {
       if (c->P > 128) return fail(c, KB2E_ERR_LIMIT, "TransR training supports embedding sizes up to 128");
-      lps = 32; nv = 1; threads = 768;
-      k = train_kernel<KB2E_MODEL_TRANSR, 32, 1, 768>;
    } else if (c->cfg.model == KB2E_MODEL_TRANSE) {
       k = pick_kernel<KB2E_MODEL_TRANSE>(lps, nv, threads);
    } else {
       k = pick_kernel<KB2E_MODEL_TRANSH>(lps, nv, threads);
    }
-   if (!k) return fail(c, KB2E_ERR_LIMIT, "no training kernel for this embedding size");
-   int per_sm = 0;
-   KB2E_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0));
-   if (per_sm < 1) return fail(c, KB2E_ERR_CUDA, "training kernel does not fit on an SM");
+   if (!k && !transr) return fail(c, KB2E_ERR_LIMIT, "no training kernel for this embedding size");
+   // small batches (FB15k / WN18 shape): one barrier per batch instead of two (train_lazy.cu)
+   int lazy_lps = lps, lazy_nv = nv;
+   if (c->cfg.model == KB2E_MODEL_TRANSE && nv == 1 && lps == 32 && c->P <= 64) { lazy_lps = 16; }
+   const bool lazy = train_lazy_wanted(c, a.batchsize, lazy_lps, lazy_nv);
+   if (!transr) {
+      int per_sm = 0;
+      KB2E_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0));
+      if (per_sm < 1) return fail(c, KB2E_ERR_CUDA, "training kernel does not fit on an SM");
+   }
    KB2E_CUDA(c, cudaMemsetAsync(c->barrier, 0, 64, c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->loss_dev, 0, (size_t)n_epochs * sizeof(double), c->stream));
-   const char* trace_path = getenv("KB2E_TRAIN_TRACE");
+   const char* trace_path = lazy ? nullptr : getenv("KB2E_TRAIN_TRACE");
    unsigned long long* trace_dev = nullptr;
    if (trace_path) {
       KB2E_CUDA(c, cudaMalloc(&trace_dev, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long)));
@@ -1022,7 +835,15 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    }
    void* params[] = {&a};
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-   KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(threads), params, 0, c->stream));
+   if (transr) {
+      int rc = train_transr_launch(c, a, &threads);
+      if (rc) return rc;
+   } else if (lazy) {
+      int rc = train_lazy_launch(c, a, lazy_lps, lazy_nv, &threads);
+      if (rc) return rc;
+   } else {
+      KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(threads), params, 0, c->stream));
+   }
    KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
    std::vector<double> loss(n_epochs);
    unsigned long long cnt[3];

@@ -2,20 +2,25 @@
 // configs[4]: 4 M entities x D=200, 100 M triples; SURVEY.md 8e "Training, scaled shape").
 //
 // One process (context) per GPU.  Entity row e lives on GPU e % G at local index e / G; the relation
-// table is small and replicated.  Every rank maps every peer's arena with CUDA IPC, so the SAME
-// persistent kernel design as train.cu runs on each GPU and simply dereferences peer pointers:
-//   phase 1  rank g takes the samples k = g (mod G) of the batch (the counter RNG makes the sample set
-//            independent of G), gathers h / t / c rows from their owners with ld.global.cg over NVLink,
-//            and pushes the update with red.global.add.v4.f32 into the OWNER's delta table; relation
-//            deltas go to the relation row's owner r % G.  Touched-row stamps are remote byte stores.
-//   barrier  local grid barrier + a cross-GPU barrier on peer-mapped counters (system-scope atomics)
-//   phase 2  every rank publishes its own stamped entity rows locally; the owner of a relation row
-//            normalises it and writes the new row into every replica
+// table is small and replicated.  Every rank maps every peer's arena with CUDA IPC, so the persistent
+// kernel of each GPU dereferences peer pointers directly -- no NCCL call and no host step inside an
+// epoch.  Measured on this pool (tools/p2p_bench.cu): random 800-byte row gathers from a peer run at
+// ~570 GB/s and row scatters at ~640 GB/s in isolation, but remote loads queue behind posted remote
+// writes when both are in flight, so every phase moves data across NVLink in ONE direction only:
+//   phase 1a  rank g takes the samples k = g (mod G) of the batch (the counter RNG makes the sample set
+//             independent of G) and gathers their h / t / c rows from the owners into a local row cache
+//             (remote READS only, two samples = six rows in flight per group)
+//   phase 1b  scores the cached rows and accumulates the update with local vector REDs: rows it owns
+//             straight into its delta table, rows owned by a peer into a local staging table; stamps them
+//   barrier   (local grid barrier + cross-GPU barrier on peer-mapped counters, system-scope atomics)
+//   phase 2a  staged rows are added into the owner's delta table with red.global.add.v4.f32 over NVLink
+//             and the owner's stamp is set (remote WRITES only)
 //   barrier
-// No NCCL call and no host round trip inside an epoch: the exchange is peer loads / REDs issued by
-// the compute kernel itself, overlapped with its math.  Loss and counters are per rank (the host
-// adds them).  Semantics are identical to the single-GPU kernel (same samples, same deferred
-// renormalisation), so results agree up to the order of float atomics.
+//   phase 2b  every owner publishes its stamped rows (row += delta, normalise once); the owner of a
+//             relation row also writes the new row into every replica (remote writes)
+//   barrier
+// Semantics are identical to the single-GPU kernel (same samples, same deferred renormalisation), so
+// results agree up to the order of float additions.  Loss and counters are per rank (the host adds them).
 
 #include <cstdio>
 #include <cstdlib>
@@ -35,22 +40,43 @@ constexpr int kDistThreads = 768;
 struct DistArgs {
    TrainArgs base;                     // sampler fields (triples, hash, pr, seeds, nE, n_train) + lr, margin, distance, D, P
    unsigned char* arena[kMaxPeers];    // arena[g] = rank g's arena as mapped into this process
+   // arena layout: tab [rows_local][P] | dtab [rows_local][P] | flag [rows_local] |
+   //               rel [nR][P] (replica) | drel [nR][P] | rflag [nR] | cross-GPU counter
    size_t off_tab, off_dtab, off_flag, off_rel, off_drel, off_rflag, off_xbar;
+   float* stage;                       // local: updates for rows owned by peers, [nE + nR][P] (global row ids)
+   uint8_t* sflag;                     // local: stamps of the staged rows, [nE + nR]
+   float* cache;                       // local: gathered rows of this rank's samples, [samples][3][P]
+   int4* pairs;                        // local: (h, t, r, c | corruptTail << 31) per sample
    uint32_t* local_bar;
    int rank, world, wshift;
    int rows_local;
    uint32_t xbase;                     // value of every rank's cross-GPU counter when this launch starts
-   int debug;                          // tuning aid (KB2E_DIST_DEBUG bits): 1 entity REDs local, 2 entity loads local, 4 relation REDs local, 8 flags local
+   int debug;                          // tuning aid (KB2E_DIST_DEBUG bit 2): gather entity rows from the local arena
 };
 
-__device__ __forceinline__ float* ent_row(const DistArgs& a, size_t off, int e) {
+// published value of entity row e (on its owner)
+__device__ __forceinline__ const float* ent_row(const DistArgs& a, int e) {
    int g = e & (a.world - 1);
-   if (((a.debug & 1) && off == a.off_dtab) || ((a.debug & 2) && off == a.off_tab)) g = a.rank;   // tuning aid only
-   return reinterpret_cast<float*>(a.arena[g] + off) + (size_t)(e >> a.wshift) * a.base.P;
+   if (a.debug & 2) g = a.rank;   // tuning aid only
+   return reinterpret_cast<const float*>(a.arena[g] + a.off_tab) + (size_t)(e >> a.wshift) * a.base.P;
 }
-__device__ __forceinline__ uint8_t* ent_flag(const DistArgs& a, int e) {
-   if (a.debug & 8) return a.arena[a.rank] + a.off_flag + (e >> a.wshift);
-   return a.arena[e & (a.world - 1)] + a.off_flag + (e >> a.wshift);
+// where this rank accumulates its update of entity row e, and the stamp that goes with it
+__device__ __forceinline__ float* ent_delta(const DistArgs& a, int e, uint8_t*& flag) {
+   if ((e & (a.world - 1)) == a.rank) {
+      const size_t l = (size_t)(e >> a.wshift);
+      flag = a.arena[a.rank] + a.off_flag + l;
+      return reinterpret_cast<float*>(a.arena[a.rank] + a.off_dtab) + l * a.base.P;
+   }
+   flag = a.sflag + e;
+   return a.stage + (size_t)e * a.base.P;
+}
+__device__ __forceinline__ float* rel_delta(const DistArgs& a, int r, uint8_t*& flag) {
+   if ((r & (a.world - 1)) == a.rank) {
+      flag = a.arena[a.rank] + a.off_rflag + r;
+      return reinterpret_cast<float*>(a.arena[a.rank] + a.off_drel) + (size_t)r * a.base.P;
+   }
+   flag = a.sflag + a.base.nE + r;
+   return a.stage + ((size_t)a.base.nE + r) * a.base.P;
 }
 
 // all CTAs of this GPU, then all GPUs, then all CTAs again (release / acquire at system scope)
@@ -75,14 +101,14 @@ __device__ __forceinline__ void cross_barrier(const DistArgs& a, uint32_t& ltarg
 }
 
 template <int LPS, int NV>
-__device__ __forceinline__ void dist_process_pair(const DistArgs& a, const Pair s, int gl, uint32_t gmask, uint8_t stamp,
-                                                  double& loss_acc, uint32_t& active_acc) {
+__device__ __forceinline__ void dist_process_pair(const DistArgs& a, const Pair s, const float* rows, int gl, uint32_t gmask,
+                                                  uint8_t stamp, double& loss_acc, uint32_t& active_acc) {
    const TrainArgs& b = a.base;
    const int P = b.P, D = b.D;
    float4 vh[NV], vt[NV], vc[NV], vr[NV];
-   load_row<LPS, NV>(ent_row(a, a.off_tab, s.h), P, gl, vh);
-   load_row<LPS, NV>(ent_row(a, a.off_tab, s.t), P, gl, vt);
-   load_row<LPS, NV>(ent_row(a, a.off_tab, s.c), P, gl, vc);
+   load_row<LPS, NV>(rows, P, gl, vh);            // cached copies gathered in phase 1a
+   load_row<LPS, NV>(rows + P, P, gl, vt);
+   load_row<LPS, NV>(rows + 2 * P, P, gl, vc);
    load_row<LPS, NV>(reinterpret_cast<float*>(a.arena[a.rank] + a.off_rel) + (size_t)s.r * P, P, gl, vr);   // local replica
    const bool l1 = b.distance == KB2E_DISTANCE_L1;
    float4 rp[NV], rn[NV];
@@ -109,11 +135,11 @@ __device__ __forceinline__ void dist_process_pair(const DistArgs& a, const Pair 
       if (l1) { gp[q] = lr * sign4(rp[q], idx, D); gn[q] = lr * sign4(rn[q], idx, D); }
       else { gp[q] = (2.f * lr) * rp[q]; gn[q] = (2.f * lr) * rn[q]; }
    }
-   float* dh = ent_row(a, a.off_dtab, s.h);
-   float* dt = ent_row(a, a.off_dtab, s.t);
-   float* dc = ent_row(a, a.off_dtab, s.c);
-   const int rg = (a.debug & 4) ? a.rank : (s.r & (a.world - 1));   // owner of the relation row
-   float* dr = reinterpret_cast<float*>(a.arena[rg] + a.off_drel) + (size_t)s.r * P;
+   uint8_t *fh, *ft, *fc, *fr;
+   float* dh = ent_delta(a, s.h, fh);
+   float* dt = ent_delta(a, s.t, ft);
+   float* dc = ent_delta(a, s.c, fc);
+   float* dr = rel_delta(a, s.r, fr);
 #pragma unroll
    for (int q = 0; q < NV; q++) u[q] = gp[q] - gn[q];
    red_row<LPS, NV>(dr, P, gl, u);
@@ -132,12 +158,7 @@ __device__ __forceinline__ void dist_process_pair(const DistArgs& a, const Pair 
       for (int q = 0; q < NV; q++) u[q] = -1.f * gn[q];
       red_row<LPS, NV>(dc, P, gl, u);
    }
-   if (gl < 3) {
-      int e = gl == 0 ? s.h : (gl == 1 ? s.t : s.c);
-      *ent_flag(a, e) = stamp;
-   } else if (gl == 3) {
-      *(a.arena[rg] + a.off_rflag + s.r) = stamp;
-   }
+   if (gl < 4) *(gl == 0 ? fh : (gl == 1 ? ft : (gl == 2 ? fc : fr))) = stamp;
 }
 
 template <int LPS, int NV>
@@ -154,9 +175,10 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
    unsigned char* me = a.arena[a.rank];
    float* tab = reinterpret_cast<float*>(me + a.off_tab);
    float* dtab = reinterpret_cast<float*>(me + a.off_dtab);
-   uint8_t* flag = me + a.off_flag;
+   const uint8_t* flag = me + a.off_flag;
    float* drel = reinterpret_cast<float*>(me + a.off_drel);
-   uint8_t* rflag = me + a.off_rflag;
+   const uint8_t* rflag = me + a.off_rflag;
+   const long long RL = a.rows_local;
    // this rank's share of a batch: global samples k = rank, rank + world, ...
    const long long my_count = (b.batchsize - a.rank + a.world - 1) >> a.wshift;
    uint32_t ltarget = 0, xtarget = a.xbase;
@@ -181,19 +203,84 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
          const uint32_t gb = gb_first + (uint32_t)ep * (uint32_t)b.batches + (uint32_t)batch;
          const uint8_t stamp = (uint8_t)(gb % 255u + 1u);
          KB2E_DTRACE();
-         // ---- phase 1 ----
-         if (has_first) dist_process_pair<LPS, NV>(a, pre, gl, gmask, stamp, loss_acc, active_acc);
-         for (long long j = g0 + G; j < my_count; j += G) {
-            Pair s = draw_pair(b, (uint32_t)(j * a.world + a.rank), gb);
-            dist_process_pair<LPS, NV>(a, s, gl, gmask, stamp, loss_acc, active_acc);
+         // ---- phase 1a: gather (remote reads only); two samples per step keep six rows in flight ----
+         for (long long j = g0; j < my_count; j += 2 * G) {
+            const long long j1 = j + G;
+            const bool two = j1 < my_count;
+            Pair s0 = (j == g0 && has_first) ? pre : draw_pair(b, (uint32_t)(j * a.world + a.rank), gb);
+            Pair s1 = s0;
+            if (two) s1 = draw_pair(b, (uint32_t)(j1 * a.world + a.rank), gb);
+            float4 v0[3][NV], v1[3][NV];
+            load_row<LPS, NV>(ent_row(a, s0.h), P, gl, v0[0]);
+            load_row<LPS, NV>(ent_row(a, s0.t), P, gl, v0[1]);
+            load_row<LPS, NV>(ent_row(a, s0.c), P, gl, v0[2]);
+            if (two) {
+               load_row<LPS, NV>(ent_row(a, s1.h), P, gl, v1[0]);
+               load_row<LPS, NV>(ent_row(a, s1.t), P, gl, v1[1]);
+               load_row<LPS, NV>(ent_row(a, s1.c), P, gl, v1[2]);
+            }
+            if (gl == 0) a.pairs[j] = make_int4(s0.h, s0.t, s0.r, s0.c | (s0.corruptTail ? 0x80000000 : 0));
+            float* c0 = a.cache + (size_t)j * 3 * P;
+#pragma unroll
+            for (int w = 0; w < 3; w++) store_row<LPS, NV>(c0 + w * P, P, gl, v0[w]);
+            if (two) {
+               if (gl == 0) a.pairs[j1] = make_int4(s1.h, s1.t, s1.r, s1.c | (s1.corruptTail ? 0x80000000 : 0));
+               float* c1 = a.cache + (size_t)j1 * 3 * P;
+#pragma unroll
+               for (int w = 0; w < 3; w++) store_row<LPS, NV>(c1 + w * P, P, gl, v1[w]);
+            }
+         }
+         KB2E_DTRACE();
+         // ---- phase 1b: score + accumulate, everything local (same group <-> same samples: no barrier) ----
+         for (long long j = g0; j < my_count; j += G) {
+            const int4 pr = __ldcg(a.pairs + j);
+            Pair s;
+            s.h = pr.x; s.t = pr.y; s.r = pr.z; s.c = pr.w & 0x7fffffff; s.corruptTail = pr.w < 0;
+            dist_process_pair<LPS, NV>(a, s, a.cache + (size_t)j * 3 * P, gl, gmask, stamp, loss_acc, active_acc);
          }
          KB2E_DTRACE();
          cross_barrier(a, ltarget, xtarget);
          KB2E_DTRACE();
-         // ---- phase 2: own entity rows ----
+         // ---- phase 2a: push the staged rows to their owners (remote writes only) ----
          {
             long long first, end;
-            group_range(0, a.rows_local, g0, G, first, end);
+            group_range(0, (long long)b.nE + b.nR, g0, G, first, end);
+            for_stamped_rows<LPS>(first, end, gl, gmask, lane, [&](long long r) { return __ldcg(a.sflag + r) == stamp; },
+                                  [&](long long r0, long long r1) {
+               float4 d0[NV], d1[NV], z[NV];
+#pragma unroll
+               for (int q = 0; q < NV; q++) z[q] = f4(0.f);
+               load_row<LPS, NV>(a.stage + (size_t)r0 * P, P, gl, d0);
+               if (r1 >= 0) load_row<LPS, NV>(a.stage + (size_t)r1 * P, P, gl, d1);
+               auto push = [&](long long r, float4 (&d)[NV]) {
+                  float* dst;
+                  uint8_t* dflag;
+                  if (r < b.nE) {
+                     unsigned char* owner = a.arena[r & (a.world - 1)];
+                     const size_t l = (size_t)(r >> a.wshift);
+                     dst = reinterpret_cast<float*>(owner + a.off_dtab) + l * P;
+                     dflag = owner + a.off_flag + l;
+                  } else {
+                     const long long rr = r - b.nE;
+                     unsigned char* owner = a.arena[rr & (a.world - 1)];
+                     dst = reinterpret_cast<float*>(owner + a.off_drel) + (size_t)rr * P;
+                     dflag = owner + a.off_rflag + rr;
+                  }
+                  red_row<LPS, NV>(dst, P, gl, d);   // several senders may add into the same owner row
+                  if (gl == 0) *dflag = stamp;
+                  store_row<LPS, NV>(a.stage + (size_t)r * P, P, gl, z);
+               };
+               push(r0, d0);
+               if (r1 >= 0) push(r1, d1);
+            });
+         }
+         KB2E_DTRACE();
+         cross_barrier(a, ltarget, xtarget);
+         KB2E_DTRACE();
+         // ---- phase 2b: own entity rows: row += delta, normalise once, publish ----
+         {
+            long long first, end;
+            group_range(0, RL, g0, G, first, end);
             for_stamped_rows<LPS>(first, end, gl, gmask, lane, [&](long long r) { return __ldcg(flag + r) == stamp; },
                                   [&](long long r0, long long r1) {
                float4 x0[NV], d0[NV], x1[NV], d1[NV];
@@ -203,24 +290,20 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
                   load_row<LPS, NV>(tab + (size_t)r1 * P, P, gl, x1);
                   load_row<LPS, NV>(dtab + (size_t)r1 * P, P, gl, d1);
                }
+               auto publish = [&](long long r, float4 (&x)[NV], float4 (&d)[NV]) {
 #pragma unroll
-               for (int q = 0; q < NV; q++) { x0[q] = x0[q] + d0[q]; d0[q] = f4(0.f); }
-               store_row<LPS, NV>(dtab + (size_t)r0 * P, P, gl, d0);
-               norm_row<LPS, NV>(x0, true, gmask);   // transe/trainer.cpp:44-45
-               store_row<LPS, NV>(tab + (size_t)r0 * P, P, gl, x0);
-               tent_acc += (gl == 0);
-               if (r1 >= 0) {
-#pragma unroll
-                  for (int q = 0; q < NV; q++) { x1[q] = x1[q] + d1[q]; d1[q] = f4(0.f); }
-                  store_row<LPS, NV>(dtab + (size_t)r1 * P, P, gl, d1);
-                  norm_row<LPS, NV>(x1, true, gmask);
-                  store_row<LPS, NV>(tab + (size_t)r1 * P, P, gl, x1);
+                  for (int q = 0; q < NV; q++) { x[q] = x[q] + d[q]; d[q] = f4(0.f); }
+                  store_row<LPS, NV>(dtab + (size_t)r * P, P, gl, d);
+                  norm_row<LPS, NV>(x, true, gmask);   // transe/trainer.cpp:44-45
+                  store_row<LPS, NV>(tab + (size_t)r * P, P, gl, x);
                   tent_acc += (gl == 0);
-               }
+               };
+               publish(r0, x0, d0);
+               if (r1 >= 0) publish(r1, x1, d1);
             });
          }
          KB2E_DTRACE();
-         // ---- phase 2: relation rows owned by this rank -> every replica ----
+         // ---- phase 2b: relation rows owned by this rank -> every replica ----
          for (long long r = (long long)a.rank + g0 * a.world; r < b.nR; r += G * a.world) {
             if (__ldcg(rflag + r) != stamp) continue;
             float4 x[NV], d[NV];
@@ -325,6 +408,11 @@ struct DistState {
    unsigned char* arena = nullptr;
    size_t arena_bytes = 0;
    size_t off_tab = 0, off_dtab = 0, off_flag = 0, off_rel = 0, off_drel = 0, off_rflag = 0, off_xbar = 0;
+   float* stage = nullptr;
+   uint8_t* sflag = nullptr;
+   float* cache = nullptr;
+   int4* pairs = nullptr;
+   long long cache_samples = 0;
    unsigned char* peers[kMaxPeers] = {};
    bool connected = false;
    uint32_t xcount = 0;   // cross-GPU barrier arrivals so far (identical on every rank: the counters are never reset)
@@ -347,12 +435,15 @@ int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) 
    d->rank = rank; d->world = world;
    while ((1 << d->wshift) < world) d->wshift++;
    d->rows_local = ((long long)c->nE - rank + world - 1) / world;
-   const size_t tab_bytes = (size_t)d->rows_local * c->P * sizeof(float);
+   // every rank uses the SAME offsets (computed from rank 0's row count, the largest), so a peer's arena can be
+   // addressed without knowing its private layout
+   const long long rows_max = ((long long)c->nE + world - 1) / world;
+   const size_t tab_bytes = (size_t)rows_max * c->P * sizeof(float);
    const size_t rel_bytes = (size_t)c->nR * c->P * sizeof(float);
    size_t off = 0;
    d->off_tab = off; off = align_up(off + tab_bytes, 256);
    d->off_dtab = off; off = align_up(off + tab_bytes, 256);
-   d->off_flag = off; off = align_up(off + (size_t)d->rows_local, 256);
+   d->off_flag = off; off = align_up(off + (size_t)rows_max, 256);
    d->off_rel = off; off = align_up(off + rel_bytes, 256);
    d->off_drel = off; off = align_up(off + rel_bytes, 256);
    d->off_rflag = off; off = align_up(off + (size_t)c->nR, 256);
@@ -360,6 +451,11 @@ int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) 
    d->arena_bytes = off;
    KB2E_CUDA(c, cudaMalloc(&d->arena, d->arena_bytes));
    KB2E_CUDA(c, cudaMemset(d->arena, 0, d->arena_bytes));
+   const size_t stage_rows = (size_t)c->nE + c->nR;
+   KB2E_CUDA(c, cudaMalloc(&d->stage, stage_rows * c->P * sizeof(float)));
+   KB2E_CUDA(c, cudaMemset(d->stage, 0, stage_rows * c->P * sizeof(float)));
+   KB2E_CUDA(c, cudaMalloc(&d->sflag, stage_rows));
+   KB2E_CUDA(c, cudaMemset(d->sflag, 0, stage_rows));
    cudaIpcMemHandle_t h;
    KB2E_CUDA(c, cudaIpcGetMemHandle(&h, d->arena));
    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -458,6 +554,18 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    for (int g = 0; g < d->world; g++) a.arena[g] = d->peers[g];
    a.off_tab = d->off_tab; a.off_dtab = d->off_dtab; a.off_flag = d->off_flag; a.off_rel = d->off_rel;
    a.off_drel = d->off_drel; a.off_rflag = d->off_rflag; a.off_xbar = d->off_xbar;
+   a.stage = d->stage; a.sflag = d->sflag;
+   {
+      const long long my_max = (b.batchsize + d->world - 1) / d->world;
+      if (my_max > d->cache_samples) {
+         cudaFree(d->cache); cudaFree(d->pairs);
+         d->cache = nullptr; d->pairs = nullptr; d->cache_samples = 0;
+         KB2E_CUDA(c, cudaMalloc(&d->cache, (size_t)my_max * 3 * c->P * sizeof(float)));
+         KB2E_CUDA(c, cudaMalloc(&d->pairs, (size_t)my_max * sizeof(int4)));
+         d->cache_samples = my_max;
+      }
+      a.cache = d->cache; a.pairs = d->pairs;
+   }
    a.local_bar = c->barrier;
    a.rank = d->rank; a.world = d->world; a.wshift = d->wshift; a.rows_local = (int)d->rows_local;
    a.debug = getenv("KB2E_DIST_DEBUG") ? atoi(getenv("KB2E_DIST_DEBUG")) : 0;
@@ -474,7 +582,7 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    // the peer-mapped cross-GPU counters are monotonic across launches (a reset could wipe a fast peer's
    // arrival); every rank runs the same barrier sequence, so the start value is known on the host
    a.xbase = d->xcount;
-   d->xcount += (uint32_t)d->world * (1u + 2u * (uint32_t)c->cfg.batches * (uint32_t)n_epochs);
+   d->xcount += (uint32_t)d->world * (1u + 3u * (uint32_t)c->cfg.batches * (uint32_t)n_epochs);
    KB2E_CUDA(c, cudaMemsetAsync(c->barrier, 0, 64, c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->loss_dev, 0, (size_t)n_epochs * sizeof(double), c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -525,6 +633,10 @@ void kb2e_dist_teardown(kb2e_ctx* c) {
    for (int g = 0; g < d->world; g++)
       if (g != d->rank && d->peers[g]) cudaIpcCloseMemHandle(d->peers[g]);
    cudaFree(d->arena);
+   cudaFree(d->stage);
+   cudaFree(d->sflag);
+   cudaFree(d->cache);
+   cudaFree(d->pairs);
    delete d;
    c->dist = nullptr;
 }

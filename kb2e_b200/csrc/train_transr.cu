@@ -1,0 +1,521 @@
+// TransR epochs (transr/transr.cpp:13-37, transr/trainer.cpp:35-64,144-188) as one persistent cooperative
+// launch: the same batch semantics and phases as train_kernel (train.cu), but a work decomposition built
+// around the D x D projection matrix.
+//
+// One warp owns one sample (phase 1) or one touched row (phase 2) and stages the M_r it needs ONCE into its
+// own slice of shared memory with coalesced 16-byte loads (all of them in flight together), then runs both
+// contractions from there:
+//   forward   y_i = sum_j M[j][i] e_j     lane owns output dims i = lane, lane + 32, ...; row j of the staged
+//                                          matrix is read with consecutive lanes on consecutive banks and e_j is
+//                                          a shared-memory broadcast
+//   backward  S_j = sum_i g_i M[j][i]     lane owns input dims j; the odd row pitch (P + 1) puts the 32 rows a
+//                                          warp reads at one column on 32 different banks -- no shuffles
+//   transRNorm sweep (sequential in i)    column i against the lane-owned x_j: two shared loads, two FMAs and one
+//                                          warp sum per step, instead of a strided global gather per step
+// The dM update is issued as flat, fully coalesced vector REDs over the D*P/4 float4 of M_r.
+// Everything else (sampler, stamps, deferred renormalisation, the transr/trainer.cpp:187 quirk, carrying the
+// constraint's perturbation of M_r into the next batch) is exactly as in train.cu / oracle orc_train_batch_dfr.
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "internal.h"
+#include "train_device.cuh"
+
+namespace kb2e {
+
+constexpr int kRMaxThreads = 576;   // 18 warps: 65536 / 576 = 113 registers per thread
+enum { S_H = 0, S_T, S_C, S_R, S_GP, S_GN, S_DP, S_DN, S_SP, S_SN, kRSlots };
+
+struct RArgs {
+   TrainArgs base;
+   int pitch;          // row pitch of the staged matrix in floats (odd)
+   int vec_off;        // offset of the vector slots inside a warp's slice (floats, multiple of 4)
+   int warp_floats;    // floats per warp slice (multiple of 4)
+   uint32_t p4_magic;  // ceil(2^32 / (P / 4)): f / (P/4) == umulhi(f, magic) for the flat indices used here
+};
+
+__device__ __forceinline__ float rcomp(const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+   return v;
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+   asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+// Stage M (global, [D][P]) into sM ([D][pitch]); SUM: stage M + dM instead and zero dM (publish of a relation).
+template <bool SUM>
+__device__ __forceinline__ void stage_matrix(const RArgs& a, const float* M, float* dM, float* sM, int lane) {
+   const int P4 = a.base.P >> 2;
+   const int nF = a.base.D * P4;
+   constexpr int U = 7;
+   for (int f0 = lane; f0 < nF; f0 += 32 * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+         const int f = f0 + 32 * u;
+         v[u] = f < nF ? ld_cg4(M + 4 * (size_t)f) : f4(0.f);
+         if (SUM && f < nF) {
+            v[u] = v[u] + ld_cg4(dM + 4 * (size_t)f);
+         }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+         const int f = f0 + 32 * u;
+         if (f < nF) {
+            const int j = (int)__umulhi((uint32_t)f, a.p4_magic);
+            float* d = sM + j * a.pitch + 4 * (f - j * P4);
+            d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+            if (SUM) st_cg4(dM + 4 * (size_t)f, f4(0.f));
+         }
+      }
+   }
+}
+
+// y[v][k] = sum_j sM[j][lane + 32 k] * vec_v[j]   (transr/transr.cpp:20-25 with zeroed work vectors)
+template <int NE, int NVEC>
+__device__ __forceinline__ void project_smem(const float* sM, int D, int pitch, int lane, const float* const (&vec)[NVEC],
+                                             float (&y)[NVEC][NE]) {
+#pragma unroll
+   for (int v = 0; v < NVEC; v++)
+#pragma unroll
+      for (int k = 0; k < NE; k++) y[v][k] = 0.f;
+   for (int j0 = 0; j0 < D; j0 += 4) {
+      float4 e[NVEC];
+#pragma unroll
+      for (int v = 0; v < NVEC; v++) e[v] = *reinterpret_cast<const float4*>(vec[v] + j0);
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+         const int j = j0 + c;
+         if (j < D) {
+#pragma unroll
+            for (int k = 0; k < NE; k++) {
+               const int i = lane + 32 * k;
+               const float m = i < D ? sM[j * pitch + i] : 0.f;
+#pragma unroll
+               for (int v = 0; v < NVEC; v++) y[v][k] = fmaf(rcomp(e[v], c), m, y[v][k]);
+            }
+         }
+      }
+   }
+}
+
+// lane-owned elements (i = lane + 32 k) -> slot; the padding [D, P) is written as zero
+template <int NE>
+__device__ __forceinline__ void put_slot(float* slot, int D, int P, int lane, const float (&v)[NE]) {
+#pragma unroll
+   for (int k = 0; k < NE; k++) {
+      const int i = lane + 32 * k;
+      if (i < P) slot[i] = i < D ? v[k] : 0.f;
+   }
+}
+template <int NE>
+__device__ __forceinline__ void get_slot(const float* slot, int D, int lane, float (&v)[NE]) {
+#pragma unroll
+   for (int k = 0; k < NE; k++) {
+      const int i = lane + 32 * k;
+      v[k] = i < D ? slot[i] : 0.f;
+   }
+}
+
+// ---- phase 1 ---------------------------------------------------------------------------------------------
+template <int NE>
+__device__ __forceinline__ void transr_pair(const RArgs& ra, const Pair s, float* sM, float* sV, int lane, uint8_t stamp,
+                                            double& loss_acc, uint32_t& active_acc) {
+   const TrainArgs& a = ra.base;
+   const int P = a.P, D = a.D, P4 = P >> 2;
+   const bool on = lane < P4;
+   const float* M = a.w + (size_t)s.r * a.w_row;
+   float* dM = a.dw + (size_t)s.r * a.w_row;
+   {
+      // rows first (they are needed last), then the matrix: everything is in flight together
+      const float4 vh = on ? ld_cg4(a.tab + (size_t)s.h * P + lane * 4) : f4(0.f);
+      const float4 vt = on ? ld_cg4(a.tab + (size_t)s.t * P + lane * 4) : f4(0.f);
+      const float4 vc = on ? ld_cg4(a.tab + (size_t)s.c * P + lane * 4) : f4(0.f);
+      const float4 vr = on ? ld_cg4(a.tab + ((size_t)a.nE + s.r) * P + lane * 4) : f4(0.f);
+      stage_matrix<false>(ra, M, nullptr, sM, lane);
+      if (on) {
+         reinterpret_cast<float4*>(sV + S_H * P)[lane] = vh;
+         reinterpret_cast<float4*>(sV + S_T * P)[lane] = vt;
+         reinterpret_cast<float4*>(sV + S_C * P)[lane] = vc;
+         reinterpret_cast<float4*>(sV + S_R * P)[lane] = vr;
+      }
+   }
+   __syncwarp();
+   float y[3][NE];
+   {
+      const float* const vec[3] = {sV + S_H * P, sV + S_T * P, sV + S_C * P};
+      project_smem<NE, 3>(sM, D, ra.pitch, lane, vec, y);
+   }
+   const bool l1 = a.distance == KB2E_DISTANCE_L1;
+   float rp[NE], rn[NE], r[NE];
+   get_slot<NE>(sV + S_R * P, D, lane, r);
+   float ep = 0.f, en = 0.f;
+#pragma unroll
+   for (int k = 0; k < NE; k++) {
+      rp[k] = (y[1][k] - y[0][k]) - r[k];
+      rn[k] = s.corruptTail ? (y[2][k] - y[0][k]) - r[k] : (y[1][k] - y[2][k]) - r[k];
+      ep += l1 ? fabsf(rp[k]) : rp[k] * rp[k];
+      en += l1 ? fabsf(rn[k]) : rn[k] * rn[k];
+   }
+   ep = warp_sum(ep);
+   en = warp_sum(en);
+   if (!(ep + a.margin > en)) { __syncwarp(); return; }  // common/trainer.cpp:138
+   if (lane == 0) {
+      loss_acc += (double)(a.margin + ep - en);
+      active_acc++;
+   }
+   const float lr = a.lr;
+   {
+      float gp[NE], gn[NE], dp[NE], dn[NE], h[NE], t[NE], c[NE];
+      get_slot<NE>(sV + S_H * P, D, lane, h);
+      get_slot<NE>(sV + S_T * P, D, lane, t);
+      get_slot<NE>(sV + S_C * P, D, lane, c);
+#pragma unroll
+      for (int k = 0; k < NE; k++) {
+         // transr/trainer.cpp:160-165: x = 2 * residual, L1 -> sign (0 -> -1)
+         gp[k] = l1 ? (rp[k] > 0.f ? lr : -lr) : (2.f * lr) * rp[k];
+         gn[k] = l1 ? (rn[k] > 0.f ? lr : -lr) : (2.f * lr) * rn[k];
+         dp[k] = h[k] - t[k];                                             // h - t   (positive)
+         dn[k] = (s.corruptTail ? h[k] : c[k]) - (s.corruptTail ? c[k] : t[k]);   // h' - t' (negative)
+      }
+      put_slot<NE>(sV + S_GP * P, D, P, lane, gp);
+      put_slot<NE>(sV + S_GN * P, D, P, lane, gn);
+      put_slot<NE>(sV + S_DP * P, D, P, lane, dp);
+      put_slot<NE>(sV + S_DN * P, D, P, lane, dn);
+   }
+   __syncwarp();
+   // transr/trainer.cpp:171: r -= beta*lr*x
+   if (on) {
+      const float4 gp4 = reinterpret_cast<const float4*>(sV + S_GP * P)[lane];
+      const float4 gn4 = reinterpret_cast<const float4*>(sV + S_GN * P)[lane];
+      red_add4(a.dtab + ((size_t)a.nE + s.r) * P + lane * 4, gp4 - gn4);
+   }
+   // transr/trainer.cpp:167: M[j][i] -= beta*lr*x_i*(h_j - t_j) -- flat over the D*P/4 vectors of M_r
+   {
+      const int nF = D * P4;
+      for (int f = lane; f < nF; f += 32) {
+         const int j = (int)__umulhi((uint32_t)f, ra.p4_magic);
+         const int i4 = f - j * P4;
+         const float pj = sV[S_DP * P + j], nj = sV[S_DN * P + j];
+         const float4 gp4 = reinterpret_cast<const float4*>(sV + S_GP * P)[i4];
+         const float4 gn4 = reinterpret_cast<const float4*>(sV + S_GN * P)[i4];
+         red_add4(dM + 4 * (size_t)f, pj * gp4 - nj * gn4);
+      }
+   }
+   // transr/trainer.cpp:168-169: e[j] -/+= beta*lr*x_i*M[j][i] summed over i; lane owns j = lane + 32 k
+   {
+      float sp[NE], sn[NE];
+#pragma unroll
+      for (int k = 0; k < NE; k++) { sp[k] = 0.f; sn[k] = 0.f; }
+      for (int i0 = 0; i0 < D; i0 += 4) {
+         const float4 gp4 = *reinterpret_cast<const float4*>(sV + S_GP * P + i0);
+         const float4 gn4 = *reinterpret_cast<const float4*>(sV + S_GN * P + i0);
+#pragma unroll
+         for (int k = 0; k < NE; k++) {
+            const int j = lane + 32 * k;
+            if (j < D) {
+               const float* m = sM + j * ra.pitch + i0;   // i0 + 3 <= P - 1 < pitch; padding columns are zero
+               const float m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
+               sp[k] += gp4.x * m0 + gp4.y * m1 + gp4.z * m2 + gp4.w * m3;
+               sn[k] += gn4.x * m0 + gn4.y * m1 + gn4.z * m2 + gn4.w * m3;
+            }
+         }
+      }
+      put_slot<NE>(sV + S_SP * P, D, P, lane, sp);
+      put_slot<NE>(sV + S_SN * P, D, P, lane, sn);
+   }
+   __syncwarp();
+   if (on) {
+      const float4 sp4 = reinterpret_cast<const float4*>(sV + S_SP * P)[lane];
+      const float4 sn4 = reinterpret_cast<const float4*>(sV + S_SN * P)[lane];
+      float* dh = a.dtab + (size_t)s.h * P + lane * 4;
+      float* dt = a.dtab + (size_t)s.t * P + lane * 4;
+      float* dc = a.dtab + (size_t)s.c * P + lane * 4;
+      if (s.corruptTail) {
+         red_add4(dh, sp4 - sn4);        // head is shared by both triples
+         red_add4(dt, -1.f * sp4);
+         red_add4(dc, sn4);
+      } else {
+         red_add4(dh, sp4);
+         red_add4(dt, sn4 - sp4);        // tail is shared
+         red_add4(dc, -1.f * sn4);
+      }
+   }
+   if (lane < 3) {
+      const int e = lane == 0 ? s.h : (lane == 1 ? s.t : s.c);
+      a.flag[e] = stamp;
+      atomicMin(a.rmin + e, s.r);
+      atomicMax(a.rmax + e, s.r);
+   } else if (lane == 3) {
+      a.flag[(size_t)a.nE + s.r] = stamp;
+   }
+   __syncwarp();
+}
+
+// ---- phase 2a: relation r -- r unit length; every row M_r[j][.] unit length (transr/trainer.cpp:174,178-180)
+template <int NE>
+__device__ __forceinline__ void transr_finish_relation(const RArgs& ra, int r, float* sM, float* sV, int lane, float4 x, float4 d) {
+   const TrainArgs& a = ra.base;
+   const int P = a.P, D = a.D, P4 = P >> 2;
+   const bool on = lane < P4;
+   float* cur = a.tab + ((size_t)a.nE + r) * P + lane * 4;
+   float* del = a.dtab + ((size_t)a.nE + r) * P + lane * 4;
+   float* M = a.w + (size_t)r * a.w_row;
+   float* dM = a.dw + (size_t)r * a.w_row;
+   stage_matrix<true>(ra, M, dM, sM, lane);
+   x = x + d;
+   const float len = sqrtf(warp_sum(dot4(x, x)));
+   if (on) {
+      st_cg4(del, f4(0.f));
+      st_cg4(cur, make_float4(x.x / len, x.y / len, x.z / len, x.w / len));
+   }
+   __syncwarp();
+   float l[NE];
+#pragma unroll
+   for (int k = 0; k < NE; k++) {
+      const int j = lane + 32 * k;
+      float s2 = 0.f;
+      if (j < D) {
+         const float* m = sM + j * ra.pitch;
+         for (int i = 0; i < D; i++) s2 = fmaf(m[i], m[i], s2);
+      }
+      l[k] = sqrtf(s2);
+   }
+   put_slot<NE>(sV + S_SP * P, D, P, lane, l);
+   __syncwarp();
+   const int nF = D * P4;
+   for (int f = lane; f < nF; f += 32) {
+      const int j = (int)__umulhi((uint32_t)f, ra.p4_magic);
+      const float* m = sM + j * ra.pitch + 4 * (f - j * P4);
+      const float lj = sV[S_SP * P + j];
+      st_cg4(M + 4 * (size_t)f, make_float4(m[0] / lj, m[1] / lj, m[2] / lj, m[3] / lj));
+   }
+   __syncwarp();
+}
+
+// transRNorm (transr/trainer.cpp:35-64) of the lane-owned entity row x (a copy lives in slot S_H) against the
+// published, read-only M_r; the perturbation the reference applies to M_r goes to the NEXT batch's delta.
+template <int NE>
+__device__ __forceinline__ void transr_constraint(const RArgs& ra, int r, float* sM, float* sV, int lane, uint8_t next_stamp,
+                                                  float (&x)[NE]) {
+   const TrainArgs& a = ra.base;
+   const int P = a.P, D = a.D;
+   const float* M = a.w + (size_t)r * a.w_row;
+   float* dM = a.dw + (size_t)r * a.w_row;
+   stage_matrix<false>(ra, M, nullptr, sM, lane);
+   __syncwarp();
+   bool touched = false;
+   for (int iter = 0; iter < 64; iter++) {
+      float y[1][NE];
+      const float* const vec[1] = {sV + S_H * P};
+      project_smem<NE, 1>(sM, D, ra.pitch, lane, vec, y);
+      float n2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < NE; k++) n2 += (lane + 32 * k < D) ? y[0][k] * y[0][k] : 0.f;
+      if (warp_sum(n2) <= 1.f) break;
+      touched = true;
+      for (int i = 0; i < D; i++) {
+         float m[NE], part = 0.f;
+#pragma unroll
+         for (int k = 0; k < NE; k++) {
+            const int j = lane + 32 * k;
+            m[k] = j < D ? sM[j * ra.pitch + i] : 0.f;
+            part += m[k] * x[k];
+         }
+         const float tmp = 2.f * warp_sum(part);
+#pragma unroll
+         for (int k = 0; k < NE; k++) {
+            const int j = lane + 32 * k;
+            const float delta = -(a.lr * tmp * x[k]);
+            if (j < D) red_add_f32(dM + (size_t)j * P + i, delta);
+            x[k] = x[k] - a.lr * tmp * (m[k] + delta);
+         }
+      }
+      __syncwarp();
+      put_slot<NE>(sV + S_H * P, D, P, lane, x);
+      __syncwarp();
+   }
+   if (touched && lane == 0) a.flag[(size_t)a.nE + r] = next_stamp;
+   __syncwarp();
+}
+
+// ---- phase 2b: entity row -- unit length (transr/trainer.cpp:175-176), then transRNorm against the lowest /
+// highest relation that touched it, and -- the reference's quirk at :187 -- against M_e when relation e was touched.
+template <int NE>
+__device__ __forceinline__ void transr_finish_entity(const RArgs& ra, int e, float* sM, float* sV, int lane, uint8_t stamp,
+                                                     uint8_t next_stamp, bool own, float4 x4, float4 d4) {
+   const TrainArgs& a = ra.base;
+   const int P = a.P, D = a.D;
+   const bool on = lane < (P >> 2);
+   int r0 = 0x7fffffff, r1 = -1;
+   if (own) {
+      x4 = x4 + d4;
+      const float len = sqrtf(warp_sum(dot4(x4, x4)));
+      x4 = make_float4(x4.x / len, x4.y / len, x4.z / len, x4.w / len);
+      if (on) st_cg4(a.dtab + (size_t)e * P + lane * 4, f4(0.f));
+      r0 = __ldcg(a.rmin + e);
+      r1 = __ldcg(a.rmax + e);
+      if (lane == 0) { a.rmin[e] = 0x7fffffff; a.rmax[e] = -1; }
+   }
+   if (on) reinterpret_cast<float4*>(sV + S_H * P)[lane] = x4;
+   __syncwarp();
+   float x[NE];
+   get_slot<NE>(sV + S_H * P, D, lane, x);
+   if (own && r1 >= 0) {
+      transr_constraint<NE>(ra, r0, sM, sV, lane, next_stamp, x);
+      if (r1 != r0) transr_constraint<NE>(ra, r1, sM, sV, lane, next_stamp, x);
+   }
+   const bool quirk = !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK) && e < a.nR && __ldcg(a.flag + a.nE + e) == stamp;
+   if (quirk && !(own && (r0 == e || r1 == e))) transr_constraint<NE>(ra, e, sM, sV, lane, next_stamp, x);
+   // slot S_H holds the final row (transr_constraint keeps it current)
+   if (on) st_cg4(a.tab + (size_t)e * P + lane * 4, reinterpret_cast<const float4*>(sV + S_H * P)[lane]);
+   __syncwarp();
+}
+
+template <int NE>
+__device__ __forceinline__ void transr_publish(const RArgs& ra, long long row_begin, long long row_end, long long g0, long long G,
+                                               uint8_t stamp, uint8_t next_stamp, float* sM, float* sV, int lane, uint32_t& tent,
+                                               uint32_t& trel) {
+   const TrainArgs& a = ra.base;
+   const int P = a.P;
+   const bool on = lane < (P >> 2);
+   const bool quirk = !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK);
+   long long first, end;
+   group_range(row_begin, row_end, g0, G, first, end);
+   auto stamped = [&](long long r) {
+      bool f = __ldcg(a.flag + r) == stamp;
+      // transr/trainer.cpp:187: entity row e is also visited when RELATION e was touched
+      if (quirk && r < a.nE && r < a.nR) f = f || __ldcg(a.flag + a.nE + r) == stamp;
+      return f;
+   };
+   auto finish = [&](long long r, float4 x, float4 d) {
+      if (r >= a.nE) {
+         transr_finish_relation<NE>(ra, (int)(r - a.nE), sM, sV, lane, x, d);
+         trel += (lane == 0);
+      } else {
+         const bool own = __ldcg(a.flag + r) == stamp;
+         transr_finish_entity<NE>(ra, (int)r, sM, sV, lane, stamp, next_stamp, own, x, d);
+         tent += (lane == 0 && own);
+      }
+   };
+   for_stamped_rows<32>(first, end, lane, 0xffffffffu, lane, stamped, [&](long long r0, long long r1) {
+      const float4 x0 = on ? ld_cg4(a.tab + (size_t)r0 * P + lane * 4) : f4(0.f);
+      const float4 d0 = on ? ld_cg4(a.dtab + (size_t)r0 * P + lane * 4) : f4(0.f);
+      float4 x1 = f4(0.f), d1 = f4(0.f);
+      if (r1 >= 0 && on) {
+         x1 = ld_cg4(a.tab + (size_t)r1 * P + lane * 4);
+         d1 = ld_cg4(a.dtab + (size_t)r1 * P + lane * 4);
+      }
+      finish(r0, x0, d0);
+      if (r1 >= 0) finish(r1, x1, d1);
+   });
+}
+
+template <int NE>
+__global__ void __launch_bounds__(kRMaxThreads, 1) train_transr_kernel(const __grid_constant__ RArgs ra) {
+   extern __shared__ float4 smem4[];
+   __shared__ double s_loss[kRMaxThreads / 32];
+   const TrainArgs& a = ra.base;
+   const int lane = threadIdx.x & 31;
+   const int warp = threadIdx.x >> 5;
+   float* sM = reinterpret_cast<float*>(smem4) + (size_t)warp * ra.warp_floats;
+   float* sV = sM + ra.vec_off;
+   const int warps = blockDim.x >> 5;
+   const long long G = (long long)gridDim.x * warps;
+   const long long g0 = (long long)warp * gridDim.x + blockIdx.x;   // round-robin over CTAs
+   const long long R = (long long)a.nE + a.nR;
+   uint32_t bar_target = 0;
+   uint32_t active_acc = 0, tent_acc = 0, trel_acc = 0;
+   int trace_slot = 0;
+#define KB2E_RTRACE()                                                                                 \
+   if (a.trace != nullptr && threadIdx.x == 0 && trace_slot < kTraceSlots) {                          \
+      unsigned long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+      a.trace[(size_t)blockIdx.x * kTraceSlots + trace_slot++] = t_;                                  \
+   }
+   const uint32_t gb_first = (uint32_t)a.first_epoch * (uint32_t)a.batches;
+   Pair pre;
+   const bool has_first = g0 < a.batchsize;
+   if (has_first) pre = draw_pair(a, (uint32_t)g0, gb_first);
+
+   for (int ep = 0; ep < a.n_epochs; ep++) {
+      double loss_acc = 0.0;
+      for (int batch = 0; batch < a.batches; batch++) {
+         const uint32_t gb = gb_first + (uint32_t)ep * (uint32_t)a.batches + (uint32_t)batch;
+         const uint8_t stamp = (uint8_t)(gb % 255u + 1u);
+         const uint8_t next_stamp = (uint8_t)((gb + 1u) % 255u + 1u);
+         KB2E_RTRACE();
+         if (has_first) transr_pair<NE>(ra, pre, sM, sV, lane, stamp, loss_acc, active_acc);
+         for (long long k = g0 + G; k < a.batchsize; k += G) {
+            Pair s = draw_pair(a, (uint32_t)k, gb);
+            transr_pair<NE>(ra, s, sM, sV, lane, stamp, loss_acc, active_acc);
+         }
+         KB2E_RTRACE();
+         grid_barrier(a.barrier, bar_target);
+         KB2E_RTRACE();
+         transr_publish<NE>(ra, a.nE, R, g0, G, stamp, next_stamp, sM, sV, lane, tent_acc, trel_acc);
+         grid_barrier(a.barrier, bar_target);
+         KB2E_RTRACE();
+         transr_publish<NE>(ra, 0, a.nE, g0, G, stamp, next_stamp, sM, sV, lane, tent_acc, trel_acc);
+         KB2E_RTRACE();
+         grid_arrive(a.barrier, bar_target);
+         if (has_first && !(ep == a.n_epochs - 1 && batch == a.batches - 1)) pre = draw_pair(a, (uint32_t)g0, gb + 1u);
+         grid_wait(a.barrier, bar_target);
+      }
+      double v = (lane == 0) ? loss_acc : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_loss[warp] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+         double t = 0.0;
+         for (int i = 0; i < warps; i++) t += s_loss[i];
+         if (t != 0.0) atomicAdd(a.loss + ep, t);
+      }
+      __syncthreads();
+   }
+   uint32_t c0 = (lane == 0) ? active_acc : 0u, c1 = tent_acc, c2 = trel_acc;
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+   }
+   if (lane == 0) {
+      if (c0) atomicAdd(a.counters + 0, (unsigned long long)c0);
+      if (c1) atomicAdd(a.counters + 1, (unsigned long long)c1);
+      if (c2) atomicAdd(a.counters + 2, (unsigned long long)c2);
+   }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------
+int train_transr_launch(kb2e_ctx* c, const TrainArgs& base, int* threads_out) {
+   if (c->P > 128) return fail(c, KB2E_ERR_LIMIT, "TransR training supports embedding sizes up to 128");
+   RArgs a;
+   a.base = base;
+   a.pitch = c->P + 1;
+   a.vec_off = (c->D * a.pitch + 3) / 4 * 4;
+   a.warp_floats = a.vec_off + kRSlots * c->P;
+   const int P4 = c->P / 4;
+   a.p4_magic = (uint32_t)(((1ull << 32) + P4 - 1) / P4);
+   int dev_smem = 0;
+   KB2E_CUDA(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+   const size_t per_warp = (size_t)a.warp_floats * sizeof(float);
+   int warps = (int)std::min<size_t>(kRMaxThreads / 32, ((size_t)dev_smem - 1024) / per_warp);
+   if (const char* env = getenv("KB2E_TRANSR_WARPS")) warps = std::max(1, std::min(warps, atoi(env)));
+   if (warps < 1) return fail(c, KB2E_ERR_LIMIT, "TransR projection matrix does not fit in shared memory");
+   const int ne = (c->D + 31) / 32;
+   void (*k)(const RArgs) = ne == 1 ? train_transr_kernel<1> : (ne == 2 ? train_transr_kernel<2> : (ne == 3 ? train_transr_kernel<3> : train_transr_kernel<4>));
+   const size_t smem = per_warp * warps;
+   KB2E_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   void* params[] = {&a};
+   *threads_out = warps * 32;
+   KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(warps * 32), params, smem, c->stream));
+   return KB2E_OK;
+}
+
+}  // namespace kb2e

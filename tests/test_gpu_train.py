@@ -181,6 +181,34 @@ def test_epoch_loop_matches_cpu_port_and_learns(gpu_lib, oracle):
         assert np.isfinite(ctx.download(TABLE_RELATION)).all()
 
 
+def test_lazy_publish_kernel_matches_two_barrier_kernel(gpu_lib, monkeypatch):
+    """The opt-in one-barrier-per-batch kernel (train_lazy.cu, KB2E_TRAIN_LAZY) has the semantics of the default
+    kernel: same samples, same deferred renormalisation, so tables agree up to the order of float additions."""
+    from kb2e_b200 import kg
+    g = kg.make_kg("tiny", seed=4)
+    nE, nR, batches, seed = g["nE"], g["nR"], 10, 77
+    hm, tm = kg.bern_stats(g["train"], nR)
+    for D, dist in ((20, 0), (100, 1)):
+        rng = np.random.default_rng(D)
+        ent = f32(rng.normal(0, 1.0 / D, (nE, D)))
+        rel = f32(rng.normal(0, 1.0 / D, (nR, D)))
+        got = []
+        for lazy in ("0", "2"):
+            monkeypatch.setenv("KB2E_TRAIN_LAZY", lazy)
+            with make_ctx("transe", D, nE, nR, method=1, distance=dist, batches=batches, rate=LR, margin=1.0, seed=seed) as ctx:
+                ctx.set_train_triples(g["train"])
+                ctx.set_bern(hm, tm)
+                upload_tables(ctx, ent, rel, None)
+                loss = np.concatenate([ctx.train_epochs(0, 3), ctx.train_epochs(3, 2)])
+                got.append((loss,) + download_tables(ctx)[:2] + (ctx.train_stats(),))
+        monkeypatch.delenv("KB2E_TRAIN_LAZY")
+        (l0, e0, r0, s0), (l1, e1, r1, s1) = got
+        assert np.allclose(l0, l1, rtol=1e-4)
+        assert np.abs(e0 - e1).max() < 5e-3 and np.abs(e0 - e1).mean() < 2e-5
+        assert np.abs(r0 - r1).max() < 5e-3
+        assert abs(s0["active"] - s1["active"]) <= 1e-3 * s0["active"] + 2
+
+
 def test_init_embeddings_statistics(gpu_lib):
     """N(0, (1/D)^2) per element, rows inside the unit ball; TransH normals unit length."""
     from kb2e_b200 import TABLE_ENTITY, TABLE_WEIGHTS

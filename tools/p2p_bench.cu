@@ -54,5 +54,24 @@ int main() {
                double bytes = (double)warps * per_warp * P * 4;
                printf("%-6s %-20s rows in flight/warp %d: %.3f ms, %.1f GB/s\n", remote ? "PEER" : "local", names[mode], inflight, ms, bytes / ms / 1e6);
             }
+   // sustained + bidirectional: both GPUs gather / scatter from each other at the same time, ~3 GB each
+   CK(cudaSetDevice(1)); CK(cudaDeviceEnablePeerAccess(0, 0));
+   float* sink1; CK(cudaMalloc(&sink1, 64));
+   cudaEvent_t f0, f1; cudaEventCreate(&f0); cudaEventCreate(&f1);
+   for (int mode = 0; mode < 3; mode++)
+      for (int both = 0; both < 2; both++) {
+         int per_warp = 1024, threads = 768, warps = 148 * threads / 32;
+         CK(cudaSetDevice(0)); cudaEventRecord(e0);
+         rows<<<148, threads>>>(t1, nrows, P, per_warp, mode, 1, sink);
+         cudaEventRecord(e1);
+         if (both) { CK(cudaSetDevice(1)); cudaEventRecord(f0); rows<<<148, threads>>>(t0, nrows, P, per_warp, mode, 1, sink1); cudaEventRecord(f1); }
+         CK(cudaSetDevice(0)); CK(cudaDeviceSynchronize());
+         CK(cudaSetDevice(1)); CK(cudaDeviceSynchronize());
+         float ms, ms1 = 0; cudaEventElapsedTime(&ms, e0, e1); if (both) cudaEventElapsedTime(&ms1, f0, f1);
+         double bytes = (double)warps * per_warp * P * 4;
+         printf("sustained %-20s %s: GPU0 %.2f ms %.1f GB/s", names[mode], both ? "both directions" : "one direction ", ms, bytes / ms / 1e6);
+         if (both) printf(" | GPU1 %.2f ms %.1f GB/s", ms1, bytes / ms1 / 1e6);
+         printf("\n");
+      }
    return 0;
 }
