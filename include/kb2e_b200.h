@@ -133,12 +133,13 @@ int kb2e_get_rank_stats(kb2e_ctx* ctx, kb2e_rank_stats* out);
 
 /* ---- entity-partitioned training across the GPUs of one NVLink box (TransE; BASELINE configs[4]) ----
  * One context per process per GPU.  Entity row e lives on rank e % world at local index e / world;
- * relation rows are replicated.  kb2e_dist_setup allocates this rank's arena and returns a 64-byte
- * CUDA IPC handle; the caller exchanges the handles of all ranks (any transport) and passes the
- * world x 64 bytes, in rank order, to kb2e_dist_connect.  All ranks must then call
- * kb2e_dist_train_epochs with the same arguments: the kernels exchange rows and updates with peer
- * loads / vector REDs over NVLink and synchronise on peer-mapped counters; no host step in between.
- * Train triples and bern statistics are set per rank with kb2e_set_train_triples / kb2e_set_bern.
+ * relation rows are replicated.  Train triples and bern statistics are set per rank with
+ * kb2e_set_train_triples / kb2e_set_bern BEFORE kb2e_dist_setup (the batch size sizes the exchange
+ * buffers).  kb2e_dist_setup allocates this rank's arena and returns a 64-byte CUDA IPC handle; the
+ * caller exchanges the handles of all ranks (any transport) and passes the world x 64 bytes, in rank
+ * order, to kb2e_dist_connect.  All ranks must then call kb2e_dist_train_epochs with the same
+ * arguments: the kernels exchange row requests, rows and updates with posted peer stores / vector
+ * REDs over NVLink and synchronise on peer-mapped counters; no host step in between.
  * loss_per_epoch receives this rank's share of the loss (add across ranks).
  * Tables: KB2E_TABLE_ENTITY = this rank's rows [ceil((N_E - rank) / world)][dim] (global ids rank,
  * rank + world, ...); KB2E_TABLE_RELATION = the replica [N_R][dim]. */

@@ -744,7 +744,8 @@ static int threads_for(int model, int nv) {
    const char* env = getenv("KB2E_TRAIN_THREADS");
    if (env) return atoi(env);
    if (nv >= 4) return 512;
-   if (nv == 2 || model != KB2E_MODEL_TRANSE) return 768;
+   if (model == KB2E_MODEL_TRANSH) return 512;   // five rows per sample live in registers: 768 threads (80 registers) spill
+   if (nv == 2) return 768;
    return 1024;
 }
 

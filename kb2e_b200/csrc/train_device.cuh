@@ -104,30 +104,53 @@ __device__ __forceinline__ void norm_row(float4 (&v)[NV], bool ignoreShort, uint
 
 // The loop of common::norm(a, b, rate), common/utils.cpp:83-108 (`sum` is deliberately not reset
 // between iterations, as in the reference).  b must already be unit length.  Returns #corrective steps.
+//
+// Every pass of the reference's loop rescales b and mixes a and b linearly (b /= sum; a -= rate b; b -= rate a),
+// so a and b stay in the plane of the initial vectors: a = a1 a0 + a2 b0, b = b1 a0 + b2 b0.  The loop therefore
+// runs on the three scalars A = |a|^2, B = |b|^2, X = a.b (one fused group reduction up front) and the four
+// coefficients -- no per-iteration shuffle reductions on the dependent path (tens of iterations are common when
+// d_r . w_r starts far above the 0.1 threshold) -- and the vectors are rebuilt once at the end.
 template <int LPS, int NV>
 __device__ __forceinline__ int soft_orth_loop(float4 (&a)[NV], float4 (&b)[NV], float rate, uint32_t gmask) {
-   float sum = 0.f;
+   float A = 0.f, B = 0.f, X = 0.f;
+#pragma unroll
+   for (int q = 0; q < NV; q++) {
+      A += dot4(a[q], a[q]);
+      B += dot4(b[q], b[q]);
+      X += dot4(a[q], b[q]);
+   }
+#pragma unroll
+   for (int o = LPS / 2; o > 0; o >>= 1) {
+      A += __shfl_xor_sync(gmask, A, o);
+      B += __shfl_xor_sync(gmask, B, o);
+      X += __shfl_xor_sync(gmask, X, o);
+   }
+   float a1 = 1.f, a2 = 0.f, b1 = 0.f, b2 = 1.f, sum = 0.f;
    int iters = 0;
    while (true) {
-      sum += len2_row<LPS, NV>(b, gmask);
-      sum = sqrtf(sum);
-      float x = 0.f;
-#pragma unroll
-      for (int q = 0; q < NV; q++) {
-         b[q] = make_float4(b[q].x / sum, b[q].y / sum, b[q].z / sum, b[q].w / sum);
-         x += dot4(a[q], b[q]);
-      }
-      x = gsum<LPS>(x, gmask);
-      if (x > 0.1f && iters < 1000) {
-#pragma unroll
-         for (int q = 0; q < NV; q++) {
-            a[q] = a[q] - rate * b[q];
-            b[q] = b[q] - rate * a[q];
-         }
+      sum = sqrtf(sum + B);
+      const float inv = 1.f / sum;
+      b1 *= inv; b2 *= inv;            // b /= sum
+      B *= inv * inv;
+      X *= inv;                        // x = a . b
+      if (X > 0.1f && iters < 1000) {
+         a1 -= rate * b1; a2 -= rate * b2;                           // a -= rate * b
+         const float A1 = A - 2.f * rate * X + rate * rate * B;
+         const float X1 = X - rate * B;                              // a_new . b
+         b1 -= rate * a1; b2 -= rate * a2;                           // b -= rate * a_new
+         const float B1 = B - 2.f * rate * X1 + rate * rate * A1;
+         X = X1 - rate * A1;
+         A = A1; B = B1;
          iters++;
       } else {
          break;
       }
+   }
+#pragma unroll
+   for (int q = 0; q < NV; q++) {
+      const float4 a0 = a[q], b0 = b[q];
+      if (iters > 0) a[q] = a1 * a0 + a2 * b0;
+      b[q] = b1 * a0 + b2 * b0;
    }
    return iters;
 }

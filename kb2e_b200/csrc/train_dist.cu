@@ -4,20 +4,28 @@
 // One process (context) per GPU.  Entity row e lives on GPU e % G at local index e / G; the relation
 // table is small and replicated.  Every rank maps every peer's arena with CUDA IPC, so the persistent
 // kernel of each GPU dereferences peer pointers directly -- no NCCL call and no host step inside an
-// epoch.  Measured on this pool (tools/p2p_bench.cu): random 800-byte row gathers from a peer run at
-// ~570 GB/s and row scatters at ~640 GB/s in isolation, but remote loads queue behind posted remote
-// writes when both are in flight, so every phase moves data across NVLink in ONE direction only:
+// epoch.  Measured on this pool (tools/p2p_bench.cu, tools/ipc_bench.cu, 2 x B200 over NV18): random
+// 800-byte row WRITES / REDs to a peer run at ~640 GB/s, but random row READS through an IPC mapping
+// reach only ~190 GB/s (315 GB/s through a cuMem fd-shared mapping, 570 GB/s inside one process), and
+// remote loads also queue behind posted writes.  So nothing is ever loaded across NVLink: every
+// transfer is a posted write issued by the side that holds the data.
 //   phase 1a  rank g takes the samples k = g (mod G) of the batch (the counter RNG makes the sample set
-//             independent of G) and gathers their h / t / c rows from the owners into a local row cache
-//             (remote READS only, two samples = six rows in flight per group)
-//   phase 1b  scores the cached rows and accumulates the update with local vector REDs: rows it owns
-//             straight into its delta table, rows owned by a peer into a local staging table; stamps them
+//             independent of G), one sample per thread, and for every row it does not own writes an
+//             8-byte request (local row index, launch-unique stamp) into the owner's request table at
+//             the slot (sample, h|t|c) -- no atomics: the slot IS the return address
 //   barrier   (local grid barrier + cross-GPU barrier on peer-mapped counters, system-scope atomics)
+//   phase 1s  every owner scans the request tables of its peers (coalesced stamp test + ballot) and
+//             writes each requested row into the requester's row cache
+//   barrier
+//   phase 1b  scores every sample (own rows straight from the table, remote rows from the cache) and
+//             accumulates the update with local vector REDs: rows it owns into its delta table, rows
+//             owned by a peer into a local staging table; stamps them
+//   barrier
 //   phase 2a  staged rows are added into the owner's delta table with red.global.add.v4.f32 over NVLink
-//             and the owner's stamp is set (remote WRITES only)
+//             and the owner's stamp is set
 //   barrier
 //   phase 2b  every owner publishes its stamped rows (row += delta, normalise once); the owner of a
-//             relation row also writes the new row into every replica (remote writes)
+//             relation row also writes the new row into every replica
 //   barrier
 // Semantics are identical to the single-GPU kernel (same samples, same deferred renormalisation), so
 // results agree up to the order of float additions.  Loss and counters are per rank (the host adds them).
@@ -41,24 +49,25 @@ struct DistArgs {
    TrainArgs base;                     // sampler fields (triples, hash, pr, seeds, nE, n_train) + lr, margin, distance, D, P
    unsigned char* arena[kMaxPeers];    // arena[g] = rank g's arena as mapped into this process
    // arena layout: tab [rows_local][P] | dtab [rows_local][P] | flag [rows_local] |
-   //               rel [nR][P] (replica) | drel [nR][P] | rflag [nR] | cross-GPU counter
-   size_t off_tab, off_dtab, off_flag, off_rel, off_drel, off_rflag, off_xbar;
+   //               rel [nR][P] (replica) | drel [nR][P] | rflag [nR] | cross-GPU counter |
+   //               req [world][req_cap] int2 (written by the peers) | cache [req_cap][P] (written by the peers)
+   size_t off_tab, off_dtab, off_flag, off_rel, off_drel, off_rflag, off_xbar, off_req, off_cache;
+   long long req_cap;                  // 3 x the largest per-rank share of a batch
    float* stage;                       // local: updates for rows owned by peers, [nE + nR][P] (global row ids)
    uint8_t* sflag;                     // local: stamps of the staged rows, [nE + nR]
-   float* cache;                       // local: gathered rows of this rank's samples, [samples][3][P]
    int4* pairs;                        // local: (h, t, r, c | corruptTail << 31) per sample
+   uint32_t stamp_base;                // launch-unique high bits of the request stamps
    uint32_t* local_bar;
    int rank, world, wshift;
    int rows_local;
    uint32_t xbase;                     // value of every rank's cross-GPU counter when this launch starts
-   int debug;                          // tuning aid (KB2E_DIST_DEBUG bit 2): gather entity rows from the local arena
 };
 
-// published value of entity row e (on its owner)
-__device__ __forceinline__ const float* ent_row(const DistArgs& a, int e) {
-   int g = e & (a.world - 1);
-   if (a.debug & 2) g = a.rank;   // tuning aid only
-   return reinterpret_cast<const float*>(a.arena[g] + a.off_tab) + (size_t)(e >> a.wshift) * a.base.P;
+// value of entity row e as this rank sees it in phase 1b: its own table, or the cache slot the owner filled
+__device__ __forceinline__ const float* ent_row(const DistArgs& a, int e, long long slot) {
+   if ((e & (a.world - 1)) == a.rank)
+      return reinterpret_cast<const float*>(a.arena[a.rank] + a.off_tab) + (size_t)(e >> a.wshift) * a.base.P;
+   return reinterpret_cast<const float*>(a.arena[a.rank] + a.off_cache) + (size_t)slot * a.base.P;
 }
 // where this rank accumulates its update of entity row e, and the stamp that goes with it
 __device__ __forceinline__ float* ent_delta(const DistArgs& a, int e, uint8_t*& flag) {
@@ -101,14 +110,14 @@ __device__ __forceinline__ void cross_barrier(const DistArgs& a, uint32_t& ltarg
 }
 
 template <int LPS, int NV>
-__device__ __forceinline__ void dist_process_pair(const DistArgs& a, const Pair s, const float* rows, int gl, uint32_t gmask,
+__device__ __forceinline__ void dist_process_pair(const DistArgs& a, const Pair s, long long j, int gl, uint32_t gmask,
                                                   uint8_t stamp, double& loss_acc, uint32_t& active_acc) {
    const TrainArgs& b = a.base;
    const int P = b.P, D = b.D;
    float4 vh[NV], vt[NV], vc[NV], vr[NV];
-   load_row<LPS, NV>(rows, P, gl, vh);            // cached copies gathered in phase 1a
-   load_row<LPS, NV>(rows + P, P, gl, vt);
-   load_row<LPS, NV>(rows + 2 * P, P, gl, vc);
+   load_row<LPS, NV>(ent_row(a, s.h, 3 * j), P, gl, vh);
+   load_row<LPS, NV>(ent_row(a, s.t, 3 * j + 1), P, gl, vt);
+   load_row<LPS, NV>(ent_row(a, s.c, 3 * j + 2), P, gl, vc);
    load_row<LPS, NV>(reinterpret_cast<float*>(a.arena[a.rank] + a.off_rel) + (size_t)s.r * P, P, gl, vr);   // local replica
    const bool l1 = b.distance == KB2E_DISTANCE_L1;
    float4 rp[NV], rn[NV];
@@ -191,52 +200,68 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
       b.trace[(size_t)blockIdx.x * kTraceSlots + trace_slot++] = t_;                                  \
    }
    const uint32_t gb_first = (uint32_t)b.first_epoch * (uint32_t)b.batches;
-   Pair pre;
-   const bool has_first = g0 < my_count;
-   if (has_first) pre = draw_pair(b, (uint32_t)(g0 * a.world + a.rank), gb_first);
+   const long long T = (long long)gridDim.x * blockDim.x;
+   const long long t0 = (long long)threadIdx.x * gridDim.x + blockIdx.x;
    // peers may still be zeroing / publishing from the previous launch
    cross_barrier(a, ltarget, xtarget);
 
    for (int ep = 0; ep < b.n_epochs; ep++) {
       double loss_acc = 0.0;
       for (int batch = 0; batch < b.batches; batch++) {
-         const uint32_t gb = gb_first + (uint32_t)ep * (uint32_t)b.batches + (uint32_t)batch;
+         const uint32_t rel_batch = (uint32_t)(ep * b.batches + batch);
+         const uint32_t gb = gb_first + rel_batch;
          const uint8_t stamp = (uint8_t)(gb % 255u + 1u);
+         const int rstamp = (int)(a.stamp_base + rel_batch + 1u);   // unique per batch and per launch, never 0
          KB2E_DTRACE();
-         // ---- phase 1a: gather (remote reads only); two samples per step keep six rows in flight ----
-         for (long long j = g0; j < my_count; j += 2 * G) {
-            const long long j1 = j + G;
-            const bool two = j1 < my_count;
-            Pair s0 = (j == g0 && has_first) ? pre : draw_pair(b, (uint32_t)(j * a.world + a.rank), gb);
-            Pair s1 = s0;
-            if (two) s1 = draw_pair(b, (uint32_t)(j1 * a.world + a.rank), gb);
-            float4 v0[3][NV], v1[3][NV];
-            load_row<LPS, NV>(ent_row(a, s0.h), P, gl, v0[0]);
-            load_row<LPS, NV>(ent_row(a, s0.t), P, gl, v0[1]);
-            load_row<LPS, NV>(ent_row(a, s0.c), P, gl, v0[2]);
-            if (two) {
-               load_row<LPS, NV>(ent_row(a, s1.h), P, gl, v1[0]);
-               load_row<LPS, NV>(ent_row(a, s1.t), P, gl, v1[1]);
-               load_row<LPS, NV>(ent_row(a, s1.c), P, gl, v1[2]);
-            }
-            if (gl == 0) a.pairs[j] = make_int4(s0.h, s0.t, s0.r, s0.c | (s0.corruptTail ? 0x80000000 : 0));
-            float* c0 = a.cache + (size_t)j * 3 * P;
+         // ---- phase 1a: one sample per thread: draw, record, request the rows owned by peers ----
+         for (long long j = t0; j < my_count; j += T) {
+            const Pair s = draw_pair(b, (uint32_t)(j * a.world + a.rank), gb);
+            a.pairs[j] = make_int4(s.h, s.t, s.r, s.c | (s.corruptTail ? 0x80000000 : 0));
 #pragma unroll
-            for (int w = 0; w < 3; w++) store_row<LPS, NV>(c0 + w * P, P, gl, v0[w]);
-            if (two) {
-               if (gl == 0) a.pairs[j1] = make_int4(s1.h, s1.t, s1.r, s1.c | (s1.corruptTail ? 0x80000000 : 0));
-               float* c1 = a.cache + (size_t)j1 * 3 * P;
-#pragma unroll
-               for (int w = 0; w < 3; w++) store_row<LPS, NV>(c1 + w * P, P, gl, v1[w]);
+            for (int w = 0; w < 3; w++) {
+               const int e = w == 0 ? s.h : (w == 1 ? s.t : s.c);
+               const int g = e & (a.world - 1);
+               if (g != a.rank) {
+                  int2* req = reinterpret_cast<int2*>(a.arena[g] + a.off_req) + (size_t)a.rank * a.req_cap + 3 * j + w;
+                  *req = make_int2(e >> a.wshift, rstamp);
+               }
             }
          }
          KB2E_DTRACE();
-         // ---- phase 1b: score + accumulate, everything local (same group <-> same samples: no barrier) ----
+         cross_barrier(a, ltarget, xtarget);
+         KB2E_DTRACE();
+         // ---- phase 1s: serve the peers' requests: own row -> the requester's cache slot ----
+         if (a.world > 1) {
+            const int2* req = reinterpret_cast<const int2*>(me + a.off_req);
+            long long first, end;
+            group_range(0, (long long)a.world * a.req_cap, g0, G, first, end);
+            for_stamped_rows<LPS>(first, end, gl, gmask, lane, [&](long long r) { return __ldcg(&req[r].y) == rstamp; },
+                                  [&](long long r0, long long r1) {
+               float4 v0[NV], v1[NV];
+               const int l0 = __ldcg(&req[r0].x);
+               load_row<LPS, NV>(tab + (size_t)l0 * P, P, gl, v0);
+               if (r1 >= 0) {
+                  const int l1 = __ldcg(&req[r1].x);
+                  load_row<LPS, NV>(tab + (size_t)l1 * P, P, gl, v1);
+               }
+               auto send = [&](long long r, float4 (&v)[NV]) {
+                  const int pr = (int)(r / a.req_cap);
+                  const long long slot = r - (long long)pr * a.req_cap;
+                  store_row<LPS, NV>(reinterpret_cast<float*>(a.arena[pr] + a.off_cache) + (size_t)slot * P, P, gl, v);
+               };
+               send(r0, v0);
+               if (r1 >= 0) send(r1, v1);
+            });
+         }
+         KB2E_DTRACE();
+         cross_barrier(a, ltarget, xtarget);
+         KB2E_DTRACE();
+         // ---- phase 1b: score + accumulate, everything local ----
          for (long long j = g0; j < my_count; j += G) {
             const int4 pr = __ldcg(a.pairs + j);
             Pair s;
             s.h = pr.x; s.t = pr.y; s.r = pr.z; s.c = pr.w & 0x7fffffff; s.corruptTail = pr.w < 0;
-            dist_process_pair<LPS, NV>(a, s, a.cache + (size_t)j * 3 * P, gl, gmask, stamp, loss_acc, active_acc);
+            dist_process_pair<LPS, NV>(a, s, j, gl, gmask, stamp, loss_acc, active_acc);
          }
          KB2E_DTRACE();
          cross_barrier(a, ltarget, xtarget);
@@ -317,8 +342,6 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
                store_row<LPS, NV>(reinterpret_cast<float*>(a.arena[g] + a.off_rel) + (size_t)r * P, P, gl, x);
             trel_acc += (gl == 0);
          }
-         if (has_first && !(ep == b.n_epochs - 1 && batch == b.batches - 1))
-            pre = draw_pair(b, (uint32_t)(g0 * a.world + a.rank), gb + 1u);
          KB2E_DTRACE();
          cross_barrier(a, ltarget, xtarget);
       }
@@ -407,12 +430,13 @@ struct DistState {
    long long rows_local = 0;
    unsigned char* arena = nullptr;
    size_t arena_bytes = 0;
-   size_t off_tab = 0, off_dtab = 0, off_flag = 0, off_rel = 0, off_drel = 0, off_rflag = 0, off_xbar = 0;
+   size_t off_tab = 0, off_dtab = 0, off_flag = 0, off_rel = 0, off_drel = 0, off_rflag = 0, off_xbar = 0, off_req = 0, off_cache = 0;
+   long long req_cap = 0;        // request / cache slots per requester: 3 x the largest per-rank share of a batch
+   long long max_share = 0;
    float* stage = nullptr;
    uint8_t* sflag = nullptr;
-   float* cache = nullptr;
    int4* pairs = nullptr;
-   long long cache_samples = 0;
+   uint32_t launches = 0;
    unsigned char* peers[kMaxPeers] = {};
    bool connected = false;
    uint32_t xcount = 0;   // cross-GPU barrier arrivals so far (identical on every rank: the counters are never reset)
@@ -429,6 +453,8 @@ int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) 
    if (c->cfg.model != KB2E_MODEL_TRANSE) return fail(c, KB2E_ERR_LIMIT, "partitioned training is built for TransE");
    if (world < 1 || world > kMaxPeers || (world & (world - 1)) || rank < 0 || rank >= world)
       return fail(c, KB2E_ERR_ARG, "kb2e_dist_setup: world must be 1, 2, 4 or 8 and 0 <= rank < world");
+   if (!c->triples || c->n_train == 0 || c->cfg.batches <= 0)
+      return fail(c, KB2E_ERR_ARG, "kb2e_dist_setup: call kb2e_set_train_triples first (the batch size sizes the exchange buffers)");
    int rc = train_alloc(c);   // barrier counter, counters, pr
    if (rc) return rc;
    DistState* d = new DistState();
@@ -448,6 +474,11 @@ int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) 
    d->off_drel = off; off = align_up(off + rel_bytes, 256);
    d->off_rflag = off; off = align_up(off + (size_t)c->nR, 256);
    d->off_xbar = off; off = align_up(off + 64, 256);
+   // exchange buffers: this rank's request table (one region per requester) and its row cache
+   d->max_share = (c->n_train / c->cfg.batches + world - 1) / world;
+   d->req_cap = 3 * d->max_share;
+   d->off_req = off; off = align_up(off + (size_t)world * d->req_cap * sizeof(int2), 256);
+   d->off_cache = off; off = align_up(off + (world > 1 ? (size_t)d->req_cap * c->P * sizeof(float) : 0), 256);
    d->arena_bytes = off;
    KB2E_CUDA(c, cudaMalloc(&d->arena, d->arena_bytes));
    KB2E_CUDA(c, cudaMemset(d->arena, 0, d->arena_bytes));
@@ -456,6 +487,7 @@ int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) 
    KB2E_CUDA(c, cudaMemset(d->stage, 0, stage_rows * c->P * sizeof(float)));
    KB2E_CUDA(c, cudaMalloc(&d->sflag, stage_rows));
    KB2E_CUDA(c, cudaMemset(d->sflag, 0, stage_rows));
+   KB2E_CUDA(c, cudaMalloc(&d->pairs, (size_t)d->max_share * sizeof(int4)));
    cudaIpcMemHandle_t h;
    KB2E_CUDA(c, cudaIpcGetMemHandle(&h, d->arena));
    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -554,21 +586,17 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    for (int g = 0; g < d->world; g++) a.arena[g] = d->peers[g];
    a.off_tab = d->off_tab; a.off_dtab = d->off_dtab; a.off_flag = d->off_flag; a.off_rel = d->off_rel;
    a.off_drel = d->off_drel; a.off_rflag = d->off_rflag; a.off_xbar = d->off_xbar;
-   a.stage = d->stage; a.sflag = d->sflag;
-   {
-      const long long my_max = (b.batchsize + d->world - 1) / d->world;
-      if (my_max > d->cache_samples) {
-         cudaFree(d->cache); cudaFree(d->pairs);
-         d->cache = nullptr; d->pairs = nullptr; d->cache_samples = 0;
-         KB2E_CUDA(c, cudaMalloc(&d->cache, (size_t)my_max * 3 * c->P * sizeof(float)));
-         KB2E_CUDA(c, cudaMalloc(&d->pairs, (size_t)my_max * sizeof(int4)));
-         d->cache_samples = my_max;
-      }
-      a.cache = d->cache; a.pairs = d->pairs;
-   }
+   a.off_req = d->off_req; a.off_cache = d->off_cache; a.req_cap = d->req_cap;
+   a.stage = d->stage; a.sflag = d->sflag; a.pairs = d->pairs;
+   if ((b.batchsize + d->world - 1) / d->world > d->max_share)
+      return fail(c, KB2E_ERR_ARG, "kb2e_dist_train_epochs: the batch grew after kb2e_dist_setup; set the train triples before kb2e_dist_setup");
+   if ((uint64_t)c->cfg.batches * (uint64_t)n_epochs >= (1u << 20))
+      return fail(c, KB2E_ERR_LIMIT, "kb2e_dist_train_epochs: at most 2^20 batches per call");
+   // request stamps: (launch number << 20) | batch-in-launch + 1: an entry left by an earlier launch can never match
+   d->launches = (d->launches + 1u) & 0x7ffu;
+   a.stamp_base = d->launches << 20;
    a.local_bar = c->barrier;
    a.rank = d->rank; a.world = d->world; a.wshift = d->wshift; a.rows_local = (int)d->rows_local;
-   a.debug = getenv("KB2E_DIST_DEBUG") ? atoi(getenv("KB2E_DIST_DEBUG")) : 0;
    // shape: same rule as the single-GPU kernel, on this rank's share of the batch
    const int vecs = (c->P + 3) / 4;
    int lps = vecs <= 16 ? 16 : 32;
@@ -582,7 +610,7 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    // the peer-mapped cross-GPU counters are monotonic across launches (a reset could wipe a fast peer's
    // arrival); every rank runs the same barrier sequence, so the start value is known on the host
    a.xbase = d->xcount;
-   d->xcount += (uint32_t)d->world * (1u + 3u * (uint32_t)c->cfg.batches * (uint32_t)n_epochs);
+   d->xcount += (uint32_t)d->world * (1u + 5u * (uint32_t)c->cfg.batches * (uint32_t)n_epochs);
    KB2E_CUDA(c, cudaMemsetAsync(c->barrier, 0, 64, c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->loss_dev, 0, (size_t)n_epochs * sizeof(double), c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -635,7 +663,6 @@ void kb2e_dist_teardown(kb2e_ctx* c) {
    cudaFree(d->arena);
    cudaFree(d->stage);
    cudaFree(d->sflag);
-   cudaFree(d->cache);
    cudaFree(d->pairs);
    delete d;
    c->dist = nullptr;

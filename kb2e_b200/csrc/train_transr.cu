@@ -8,10 +8,14 @@
 //   forward   y_i = sum_j M[j][i] e_j     lane owns output dims i = lane, lane + 32, ...; row j of the staged
 //                                          matrix is read with consecutive lanes on consecutive banks and e_j is
 //                                          a shared-memory broadcast
-//   backward  S_j = sum_i g_i M[j][i]     lane owns input dims j; the odd row pitch (P + 1) puts the 32 rows a
-//                                          warp reads at one column on 32 different banks -- no shuffles
-//   transRNorm sweep (sequential in i)    column i against the lane-owned x_j: two shared loads, two FMAs and one
-//                                          warp sum per step, instead of a strided global gather per step
+//   backward  S_j = sum_i g_i M[j][i]     lane owns input dims j and reads its row with 16-byte shared loads; the
+//                                          row pitch is a multiple of 4 floats with pitch/4 odd, which puts the
+//                                          8 rows of a quarter-warp on disjoint banks -- no shuffles
+//   transRNorm sweep (sequential in i)    four columns per step: one 16-byte shared load per lane-owned row, four
+//                                          interleaved warp sums, and a scalar recurrence on the chunk's 4x4 Gram
+//                                          block for the dependence between the four steps (transr_constraint)
+// Phase 2 work (touched relations / entity rows) is compacted into shared-memory lists and dealt dynamically.
+// Staging uses cp.async (16-byte, L2-only) so that all of M_r is in flight at once without holding registers.
 // The dM update is issued as flat, fully coalesced vector REDs over the D*P/4 float4 of M_r.
 // Everything else (sampler, stamps, deferred renormalisation, the transr/trainer.cpp:187 quirk, carrying the
 // constraint's perturbation of M_r into the next batch) is exactly as in train.cu / oracle orc_train_batch_dfr.
@@ -30,7 +34,7 @@ enum { S_H = 0, S_T, S_C, S_R, S_GP, S_GN, S_DP, S_DN, S_SP, S_SN, kRSlots };
 
 struct RArgs {
    TrainArgs base;
-   int pitch;          // row pitch of the staged matrix in floats (odd)
+   int pitch;          // row pitch of the staged matrix in floats (multiple of 4, pitch / 4 odd)
    int vec_off;        // offset of the vector slots inside a warp's slice (floats, multiple of 4)
    int warp_floats;    // floats per warp slice (multiple of 4)
    uint32_t p4_magic;  // ceil(2^32 / (P / 4)): f / (P/4) == umulhi(f, magic) for the flat indices used here
@@ -46,30 +50,44 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Stage M (global, [D][P]) into sM ([D][pitch]); SUM: stage M + dM instead and zero dM (publish of a relation).
 template <bool SUM>
 __device__ __forceinline__ void stage_matrix(const RArgs& a, const float* M, float* dM, float* sM, int lane) {
    const int P4 = a.base.P >> 2;
    const int nF = a.base.D * P4;
-   constexpr int U = 7;
+   if (!SUM) {
+      // asynchronous copies: the caller waits (cp_async_wait_all + __syncwarp) before reading
+      if (a.pitch == a.base.P) {
+         for (int f = lane; f < nF; f += 32) cp_async16(sM + 4 * f, M + 4 * (size_t)f);
+      } else {
+         for (int f = lane; f < nF; f += 32) {
+            const int j = (int)__umulhi((uint32_t)f, a.p4_magic);
+            cp_async16(sM + j * a.pitch + 4 * (f - j * P4), M + 4 * (size_t)f);
+         }
+      }
+      return;
+   }
+   constexpr int U = 4;
    for (int f0 = lane; f0 < nF; f0 += 32 * U) {
-      float4 v[U];
+      float4 v[U], w[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
          const int f = f0 + 32 * u;
          v[u] = f < nF ? ld_cg4(M + 4 * (size_t)f) : f4(0.f);
-         if (SUM && f < nF) {
-            v[u] = v[u] + ld_cg4(dM + 4 * (size_t)f);
-         }
+         w[u] = f < nF ? ld_cg4(dM + 4 * (size_t)f) : f4(0.f);
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
          const int f = f0 + 32 * u;
          if (f < nF) {
             const int j = (int)__umulhi((uint32_t)f, a.p4_magic);
-            float* d = sM + j * a.pitch + 4 * (f - j * P4);
-            d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
-            if (SUM) st_cg4(dM + 4 * (size_t)f, f4(0.f));
+            *reinterpret_cast<float4*>(sM + j * a.pitch + 4 * (f - j * P4)) = v[u] + w[u];
+            st_cg4(dM + 4 * (size_t)f, f4(0.f));
          }
       }
    }
@@ -130,20 +148,15 @@ __device__ __forceinline__ void transr_pair(const RArgs& ra, const Pair s, float
    const bool on = lane < P4;
    const float* M = a.w + (size_t)s.r * a.w_row;
    float* dM = a.dw + (size_t)s.r * a.w_row;
-   {
-      // rows first (they are needed last), then the matrix: everything is in flight together
-      const float4 vh = on ? ld_cg4(a.tab + (size_t)s.h * P + lane * 4) : f4(0.f);
-      const float4 vt = on ? ld_cg4(a.tab + (size_t)s.t * P + lane * 4) : f4(0.f);
-      const float4 vc = on ? ld_cg4(a.tab + (size_t)s.c * P + lane * 4) : f4(0.f);
-      const float4 vr = on ? ld_cg4(a.tab + ((size_t)a.nE + s.r) * P + lane * 4) : f4(0.f);
-      stage_matrix<false>(ra, M, nullptr, sM, lane);
-      if (on) {
-         reinterpret_cast<float4*>(sV + S_H * P)[lane] = vh;
-         reinterpret_cast<float4*>(sV + S_T * P)[lane] = vt;
-         reinterpret_cast<float4*>(sV + S_C * P)[lane] = vc;
-         reinterpret_cast<float4*>(sV + S_R * P)[lane] = vr;
-      }
+   // the four rows and the matrix: everything is in flight together, nothing passes through registers
+   if (on) {
+      cp_async16(sV + S_H * P + lane * 4, a.tab + (size_t)s.h * P + lane * 4);
+      cp_async16(sV + S_T * P + lane * 4, a.tab + (size_t)s.t * P + lane * 4);
+      cp_async16(sV + S_C * P + lane * 4, a.tab + (size_t)s.c * P + lane * 4);
+      cp_async16(sV + S_R * P + lane * 4, a.tab + ((size_t)a.nE + s.r) * P + lane * 4);
    }
+   stage_matrix<false>(ra, M, nullptr, sM, lane);
+   cp_async_wait_all();
    __syncwarp();
    float y[3][NE];
    {
@@ -218,10 +231,9 @@ __device__ __forceinline__ void transr_pair(const RArgs& ra, const Pair s, float
          for (int k = 0; k < NE; k++) {
             const int j = lane + 32 * k;
             if (j < D) {
-               const float* m = sM + j * ra.pitch + i0;   // i0 + 3 <= P - 1 < pitch; padding columns are zero
-               const float m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
-               sp[k] += gp4.x * m0 + gp4.y * m1 + gp4.z * m2 + gp4.w * m3;
-               sn[k] += gn4.x * m0 + gn4.y * m1 + gn4.z * m2 + gn4.w * m3;
+               const float4 m = *reinterpret_cast<const float4*>(sM + j * ra.pitch + i0);   // i0 + 3 <= P - 1; padding columns are zero
+               sp[k] += dot4(gp4, m);
+               sn[k] += dot4(gn4, m);
             }
          }
       }
@@ -256,22 +268,50 @@ __device__ __forceinline__ void transr_pair(const RArgs& ra, const Pair s, float
    __syncwarp();
 }
 
-// ---- phase 2a: relation r -- r unit length; every row M_r[j][.] unit length (transr/trainer.cpp:174,178-180)
+// ---- phase 2a: rows [j_begin, j_end) of relation r -- every row M_r[j][.] unit length after the delta
+// (transr/trainer.cpp:178-180); the segment that starts at row 0 also publishes r itself (unit length, :174).
+// A relation is cut into segments so that the few touched relations of a batch spread over all warps.
 template <int NE>
-__device__ __forceinline__ void transr_finish_relation(const RArgs& ra, int r, float* sM, float* sV, int lane, float4 x, float4 d) {
+__device__ __forceinline__ void transr_finish_relation(const RArgs& ra, int r, int j_begin, int j_end, float* sM, float* sV, int lane) {
    const TrainArgs& a = ra.base;
-   const int P = a.P, D = a.D, P4 = P >> 2;
+   const int P = a.P, P4 = P >> 2;
    const bool on = lane < P4;
-   float* cur = a.tab + ((size_t)a.nE + r) * P + lane * 4;
-   float* del = a.dtab + ((size_t)a.nE + r) * P + lane * 4;
-   float* M = a.w + (size_t)r * a.w_row;
-   float* dM = a.dw + (size_t)r * a.w_row;
-   stage_matrix<true>(ra, M, dM, sM, lane);
-   x = x + d;
-   const float len = sqrtf(warp_sum(dot4(x, x)));
-   if (on) {
-      st_cg4(del, f4(0.f));
-      st_cg4(cur, make_float4(x.x / len, x.y / len, x.z / len, x.w / len));
+   float* M = a.w + (size_t)r * a.w_row + (size_t)j_begin * P;
+   float* dM = a.dw + (size_t)r * a.w_row + (size_t)j_begin * P;
+   const int rows = j_end - j_begin;
+   const int nF = rows * P4;
+   float4 x = f4(0.f), d = f4(0.f);
+   if (j_begin == 0 && on) {
+      x = ld_cg4(a.tab + ((size_t)a.nE + r) * P + lane * 4);
+      d = ld_cg4(a.dtab + ((size_t)a.nE + r) * P + lane * 4);
+   }
+   // M + dM -> shared, dM = 0
+   constexpr int U = 4;
+   for (int f0 = lane; f0 < nF; f0 += 32 * U) {
+      float4 v[U], w[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+         const int f = f0 + 32 * u;
+         v[u] = f < nF ? ld_cg4(M + 4 * (size_t)f) : f4(0.f);
+         w[u] = f < nF ? ld_cg4(dM + 4 * (size_t)f) : f4(0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+         const int f = f0 + 32 * u;
+         if (f < nF) {
+            const int j = (int)__umulhi((uint32_t)f, ra.p4_magic);
+            *reinterpret_cast<float4*>(sM + j * ra.pitch + 4 * (f - j * P4)) = v[u] + w[u];
+            st_cg4(dM + 4 * (size_t)f, f4(0.f));
+         }
+      }
+   }
+   if (j_begin == 0) {
+      x = x + d;
+      const float len = sqrtf(warp_sum(dot4(x, x)));
+      if (on) {
+         st_cg4(a.dtab + ((size_t)a.nE + r) * P + lane * 4, f4(0.f));
+         st_cg4(a.tab + ((size_t)a.nE + r) * P + lane * 4, make_float4(x.x / len, x.y / len, x.z / len, x.w / len));
+      }
    }
    __syncwarp();
    float l[NE];
@@ -279,67 +319,113 @@ __device__ __forceinline__ void transr_finish_relation(const RArgs& ra, int r, f
    for (int k = 0; k < NE; k++) {
       const int j = lane + 32 * k;
       float s2 = 0.f;
-      if (j < D) {
-         const float* m = sM + j * ra.pitch;
-         for (int i = 0; i < D; i++) s2 = fmaf(m[i], m[i], s2);
+      if (j < rows) {
+         const float4* m = reinterpret_cast<const float4*>(sM + j * ra.pitch);
+         for (int i4 = 0; i4 < P4; i4++) { const float4 v = m[i4]; s2 += dot4(v, v); }   // padding columns are zero
       }
       l[k] = sqrtf(s2);
    }
-   put_slot<NE>(sV + S_SP * P, D, P, lane, l);
+   put_slot<NE>(sV + S_SP * P, rows, P, lane, l);
    __syncwarp();
-   const int nF = D * P4;
    for (int f = lane; f < nF; f += 32) {
       const int j = (int)__umulhi((uint32_t)f, ra.p4_magic);
-      const float* m = sM + j * ra.pitch + 4 * (f - j * P4);
+      const float4 m = *reinterpret_cast<const float4*>(sM + j * ra.pitch + 4 * (f - j * P4));
       const float lj = sV[S_SP * P + j];
-      st_cg4(M + 4 * (size_t)f, make_float4(m[0] / lj, m[1] / lj, m[2] / lj, m[3] / lj));
+      st_cg4(M + 4 * (size_t)f, make_float4(m.x / lj, m.y / lj, m.z / lj, m.w / lj));
    }
    __syncwarp();
 }
 
 // transRNorm (transr/trainer.cpp:35-64) of the lane-owned entity row x (a copy lives in slot S_H) against the
 // published, read-only M_r; the perturbation the reference applies to M_r goes to the NEXT batch's delta.
+//
+// One pass of the reference's loop is, for i = 0 .. D-1 in order (m_i = column i of M_r):
+//    tmp = 2 (m_i . x);   dM[.][i] += delta, delta = -lr tmp x;   x <- x - lr tmp (m_i + delta)
+// i.e. x <- x - c (m_i - c x) with c = lr tmp.  The D dependent warp-wide dot products are the critical path, so
+// the pass runs in chunks of four columns: the four dots q_a = m_(i0+a) . x are reduced TOGETHER (one 16-byte
+// shared load per lane-owned row, four interleaved butterflies), and the effect of step a on the later dots of
+// the chunk follows from dotting the update with m_b:  q_b <- q_b - c_a (g_ba - c_a q_b),  g_ba = m_b . m_a  (six
+// numbers per chunk, computed once per call when the constraint is violated at all).  Same recurrence, a
+// quarter of the dependent reductions.
 template <int NE>
 __device__ __forceinline__ void transr_constraint(const RArgs& ra, int r, float* sM, float* sV, int lane, uint8_t next_stamp,
                                                   float (&x)[NE]) {
    const TrainArgs& a = ra.base;
-   const int P = a.P, D = a.D;
+   const int P = a.P, D = a.D, P4 = P >> 2, pitch = ra.pitch;
    const float* M = a.w + (size_t)r * a.w_row;
    float* dM = a.dw + (size_t)r * a.w_row;
+   float* sG = sV + S_GP * P;   // 6 * P4 floats (slots S_GP, S_GN): g10 g20 g21 g30 g31 g32 per chunk
    stage_matrix<false>(ra, M, nullptr, sM, lane);
+   cp_async_wait_all();
    __syncwarp();
-   bool touched = false;
+   bool have_gram = false;
    for (int iter = 0; iter < 64; iter++) {
       float y[1][NE];
       const float* const vec[1] = {sV + S_H * P};
-      project_smem<NE, 1>(sM, D, ra.pitch, lane, vec, y);
+      project_smem<NE, 1>(sM, D, pitch, lane, vec, y);
       float n2 = 0.f;
 #pragma unroll
       for (int k = 0; k < NE; k++) n2 += (lane + 32 * k < D) ? y[0][k] * y[0][k] : 0.f;
       if (warp_sum(n2) <= 1.f) break;
-      touched = true;
-      for (int i = 0; i < D; i++) {
-         float m[NE], part = 0.f;
-#pragma unroll
-         for (int k = 0; k < NE; k++) {
-            const int j = lane + 32 * k;
-            m[k] = j < D ? sM[j * ra.pitch + i] : 0.f;
-            part += m[k] * x[k];
+      if (!have_gram) {
+         for (int t = lane; t < 6 * P4; t += 32) {
+            const int chunk = t / 6, pr = t - 6 * chunk;
+            const int ca = pr == 0 ? 0 : (pr < 3 ? pr - 1 : pr - 3);   // pairs (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
+            const int cb = pr == 0 ? 1 : (pr < 3 ? 2 : 3);
+            const float* col = sM + 4 * chunk;
+            float g = 0.f;
+            for (int j = 0; j < D; j++) g = fmaf(col[j * pitch + ca], col[j * pitch + cb], g);
+            sG[t] = g;
          }
-         const float tmp = 2.f * warp_sum(part);
+         have_gram = true;
+         __syncwarp();
+      }
+      for (int c4 = 0; c4 < P4; c4++) {
+         float4 mk[NE];
+         float4 q = f4(0.f);
 #pragma unroll
          for (int k = 0; k < NE; k++) {
             const int j = lane + 32 * k;
-            const float delta = -(a.lr * tmp * x[k]);
-            if (j < D) red_add_f32(dM + (size_t)j * P + i, delta);
-            x[k] = x[k] - a.lr * tmp * (m[k] + delta);
+            mk[k] = j < D ? *reinterpret_cast<const float4*>(sM + j * pitch + 4 * c4) : f4(0.f);
+            q.x = fmaf(mk[k].x, x[k], q.x); q.y = fmaf(mk[k].y, x[k], q.y);
+            q.z = fmaf(mk[k].z, x[k], q.z); q.w = fmaf(mk[k].w, x[k], q.w);
+         }
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) {
+            q.x += __shfl_xor_sync(0xffffffffu, q.x, o); q.y += __shfl_xor_sync(0xffffffffu, q.y, o);
+            q.z += __shfl_xor_sync(0xffffffffu, q.z, o); q.w += __shfl_xor_sync(0xffffffffu, q.w, o);
+         }
+         const float* g = sG + 6 * c4;
+         const float c0 = a.lr * (2.f * q.x);
+         float q1 = q.y - c0 * (g[0] - c0 * q.y);
+         float q2 = q.z - c0 * (g[1] - c0 * q.z);
+         float q3 = q.w - c0 * (g[3] - c0 * q.w);
+         const float c1 = a.lr * (2.f * q1);
+         q2 = q2 - c1 * (g[2] - c1 * q2);
+         q3 = q3 - c1 * (g[4] - c1 * q3);
+         const float c2 = a.lr * (2.f * q2);
+         q3 = q3 - c2 * (g[5] - c2 * q3);
+         const float c3 = a.lr * (2.f * q3);
+#pragma unroll
+         for (int k = 0; k < NE; k++) {
+            const int j = lane + 32 * k;
+            if (j < D) {
+               float xv = x[k];
+               float4 dl;
+               dl.x = -(c0 * xv); xv = xv - c0 * (mk[k].x + dl.x);
+               dl.y = -(c1 * xv); xv = xv - c1 * (mk[k].y + dl.y);
+               dl.z = -(c2 * xv); xv = xv - c2 * (mk[k].z + dl.z);
+               dl.w = -(c3 * xv); xv = xv - c3 * (mk[k].w + dl.w);
+               x[k] = xv;
+               red_add4(dM + (size_t)j * P + 4 * c4, dl);   // padding columns: m = 0 -> q = c = delta = 0
+            }
          }
       }
       __syncwarp();
       put_slot<NE>(sV + S_H * P, D, P, lane, x);
       __syncwarp();
    }
-   if (touched && lane == 0) a.flag[(size_t)a.nE + r] = next_stamp;
+   if (have_gram && lane == 0) a.flag[(size_t)a.nE + r] = next_stamp;
    __syncwarp();
 }
 
@@ -347,18 +433,20 @@ __device__ __forceinline__ void transr_constraint(const RArgs& ra, int r, float*
 // highest relation that touched it, and -- the reference's quirk at :187 -- against M_e when relation e was touched.
 template <int NE>
 __device__ __forceinline__ void transr_finish_entity(const RArgs& ra, int e, float* sM, float* sV, int lane, uint8_t stamp,
-                                                     uint8_t next_stamp, bool own, float4 x4, float4 d4) {
+                                                     uint8_t next_stamp, bool own) {
    const TrainArgs& a = ra.base;
    const int P = a.P, D = a.D;
    const bool on = lane < (P >> 2);
+   float4 x4 = on ? ld_cg4(a.tab + (size_t)e * P + lane * 4) : f4(0.f);
    int r0 = 0x7fffffff, r1 = -1;
    if (own) {
+      const float4 d4 = on ? ld_cg4(a.dtab + (size_t)e * P + lane * 4) : f4(0.f);
+      r0 = __ldcg(a.rmin + e);
+      r1 = __ldcg(a.rmax + e);
       x4 = x4 + d4;
       const float len = sqrtf(warp_sum(dot4(x4, x4)));
       x4 = make_float4(x4.x / len, x4.y / len, x4.z / len, x4.w / len);
       if (on) st_cg4(a.dtab + (size_t)e * P + lane * 4, f4(0.f));
-      r0 = __ldcg(a.rmin + e);
-      r1 = __ldcg(a.rmax + e);
       if (lane == 0) { a.rmin[e] = 0x7fffffff; a.rmax[e] = -1; }
    }
    if (on) reinterpret_cast<float4*>(sV + S_H * P)[lane] = x4;
@@ -376,49 +464,56 @@ __device__ __forceinline__ void transr_finish_entity(const RArgs& ra, int e, flo
    __syncwarp();
 }
 
-template <int NE>
-__device__ __forceinline__ void transr_publish(const RArgs& ra, long long row_begin, long long row_end, long long g0, long long G,
-                                               uint8_t stamp, uint8_t next_stamp, float* sM, float* sV, int lane, uint32_t& tent,
-                                               uint32_t& trel) {
-   const TrainArgs& a = ra.base;
-   const int P = a.P;
-   const bool on = lane < (P >> 2);
-   const bool quirk = !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK);
-   long long first, end;
-   group_range(row_begin, row_end, g0, G, first, end);
-   auto stamped = [&](long long r) {
-      bool f = __ldcg(a.flag + r) == stamp;
-      // transr/trainer.cpp:187: entity row e is also visited when RELATION e was touched
-      if (quirk && r < a.nE && r < a.nR) f = f || __ldcg(a.flag + a.nE + r) == stamp;
-      return f;
-   };
-   auto finish = [&](long long r, float4 x, float4 d) {
-      if (r >= a.nE) {
-         transr_finish_relation<NE>(ra, (int)(r - a.nE), sM, sV, lane, x, d);
-         trel += (lane == 0);
-      } else {
-         const bool own = __ldcg(a.flag + r) == stamp;
-         transr_finish_entity<NE>(ra, (int)r, sM, sV, lane, stamp, next_stamp, own, x, d);
-         tent += (lane == 0 && own);
+// ---- touched-row lists ---------------------------------------------------------------------------------
+// Phase 2 work is a small, irregular subset of the rows, and one row costs microseconds (it stages 10 KB
+// matrices), so static row ranges leave most warps idle behind the unlucky ones.  Instead the CTA compacts
+// the stamps of a window of rows into an ordered list in shared memory (ballot + warp-count prefix) and its
+// warps take list entries one at a time.
+constexpr int kListCap = 1024;
+
+struct RowList {
+   int n;
+   int next;
+   int wcnt[kRMaxThreads / 32];
+   int item[kListCap];
+};
+
+// rows [begin, end) (end - begin <= kListCap) for which pred holds -> list.item[0 .. list.n), ascending
+template <typename Pred>
+__device__ __forceinline__ void compact_rows(RowList& list, long long begin, long long end, Pred&& pred) {
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+   if (threadIdx.x == 0) { list.n = 0; list.next = 0; }
+   __syncthreads();
+   for (long long base = begin; base < end; base += blockDim.x) {
+      const long long r = base + threadIdx.x;
+      const bool f = r < end && pred(r);
+      const uint32_t m = __ballot_sync(0xffffffffu, f);
+      if (lane == 0) list.wcnt[warp] = __popc(m);
+      __syncthreads();
+      int off = list.n, total = 0;
+      for (int w = 0; w < warps; w++) {
+         const int c = list.wcnt[w];
+         if (w < warp) off += c;
+         total += c;
       }
-   };
-   for_stamped_rows<32>(first, end, lane, 0xffffffffu, lane, stamped, [&](long long r0, long long r1) {
-      const float4 x0 = on ? ld_cg4(a.tab + (size_t)r0 * P + lane * 4) : f4(0.f);
-      const float4 d0 = on ? ld_cg4(a.dtab + (size_t)r0 * P + lane * 4) : f4(0.f);
-      float4 x1 = f4(0.f), d1 = f4(0.f);
-      if (r1 >= 0 && on) {
-         x1 = ld_cg4(a.tab + (size_t)r1 * P + lane * 4);
-         d1 = ld_cg4(a.dtab + (size_t)r1 * P + lane * 4);
-      }
-      finish(r0, x0, d0);
-      if (r1 >= 0) finish(r1, x1, d1);
-   });
+      if (f) list.item[off + __popc(m & ((1u << lane) - 1u))] = (int)(r - begin);
+      __syncthreads();
+      if (threadIdx.x == 0) list.n += total;
+      __syncthreads();
+   }
+}
+
+__device__ __forceinline__ int take_item(RowList& list, int lane) {
+   int t = 0;
+   if (lane == 0) t = atomicAdd(&list.next, 1);
+   return __shfl_sync(0xffffffffu, t, 0);
 }
 
 template <int NE>
 __global__ void __launch_bounds__(kRMaxThreads, 1) train_transr_kernel(const __grid_constant__ RArgs ra) {
    extern __shared__ float4 smem4[];
    __shared__ double s_loss[kRMaxThreads / 32];
+   __shared__ RowList s_list;
    const TrainArgs& a = ra.base;
    const int lane = threadIdx.x & 31;
    const int warp = threadIdx.x >> 5;
@@ -427,7 +522,11 @@ __global__ void __launch_bounds__(kRMaxThreads, 1) train_transr_kernel(const __g
    const int warps = blockDim.x >> 5;
    const long long G = (long long)gridDim.x * warps;
    const long long g0 = (long long)warp * gridDim.x + blockIdx.x;   // round-robin over CTAs
-   const long long R = (long long)a.nE + a.nR;
+   const bool quirk_on = !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK);
+   // this CTA's contiguous share of the entity rows (phase 2b)
+   const long long ent_per = (a.nE + gridDim.x - 1) / gridDim.x;
+   const long long ent_first = min((long long)a.nE, ent_per * blockIdx.x);
+   const long long ent_end = min((long long)a.nE, ent_first + ent_per);
    uint32_t bar_target = 0;
    uint32_t active_acc = 0, tent_acc = 0, trel_acc = 0;
    int trace_slot = 0;
@@ -457,10 +556,46 @@ __global__ void __launch_bounds__(kRMaxThreads, 1) train_transr_kernel(const __g
          KB2E_RTRACE();
          grid_barrier(a.barrier, bar_target);
          KB2E_RTRACE();
-         transr_publish<NE>(ra, a.nE, R, g0, G, stamp, next_stamp, sM, sV, lane, tent_acc, trel_acc);
+         // ---- phase 2a: every CTA builds the same list of touched relations; entry t is cut into S row segments
+         // and (entry, segment) pairs are dealt round-robin over all warps of the grid
+         for (long long w0 = 0; w0 < a.nR; w0 += kListCap) {
+            const long long w1 = min((long long)a.nR, w0 + kListCap);
+            compact_rows(s_list, w0, w1, [&](long long r) { return __ldcg(a.flag + a.nE + r) == stamp; });
+            const int n = s_list.n;
+            if (n > 0) {
+               int S = (int)min((long long)8, max((long long)1, G / n));
+               S = min(S, max(1, a.D / 4));
+               const int rows_per = (a.D + S - 1) / S;
+               for (long long it = g0; it < (long long)n * S; it += G) {
+                  const int e = (int)(it / S), seg = (int)(it - (long long)e * S);
+                  const int jb = seg * rows_per, je = min(a.D, jb + rows_per);
+                  if (jb < je) transr_finish_relation<NE>(ra, (int)w0 + s_list.item[e], jb, je, sM, sV, lane);
+                  trel_acc += (lane == 0 && seg == 0);
+               }
+            }
+            __syncthreads();
+         }
+         KB2E_RTRACE();
          grid_barrier(a.barrier, bar_target);
          KB2E_RTRACE();
-         transr_publish<NE>(ra, 0, a.nE, g0, G, stamp, next_stamp, sM, sV, lane, tent_acc, trel_acc);
+         // ---- phase 2b: this CTA's touched entity rows, taken one at a time by its warps
+         for (long long w0 = ent_first; w0 < ent_end; w0 += kListCap) {
+            const long long w1 = min(ent_end, w0 + kListCap);
+            compact_rows(s_list, w0, w1, [&](long long r) {
+               bool f = __ldcg(a.flag + r) == stamp;
+               // transr/trainer.cpp:187: entity row e is also visited when RELATION e was touched
+               if (quirk_on && r < a.nR) f = f || __ldcg(a.flag + a.nE + r) == stamp;
+               return f;
+            });
+            const int n = s_list.n;
+            for (int t = take_item(s_list, lane); t < n; t = take_item(s_list, lane)) {
+               const long long e = w0 + s_list.item[t];
+               const bool own = __ldcg(a.flag + e) == stamp;
+               transr_finish_entity<NE>(ra, (int)e, sM, sV, lane, stamp, next_stamp, own);
+               tent_acc += (lane == 0 && own);
+            }
+            __syncthreads();
+         }
          KB2E_RTRACE();
          grid_arrive(a.barrier, bar_target);
          if (has_first && !(ep == a.n_epochs - 1 && batch == a.batches - 1)) pre = draw_pair(a, (uint32_t)g0, gb + 1u);
@@ -497,17 +632,17 @@ int train_transr_launch(kb2e_ctx* c, const TrainArgs& base, int* threads_out) {
    if (c->P > 128) return fail(c, KB2E_ERR_LIMIT, "TransR training supports embedding sizes up to 128");
    RArgs a;
    a.base = base;
-   a.pitch = c->P + 1;
-   a.vec_off = (c->D * a.pitch + 3) / 4 * 4;
+   a.pitch = ((c->P / 4) & 1) ? c->P : c->P + 4;   // multiple of 4 floats with pitch/4 odd (bank-conflict-free 16-byte row reads)
+   a.vec_off = c->D * a.pitch;
    a.warp_floats = a.vec_off + kRSlots * c->P;
    const int P4 = c->P / 4;
    a.p4_magic = (uint32_t)(((1ull << 32) + P4 - 1) / P4);
    int dev_smem = 0;
    KB2E_CUDA(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
    const size_t per_warp = (size_t)a.warp_floats * sizeof(float);
-   int warps = (int)std::min<size_t>(kRMaxThreads / 32, ((size_t)dev_smem - 1024) / per_warp);
+   int warps = (int)std::min<size_t>(kRMaxThreads / 32, ((size_t)dev_smem - sizeof(RowList) - 512) / per_warp);
    if (const char* env = getenv("KB2E_TRANSR_WARPS")) warps = std::max(1, std::min(warps, atoi(env)));
-   if (warps < 1) return fail(c, KB2E_ERR_LIMIT, "TransR projection matrix does not fit in shared memory");
+   if (warps < 2) return fail(c, KB2E_ERR_LIMIT, "TransR projection matrix does not fit in shared memory");
    const int ne = (c->D + 31) / 32;
    void (*k)(const RArgs) = ne == 1 ? train_transr_kernel<1> : (ne == 2 ? train_transr_kernel<2> : (ne == 3 ? train_transr_kernel<3> : train_transr_kernel<4>));
    const size_t smem = per_warp * warps;

@@ -1,7 +1,7 @@
 """Entity-partitioned TransE training across the GPUs of one NVLink box: host-side plumbing.
 
 One process per GPU (torchrun).  The data path has no collective: the persistent kernels exchange rows
-and updates with peer loads / REDs over NVLink (kb2e_b200/csrc/train_dist.cu).  torch.distributed is
+and updates with posted peer stores / REDs over NVLink (kb2e_b200/csrc/train_dist.cu).  torch.distributed is
 used only to exchange the 64-byte CUDA IPC handles once and to add the per-rank losses."""
 import numpy as np
 
@@ -15,22 +15,28 @@ def owned_ids(num_entities, rank, world):
 
 class PartitionedTrainer:
     def __init__(self, dim, num_entities, num_relations, rank, world, device, **cfg):
-        import torch.distributed as dist
         self.rank, self.world = rank, world
         self.ctx = Context("transe", dim, num_entities, num_relations, device=device, **cfg)
-        handle = self.ctx.dist_setup(rank, world)
-        if world > 1:
-            handles = [None] * world
+        self._connected = False
+
+    def set_training_set(self, train, head_mean, tail_mean):
+        """Collective on first use: the batch size (len(train) // batches) sizes the exchange buffers of the
+        arena, so the arenas are allocated and mapped into every peer once the training set is known."""
+        self.ctx.set_train_triples(train)
+        self.ctx.set_bern(head_mean, tail_mean)
+        if self._connected:
+            return
+        import torch.distributed as dist
+        handle = self.ctx.dist_setup(self.rank, self.world)
+        if self.world > 1:
+            handles = [None] * self.world
             dist.all_gather_object(handles, handle)
         else:
             handles = [handle]
         self.ctx.dist_connect(handles)
-        if world > 1:
+        self._connected = True
+        if self.world > 1:
             dist.barrier()  # every arena is mapped everywhere before anyone launches
-
-    def set_training_set(self, train, head_mean, tail_mean):
-        self.ctx.set_train_triples(train)
-        self.ctx.set_bern(head_mean, tail_mean)
 
     def init_embeddings(self):
         self.ctx.dist_init_embeddings()
