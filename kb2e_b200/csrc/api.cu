@@ -197,7 +197,7 @@ static int stage_triples(kb2e_ctx* c, const int32_t* h, const int32_t* t, const 
       if (h[i] < 0 || h[i] >= c->nE || t[i] < 0 || t[i] >= c->nE || r[i] < 0 || r[i] >= c->nR)
          return fail(c, KB2E_ERR_ARG, "triple " + std::to_string(i) + " has an id out of range");
    }
-   KB2E_CUDA(c, cudaMalloc(dev, 3 * (size_t)n * sizeof(int32_t)));
+   KB2E_CUDA(c, pool_alloc(c, dev, 3 * (size_t)n * sizeof(int32_t)));
    KB2E_CUDA(c, cudaMemcpyAsync(*dev, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(*dev + n, t, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(*dev + 2 * n, r, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -210,17 +210,17 @@ int kb2e_score(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t* r
    if (n == 0) return KB2E_OK;
    int32_t* dev = nullptr;
    int rc = stage_triples(c, h, t, r, n, &dev);
-   if (rc) { cudaFree(dev); return rc; }
+   if (rc) { pool_free(c, dev); return rc; }
    double* dout = nullptr;
-   KB2E_CUDA(c, cudaMalloc(&dout, (size_t)n * sizeof(double)));
+   KB2E_CUDA(c, pool_alloc(c, &dout, (size_t)n * sizeof(double)));
    rc = precision == 0 ? train_score32(c, dev, dev + n, dev + 2 * n, n, dout) : rank_score64(c, dev, dev + n, dev + 2 * n, n, dout);
    if (rc == KB2E_OK) {
       cudaError_t e = cudaMemcpyAsync(out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
       if (e != cudaSuccess) rc = cuda_fail(c, e, "kb2e_score copy");
    }
-   cudaFree(dev);
-   cudaFree(dout);
+   pool_free(c, dev);
+   pool_free(c, dout);
    return rc;
 }
 
@@ -268,14 +268,14 @@ int kb2e_sample_batch(kb2e_ctx* c, int32_t epoch, int32_t batch, int64_t count, 
    KB2E_ENTER(c);
    if (count <= 0 || !pairs_out) return fail(c, KB2E_ERR_ARG, "kb2e_sample_batch: bad arguments");
    int32_t* dev = nullptr;
-   KB2E_CUDA(c, cudaMalloc(&dev, 6 * (size_t)count * sizeof(int32_t)));
+   KB2E_CUDA(c, pool_alloc(c, &dev, 6 * (size_t)count * sizeof(int32_t)));
    int rc = train_sample(c, epoch, batch, count, dev);
    if (rc == KB2E_OK) {
       cudaError_t e = cudaMemcpyAsync(pairs_out, dev, 6 * (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
       if (e != cudaSuccess) rc = cuda_fail(c, e, "kb2e_sample_batch copy");
    }
-   cudaFree(dev);
+   pool_free(c, dev);
    return rc;
 }
 
@@ -291,9 +291,9 @@ int kb2e_train_batch_pairs(kb2e_ctx* c, const int32_t* pairs, int64_t n, double*
    int rc = train_alloc(c);
    if (rc) return rc;
    if (n > c->pairs_cap) {
-      cudaFree(c->pairs_dev);
+      pool_free(c, c->pairs_dev);
       c->pairs_dev = nullptr;
-      KB2E_CUDA(c, cudaMalloc(&c->pairs_dev, 6 * (size_t)n * sizeof(int32_t)));
+      KB2E_CUDA(c, pool_alloc(c, &c->pairs_dev, 6 * (size_t)n * sizeof(int32_t)));
       c->pairs_cap = n;
    }
    KB2E_CUDA(c, cudaMemcpyAsync(c->pairs_dev, pairs, 6 * (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));

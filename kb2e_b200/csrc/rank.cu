@@ -46,8 +46,12 @@ struct RankState {
    uint32_t* seg_val = nullptr;   // offset of the segment in ent_key / nbr
    uint64_t* ent_key = nullptr;   // sorted segment keys, one per entry
    int32_t* nbr = nullptr;        // neighbour entity ids, sorted within a segment (duplicates adjacent)
+   uint32_t* seg_end = nullptr;   // hash slot -> one past the segment's last entry
    uint64_t seg_mask = 0;
    uint32_t n_ent = 0;
+   int4* chunks = nullptr;        // (query, first entry, #entries <= 32, segment start) work items of the filter pass
+   unsigned int chunk_cap = 0;    // chunks needed by the whole test set (both sides): bound for any window
+   unsigned int* chunk_count = nullptr;
    // candidate matrices
    double* ct0 = nullptr;         // entity table transposed [D][ld]
    double* pt = nullptr;          // projected slots [slots][D][ld]
@@ -63,7 +67,9 @@ struct RankState {
    int64_t slot_cap = 0;
    unsigned long long* sums = nullptr;
    int32_t* out = nullptr;        // 4 x cap results in original order
-   cudaEvent_t m0 = nullptr, m1 = nullptr;
+   std::vector<cudaEvent_t> pass_ev;   // two per pass, around the all-candidates kernel
+   int32_t* ids = nullptr;        // h | t | r columns of the known triples (test first), kept for the device query builder
+   size_t ids_n = 0;
    kb2e::TcState tc;
 };
 
@@ -179,28 +185,50 @@ __global__ void etrue_kernel(const RankArgs a) {
 
 // Exact re-score of the (query, candidate) pairs the tensor-core pre-filter could not decide
 // (rank_tc.cu): same arithmetic and order as exact_energy, rows read from the row-major fp64 table.
+// The band size lives on the device (*band_count, capped by band_cap): the launch is a fixed grid striding over it,
+// so the host never waits for the tensor-core kernel before enqueueing the rest of the call.
 template <int L2>
-__global__ void recheck_kernel(const int2* __restrict__ band, unsigned int n, const double* __restrict__ ent64,
-                               const double* __restrict__ rel64, const int32_t* q_fixed, const int32_t* q_truth,
-                               const int32_t* q_rel, const int32_t* q_side, const double* q_etrue,
+__global__ void recheck_kernel(const int2* __restrict__ band, const unsigned int* __restrict__ band_count, unsigned int band_cap,
+                               const double* __restrict__ ent64, const double* __restrict__ rel64, const int32_t* q_fixed,
+                               const int32_t* q_truth, const int32_t* q_rel, const int32_t* q_side, const double* q_etrue,
                                int32_t* q_cnt, long long nq, int D) {
-   unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
-   if (k >= n) return;
-   const int q = band[k].x, c = band[k].y;
-   if (c == q_truth[q]) return;
-   const double* v = ent64 + (size_t)q_fixed[q] * D;
-   const double* e = ent64 + (size_t)c * D;
-   const double* d = rel64 + (size_t)q_rel[q] * D;
-   const double dsign = q_side[q] ? -1.0 : 1.0;
-   double acc = 0.0;
-   for (int i = 0; i < D; i++) {
-      double u = __dsub_rn(v[i], e[i]);
-      double w = __dsub_rn(u, dsign * d[i]);
-      acc = L2 ? __dadd_rn(acc, __dmul_rn(w, w)) : __dadd_rn(acc, fabs(w));
+   const unsigned int n = min(*band_count, band_cap);
+   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+      const int q = band[k].x, c = band[k].y;
+      if (c == q_truth[q]) continue;
+      const double* v = ent64 + (size_t)q_fixed[q] * D;
+      const double* e = ent64 + (size_t)c * D;
+      const double* d = rel64 + (size_t)q_rel[q] * D;
+      const double dsign = q_side[q] ? -1.0 : 1.0;
+      double acc = 0.0;
+      for (int i = 0; i < D; i++) {
+         double u = __dsub_rn(v[i], e[i]);
+         double w = __dsub_rn(u, dsign * d[i]);
+         acc = L2 ? __dadd_rn(acc, __dmul_rn(w, w)) : __dadd_rn(acc, fabs(w));
+      }
+      const double et = q_etrue[q];
+      if (acc < et) atomicAdd(q_cnt + q, 1);
+      else if (acc == et) atomicAdd(q_cnt + nq + q, 1);
    }
-   const double et = q_etrue[q];
-   if (acc < et) atomicAdd(q_cnt + q, 1);
-   else if (acc == et) atomicAdd(q_cnt + nq + q, 1);
+}
+
+// TransE: the query arrays in original test order, built on the device from the resident test triples
+// (fixed entity, true answer, relation, side, slot = 0, original index); query 2 i is the head corruption of
+// test triple first + i, query 2 i + 1 its tail corruption (common/evaluation.cpp:230-238).
+__global__ void build_queries_kernel(const int32_t* __restrict__ th, const int32_t* __restrict__ tt, const int32_t* __restrict__ tr,
+                                     long long first, long long count, int32_t* q_int) {
+   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   const long long nq = 2 * count;
+   if (q >= nq) return;
+   const long long i = first + (q >> 1);
+   const int side = (int)(q & 1);
+   const int h = th[i], t = tt[i];
+   q_int[q] = side == 0 ? t : h;
+   q_int[nq + q] = side == 0 ? h : t;
+   q_int[2 * nq + q] = tr[i];
+   q_int[3 * nq + q] = side;
+   q_int[4 * nq + q] = 0;
+   q_int[5 * nq + q] = (int32_t)q;
 }
 
 // ---- the all-candidates kernel ---------------------------------------------------------------------
@@ -321,72 +349,127 @@ __global__ void segment_hash_kernel(const uint64_t* ent_key, uint32_t n, uint64_
    }
 }
 
-// ---- filter adjustment: a group of 8 lanes per query walks the known-true neighbours ---------------
-// (planted / FB15k-like graphs have a handful of known answers per query, so a whole warp per query
-// leaves most lanes idle).  ROWS = true (TransE): the candidate matrix IS the entity table, so the
-// energies are taken from the row-major fp64 table (contiguous 8*D-byte rows, every fetched sector is
-// used) instead of the transposed copy (one 8-byte word per sector); the arithmetic and its order are
-// those of exact_energy either way.
-constexpr int kFilterLanes = 8;
+// last entry of every segment -> seg_end[slot of its key] = index one past it (runs after segment_hash_kernel)
+__global__ void segment_end_kernel(const uint64_t* ent_key, uint32_t n, const uint64_t* slots, uint32_t* ends, uint64_t mask) {
+   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   const uint64_t k = ent_key[i];
+   if (i + 1 < n && ent_key[i + 1] == k) return;  // not the last entry of its segment
+   uint64_t p = mix64(k) & mask;
+   while (slots[p] != k) p = (p + 1) & mask;
+   ends[p] = i + 1;
+}
 
-template <int L2, bool ROWS>
-__global__ void filter_kernel(const RankArgs a, const double* __restrict__ ent64) {
-   const long long q = a.q_begin + (((long long)blockIdx.x * blockDim.x + threadIdx.x) / kFilterLanes);
-   const int lane = threadIdx.x & 31;
-   const int sub = lane & (kFilterLanes - 1);
-   const uint32_t gmask = ((1u << kFilterLanes) - 1u) << (lane & ~(kFilterLanes - 1));
-   if (q >= a.q_end) return;
-   const int side = a.q_side[q], rel = a.q_rel[q], fixed = a.q_fixed[q], truth = a.q_truth[q];
-   const uint64_t key = seg_key_of(side, rel, fixed);
-   uint64_t slot = mix64(key) & a.seg_mask;
-   uint32_t off = 0;
-   bool found = false;
+// ---- filter adjustment ---------------------------------------------------------------------------------
+// The known-true neighbours of a query are one segment of the sorted entry list.  Segment lengths are
+// heavy-tailed (FB15k-shape planted KG: median 2, 99th percentile 222, maximum 775 entries), and one exact
+// energy is a chain of D dependent fp64 additions, so "one group of lanes per query" is bound by the longest
+// segment.  Instead the segments are cut into chunks of up to 32 entries (filter_plan_kernel: hash lookup,
+// warp scan, one atomic per warp to reserve chunk slots) and a persistent grid takes the chunks one per warp,
+// one (query, neighbour) pair per lane (filter_pairs_kernel).  No host step: the chunk count stays on the device.
+struct SegRef { uint32_t off, len; };
+
+__device__ __forceinline__ SegRef find_segment(const uint64_t* __restrict__ seg_key, const uint32_t* __restrict__ seg_val,
+                                               const uint32_t* __restrict__ seg_end, uint64_t mask, uint64_t key) {
+   uint64_t slot = mix64(key) & mask;
    while (true) {
-      uint64_t k = __ldg(a.seg_key + slot);
-      if (k == key) { off = __ldg(a.seg_val + slot); found = true; break; }
-      if (k == kEmptyKey) break;
-      slot = (slot + 1) & a.seg_mask;
+      const uint64_t k = __ldg(seg_key + slot);
+      if (k == key) { const uint32_t o = __ldg(seg_val + slot); return SegRef{o, __ldg(seg_end + slot) - o}; }
+      if (k == kEmptyKey) return SegRef{0u, 0u};
+      slot = (slot + 1) & mask;
    }
-   const double* ct = a.ct + (size_t)a.q_slot[q] * a.D * a.ld;
-   const double* d = a.rel64 + (size_t)rel * a.D;
-   const double dsign = side ? -1.0 : 1.0;
-   const double et = a.q_etrue[q];
-   int less = 0, eq = 0;
-   if (found) {
-      for (uint32_t base = off; base < a.n_ent; base += kFilterLanes) {
-         const uint32_t k = base + sub;
-         const bool mine = k < a.n_ent && __ldg(a.ent_key + k) == key;
-         if (mine) {
-            const int c = __ldg(a.nbr + k);
-            const bool dup = k > off && __ldg(a.nbr + k - 1) == c;  // the same triple listed twice (e.g. in train and valid)
-            if (c != truth && !dup) {
-               double e;
-               if (ROWS) {
-                  const double* v = ent64 + (size_t)fixed * a.D;
-                  const double* x = ent64 + (size_t)c * a.D;
-                  e = 0.0;
-                  for (int i = 0; i < a.D; i++) {
-                     const double w = __dsub_rn(__dsub_rn(__ldg(v + i), __ldg(x + i)), dsign * __ldg(d + i));
-                     e = L2 ? __dadd_rn(e, __dmul_rn(w, w)) : __dadd_rn(e, fabs(w));
-                  }
-               } else {
-                  e = exact_energy<L2>(ct, a.ld, a.D, fixed, c, d, dsign);
-               }
-               less += e < et;
-               eq += e == et;
-            }
-         }
-         if (__ballot_sync(gmask, mine) != gmask) break;  // the segment ended inside this chunk
-      }
+}
+
+constexpr int kChunk = 32;
+
+// upper bound of the chunks any kb2e_rank window can need: all test triples, both sides (runs once per filter build)
+__global__ void count_chunks_kernel(const int32_t* __restrict__ th, const int32_t* __restrict__ tt, const int32_t* __restrict__ tr,
+                                    long long n_test, const uint64_t* seg_key, const uint32_t* seg_val, const uint32_t* seg_end,
+                                    uint64_t mask, unsigned long long* total) {
+   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   unsigned int n = 0;
+   if (q < 2 * n_test) {
+      const long long i = q >> 1;
+      const int side = (int)(q & 1);
+      const SegRef sr = find_segment(seg_key, seg_val, seg_end, mask, seg_key_of(side, tr[i], side == 0 ? tt[i] : th[i]));
+      n = (sr.len + kChunk - 1) / kChunk;
    }
 #pragma unroll
-   for (int o = kFilterLanes / 2; o > 0; o >>= 1) {
-      less += __shfl_xor_sync(gmask, less, o);
-      eq += __shfl_xor_sync(gmask, eq, o);
+   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+   if ((threadIdx.x & 31) == 0 && n) atomicAdd(total, (unsigned long long)n);
+}
+
+__global__ void filter_plan_kernel(const RankArgs a, const uint32_t* __restrict__ seg_end, int4* chunks, unsigned int* chunk_count,
+                                   unsigned int chunk_cap) {
+   const long long q = a.q_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   const int lane = threadIdx.x & 31;
+   SegRef sr{0u, 0u};
+   if (q < a.q_end) sr = find_segment(a.seg_key, a.seg_val, seg_end, a.seg_mask, seg_key_of(a.q_side[q], a.q_rel[q], a.q_fixed[q]));
+   const unsigned int n = (sr.len + kChunk - 1) / kChunk;
+   unsigned int x = n;   // inclusive warp scan
+#pragma unroll
+   for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
    }
-   if (sub == 0) {
-      a.q_cnt[2 * a.nq + q] = less;
-      a.q_cnt[3 * a.nq + q] = eq;
+   const unsigned int total = __shfl_sync(0xffffffffu, x, 31);
+   unsigned int base = 0;
+   if (lane == 0 && total) base = atomicAdd(chunk_count, total);
+   base = __shfl_sync(0xffffffffu, base, 0) + (x - n);
+   for (unsigned int k = 0; k < n; k++) {
+      if (base + k < chunk_cap)
+         chunks[base + k] = make_int4((int)q, (int)(sr.off + k * kChunk), (int)min((unsigned int)kChunk, sr.len - k * kChunk), (int)sr.off);
+   }
+}
+
+// ROWS = true (TransE): the candidate matrix IS the entity table, so the energies are taken from the row-major
+// fp64 table (contiguous 8*D-byte rows) instead of the transposed copy; arithmetic and order are exact_energy's.
+template <int L2, bool ROWS>
+__global__ void filter_pairs_kernel(const RankArgs a, const double* __restrict__ ent64, const int4* __restrict__ chunks,
+                                    const unsigned int* __restrict__ chunk_count, unsigned int chunk_cap) {
+   const unsigned int n = min(*chunk_count, chunk_cap);
+   const int lane = threadIdx.x & 31;
+   const unsigned int warps = (gridDim.x * blockDim.x) >> 5;
+   for (unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps) {
+      const int4 ch = __ldg(chunks + w);
+      const long long q = ch.x;
+      const int side = a.q_side[q], rel = a.q_rel[q], fixed = a.q_fixed[q], truth = a.q_truth[q];
+      const double et = a.q_etrue[q];
+      const double dsign = side ? -1.0 : 1.0;
+      const double* d = a.rel64 + (size_t)rel * a.D;
+      int less = 0, eq = 0;
+      if (lane < ch.z) {
+         const uint32_t k = (uint32_t)ch.y + lane;
+         const int c = __ldg(a.nbr + k);
+         const bool dup = k > (uint32_t)ch.w && __ldg(a.nbr + k - 1) == c;  // the same triple listed twice (e.g. in train and valid)
+         if (c != truth && !dup) {
+            double e;
+            if (ROWS) {
+               const double* v = ent64 + (size_t)fixed * a.D;
+               const double* x = ent64 + (size_t)c * a.D;
+               e = 0.0;
+#pragma unroll 8
+               for (int i = 0; i < a.D; i++) {
+                  const double t = __dsub_rn(__dsub_rn(__ldg(v + i), __ldg(x + i)), dsign * __ldg(d + i));
+                  e = L2 ? __dadd_rn(e, __dmul_rn(t, t)) : __dadd_rn(e, fabs(t));
+               }
+            } else {
+               const double* ct = a.ct + (size_t)a.q_slot[q] * a.D * a.ld;
+               e = exact_energy<L2>(ct, a.ld, a.D, fixed, c, d, dsign);
+            }
+            less = e < et;
+            eq = e == et;
+         }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+         less += __shfl_xor_sync(0xffffffffu, less, o);
+         eq += __shfl_xor_sync(0xffffffffu, eq, o);
+      }
+      if (lane == 0) {
+         if (less) atomicAdd(a.q_cnt + 2 * a.nq + q, less);
+         if (eq) atomicAdd(a.q_cnt + 3 * a.nq + q, eq);
+      }
    }
 }
 
@@ -430,20 +513,18 @@ static int ensure_state(kb2e_ctx* c) {
    if (!c->rank) c->rank = new RankState();
    RankState* s = c->rank;
    s->ld = ((c->nE + 31) / 32) * 32;
-   if (!s->ct0) KB2E_CUDA(c, cudaMalloc(&s->ct0, (size_t)c->D * s->ld * sizeof(double)));
-   if (!s->sums) KB2E_CUDA(c, cudaMalloc(&s->sums, 4 * sizeof(unsigned long long)));
-   if (!s->m0) {
-      KB2E_CUDA(c, cudaEventCreate(&s->m0));
-      KB2E_CUDA(c, cudaEventCreate(&s->m1));
-   }
+   if (!s->ct0) KB2E_CUDA(c, pool_alloc(c, &s->ct0, (size_t)c->D * s->ld * sizeof(double)));
+   if (!s->sums) KB2E_CUDA(c, pool_alloc(c, &s->sums, 4 * sizeof(unsigned long long)));
    return KB2E_OK;
 }
 
 static int build_filter(kb2e_ctx* c) {
    RankState* s = c->rank;
    if (!c->filter_dirty && s->seg_key) return KB2E_OK;
-   cudaFree(s->seg_key); cudaFree(s->seg_val); cudaFree(s->nbr); cudaFree(s->ent_key);
-   s->seg_key = nullptr; s->seg_val = nullptr; s->nbr = nullptr; s->ent_key = nullptr;
+   pool_free(c, s->seg_key); pool_free(c, s->seg_val); pool_free(c, s->seg_end); pool_free(c, s->nbr); pool_free(c, s->ent_key);
+   pool_free(c, s->ids); pool_free(c, s->chunks);
+   s->seg_key = nullptr; s->seg_val = nullptr; s->seg_end = nullptr; s->nbr = nullptr; s->ent_key = nullptr; s->ids = nullptr;
+   s->ids_n = 0; s->chunks = nullptr; s->chunk_cap = 0;
    // known triples = test + filter (common/evaluation.cpp:59-61)
    const size_t nt = c->test_h.size(), nf = c->filt_h.size(), n = nt + nf;
    if (2 * n >= (1ull << 32)) return fail(c, KB2E_ERR_LIMIT, "filter set larger than 2^31 triples");
@@ -451,19 +532,21 @@ static int build_filter(kb2e_ctx* c) {
    uint64_t slots = 1024;
    while (slots < 4 * n) slots <<= 1;  // <= 2n segments, load <= 0.5
    s->seg_mask = slots - 1;
-   KB2E_CUDA(c, cudaMalloc(&s->seg_key, slots * sizeof(uint64_t)));
-   KB2E_CUDA(c, cudaMalloc(&s->seg_val, slots * sizeof(uint32_t)));
-   KB2E_CUDA(c, cudaMalloc(&s->ent_key, std::max<size_t>(1, 2 * n) * sizeof(uint64_t)));
-   KB2E_CUDA(c, cudaMalloc(&s->nbr, std::max<size_t>(1, 2 * n) * sizeof(int32_t)));
+   KB2E_CUDA(c, pool_alloc(c, &s->seg_key, slots * sizeof(uint64_t)));
+   KB2E_CUDA(c, pool_alloc(c, &s->seg_val, slots * sizeof(uint32_t)));
+   KB2E_CUDA(c, pool_alloc(c, &s->seg_end, slots * sizeof(uint32_t)));
+   if (!s->chunk_count) KB2E_CUDA(c, pool_alloc(c, &s->chunk_count, 2 * sizeof(unsigned long long)));
+   KB2E_CUDA(c, pool_alloc(c, &s->ent_key, std::max<size_t>(1, 2 * n) * sizeof(uint64_t)));
+   KB2E_CUDA(c, pool_alloc(c, &s->nbr, std::max<size_t>(1, 2 * n) * sizeof(int32_t)));
    KB2E_CUDA(c, cudaMemsetAsync(s->seg_key, 0xff, slots * sizeof(uint64_t), c->stream));
    if (n == 0) { c->filter_dirty = false; return KB2E_OK; }
    int32_t* ids = nullptr;      // h | t | r columns of test then filter triples
    uint64_t* key_tmp = nullptr;
    int32_t* val_tmp = nullptr;
    void* cub_tmp = nullptr;
-   KB2E_CUDA(c, cudaMalloc(&ids, 3 * n * sizeof(int32_t)));
-   KB2E_CUDA(c, cudaMalloc(&key_tmp, 2 * n * sizeof(uint64_t)));
-   KB2E_CUDA(c, cudaMalloc(&val_tmp, 2 * n * sizeof(int32_t)));
+   KB2E_CUDA(c, pool_alloc(c, &ids, 3 * n * sizeof(int32_t)));
+   KB2E_CUDA(c, pool_alloc(c, &key_tmp, 2 * n * sizeof(uint64_t)));
+   KB2E_CUDA(c, pool_alloc(c, &val_tmp, 2 * n * sizeof(int32_t)));
    const std::vector<int32_t>* cols[3][2] = {{&c->test_h, &c->filt_h}, {&c->test_t, &c->filt_t}, {&c->test_r, &c->filt_r}};
    for (int k = 0; k < 3; k++) {
       if (nt) KB2E_CUDA(c, cudaMemcpyAsync(ids + k * n, cols[k][0]->data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -474,15 +557,28 @@ static int build_filter(kb2e_ctx* c) {
    size_t bytes1 = 0, bytes2 = 0;
    cub::DeviceRadixSort::SortPairs(nullptr, bytes1, val_tmp, s->nbr, key_tmp, s->ent_key, (int)(2 * n), 0, kEntityBits, c->stream);
    cub::DeviceRadixSort::SortPairs(nullptr, bytes2, s->ent_key, key_tmp, s->nbr, val_tmp, (int)(2 * n), 0, 41, c->stream);
-   KB2E_CUDA(c, cudaMalloc(&cub_tmp, std::max(bytes1, bytes2)));
+   KB2E_CUDA(c, pool_alloc(c, &cub_tmp, std::max(bytes1, bytes2)));
    KB2E_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, bytes1, val_tmp, s->nbr, key_tmp, s->ent_key, (int)(2 * n), 0, kEntityBits, c->stream));
    KB2E_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, bytes2, s->ent_key, key_tmp, s->nbr, val_tmp, (int)(2 * n), 0, 41, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(s->ent_key, key_tmp, 2 * n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(s->nbr, val_tmp, 2 * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
    segment_hash_kernel<<<nblk((long long)(2 * n), 256), 256, 0, c->stream>>>(s->ent_key, s->n_ent, s->seg_key, s->seg_val, s->seg_mask);
+   segment_end_kernel<<<nblk((long long)(2 * n), 256), 256, 0, c->stream>>>(s->ent_key, s->n_ent, s->seg_key, s->seg_end, s->seg_mask);
+   // work items the filter pass of the whole test set needs (kb2e_rank windows need at most as many)
+   unsigned long long* total_dev = reinterpret_cast<unsigned long long*>(s->chunk_count) + 1;
+   unsigned long long total = 0;
+   KB2E_CUDA(c, cudaMemsetAsync(total_dev, 0, sizeof(unsigned long long), c->stream));
+   if (nt) count_chunks_kernel<<<nblk(2 * (long long)nt, 256), 256, 0, c->stream>>>(ids, ids + n, ids + 2 * n, (long long)nt, s->seg_key, s->seg_val,
+                                                                                  s->seg_end, s->seg_mask, total_dev);
    KB2E_CUDA(c, cudaGetLastError());
+   KB2E_CUDA(c, cudaMemcpyAsync(&total, total_dev, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
-   cudaFree(ids); cudaFree(key_tmp); cudaFree(val_tmp); cudaFree(cub_tmp);
+   pool_free(c, key_tmp); pool_free(c, val_tmp); pool_free(c, cub_tmp);
+   if (total >= (1ull << 31)) return fail(c, KB2E_ERR_LIMIT, "filter pass needs more than 2^31 work items");
+   s->chunk_cap = (unsigned int)std::max<unsigned long long>(1, total);
+   KB2E_CUDA(c, pool_alloc(c, &s->chunks, (size_t)s->chunk_cap * sizeof(int4)));
+   s->ids = ids;
+   s->ids_n = n;
    c->filter_dirty = false;
    return KB2E_OK;
 }
@@ -490,13 +586,13 @@ static int build_filter(kb2e_ctx* c) {
 static int ensure_query_buffers(kb2e_ctx* c, int64_t nq) {
    RankState* s = c->rank;
    if (nq <= s->q_cap) return KB2E_OK;
-   cudaFree(s->q_int); cudaFree(s->q_etrue); cudaFree(s->q_cnt); cudaFree(s->out);
+   pool_free(c, s->q_int); pool_free(c, s->q_etrue); pool_free(c, s->q_cnt); pool_free(c, s->out);
    s->q_int = nullptr; s->q_etrue = nullptr; s->q_cnt = nullptr; s->out = nullptr;
    s->q_cap = 0;
-   KB2E_CUDA(c, cudaMalloc(&s->q_int, (size_t)nq * 6 * sizeof(int32_t)));
-   KB2E_CUDA(c, cudaMalloc(&s->q_etrue, (size_t)nq * sizeof(double)));
-   KB2E_CUDA(c, cudaMalloc(&s->q_cnt, (size_t)nq * 4 * sizeof(int32_t)));
-   KB2E_CUDA(c, cudaMalloc(&s->out, (size_t)nq * 4 * sizeof(int32_t)));
+   KB2E_CUDA(c, pool_alloc(c, &s->q_int, (size_t)nq * 6 * sizeof(int32_t)));
+   KB2E_CUDA(c, pool_alloc(c, &s->q_etrue, (size_t)nq * sizeof(double)));
+   KB2E_CUDA(c, pool_alloc(c, &s->q_cnt, (size_t)nq * 4 * sizeof(int32_t)));
+   KB2E_CUDA(c, pool_alloc(c, &s->out, (size_t)nq * 4 * sizeof(int32_t)));
    s->q_cap = nq;
    return KB2E_OK;
 }
@@ -506,15 +602,15 @@ static int project(kb2e_ctx* c, const std::vector<int32_t>& rels) {
    RankState* s = c->rank;
    size_t slots = rels.size();
    if (slots > s->pt_slots) {
-      cudaFree(s->pt);
+      pool_free(c, s->pt);
       s->pt = nullptr;
-      KB2E_CUDA(c, cudaMalloc(&s->pt, slots * (size_t)c->D * s->ld * sizeof(double)));
+      KB2E_CUDA(c, pool_alloc(c, &s->pt, slots * (size_t)c->D * s->ld * sizeof(double)));
       s->pt_slots = slots;
    }
    if ((int64_t)slots > s->slot_cap) {
-      cudaFree(s->slot_rel);
+      pool_free(c, s->slot_rel);
       s->slot_rel = nullptr;
-      KB2E_CUDA(c, cudaMalloc(&s->slot_rel, slots * sizeof(int32_t)));
+      KB2E_CUDA(c, pool_alloc(c, &s->slot_rel, slots * sizeof(int32_t)));
       s->slot_cap = (int64_t)slots;
    }
    KB2E_CUDA(c, cudaMemcpyAsync(s->slot_rel, rels.data(), slots * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -569,38 +665,43 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    const bool per_rel = c->cfg.model != KB2E_MODEL_TRANSE;
    const bool l2 = c->cfg.model != KB2E_MODEL_TRANSH && c->cfg.distance == KB2E_DISTANCE_L2;
    const int64_t nq = 2 * count;
-
-   // query order: grouped by relation (slot) for TransH/TransR, original order for TransE
-   std::vector<int64_t> order(count);
-   std::iota(order.begin(), order.end(), first);
-   std::vector<int32_t> rels;
-   if (per_rel) {
-      std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return c->test_r[x] < c->test_r[y]; });
-      for (int64_t i = 0; i < count; i++)
-         if (rels.empty() || rels.back() != c->test_r[order[i]]) rels.push_back(c->test_r[order[i]]);
-   }
-   // slots per pass bounded by a memory budget for the projected matrices
-   const size_t slot_bytes = (size_t)c->D * s->ld * sizeof(double);
-   const size_t budget = (size_t)16 << 30;
-   const size_t max_slots = std::max<size_t>(1, budget / slot_bytes);
+   const bool use_tc = tc_supported(c);
 
    rc = ensure_query_buffers(c, nq);
    if (rc) return rc;
    KB2E_CUDA(c, cudaMemsetAsync(s->q_cnt, 0, (size_t)nq * 4 * sizeof(int32_t), c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(s->sums, 0, 4 * sizeof(unsigned long long), c->stream));
 
-   // query arrays (SoA, nq each): fixed entity, true answer, relation, side, slot, original index
-   std::vector<int32_t> qi(6 * (size_t)nq);
-   int32_t* qf = qi.data();
-   int32_t* qt = qf + nq;
-   int32_t* qr = qt + nq;
-   int32_t* qs = qr + nq;
-   int32_t* qslot = qs + nq;
-   int32_t* qo = qslot + nq;
    struct Pass { int64_t q_begin, q_end; size_t tile_begin, tile_end; std::vector<int32_t> rels; };
    std::vector<Pass> passes(1);
    std::vector<int4> tiles;  // (first query, #queries, slot, -)
-   {
+   if (!per_rel) {
+      // TransE: one pass over the entity table, queries in test order, built on the device
+      build_queries_kernel<<<nblk(nq, 256), 256, 0, c->stream>>>(s->ids, s->ids + s->ids_n, s->ids + 2 * s->ids_n, first, count, s->q_int);
+      KB2E_CUDA(c, cudaGetLastError());
+      passes[0].q_begin = 0;
+      passes[0].q_end = nq;
+      passes[0].tile_begin = 0;
+      if (!use_tc)
+         for (int64_t q = 0; q < nq; q += kQT) tiles.push_back(make_int4((int)q, (int)std::min<int64_t>(kQT, nq - q), 0, 0));
+      passes[0].tile_end = tiles.size();
+   } else {
+      // query order: grouped by relation (slot) for TransH/TransR
+      std::vector<int64_t> order(count);
+      std::iota(order.begin(), order.end(), first);
+      std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return c->test_r[x] < c->test_r[y]; });
+      // slots per pass bounded by a memory budget for the projected matrices
+      const size_t slot_bytes = (size_t)c->D * s->ld * sizeof(double);
+      const size_t budget = (size_t)16 << 30;
+      const size_t max_slots = std::max<size_t>(1, budget / slot_bytes);
+      // query arrays (SoA, nq each): fixed entity, true answer, relation, side, slot, original index
+      std::vector<int32_t> qi(6 * (size_t)nq);
+      int32_t* qf = qi.data();
+      int32_t* qt = qf + nq;
+      int32_t* qr = qt + nq;
+      int32_t* qs = qr + nq;
+      int32_t* qslot = qs + nq;
+      int32_t* qo = qslot + nq;
       int64_t q = 0, tile_start = 0;
       int cur_slot = 0;
       passes[0].q_begin = 0;
@@ -612,21 +713,19 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       for (int64_t i = 0; i < count; i++) {
          const int64_t ti = order[i];
          const int32_t h = c->test_h[ti], t = c->test_t[ti], r = c->test_r[ti];
-         if (per_rel) {
-            Pass& cur = passes.back();
-            if (cur.rels.empty() || cur.rels.back() != r) {
-               close_tile(q);
-               if (cur.rels.size() == max_slots) {
-                  cur.q_end = q;
-                  cur.tile_end = tiles.size();
-                  Pass next;
-                  next.q_begin = q;
-                  next.tile_begin = tiles.size();
-                  passes.push_back(next);
-               }
-               passes.back().rels.push_back(r);
-               cur_slot = (int)passes.back().rels.size() - 1;
+         Pass& cur = passes.back();
+         if (cur.rels.empty() || cur.rels.back() != r) {
+            close_tile(q);
+            if (cur.rels.size() == max_slots) {
+               cur.q_end = q;
+               cur.tile_end = tiles.size();
+               Pass next;
+               next.q_begin = q;
+               next.tile_begin = tiles.size();
+               passes.push_back(next);
             }
+            passes.back().rels.push_back(r);
+            cur_slot = (int)passes.back().rels.size() - 1;
          }
          for (int side = 0; side < 2; side++) {
             if (q - tile_start == kQT) close_tile(q);
@@ -642,16 +741,18 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       close_tile(q);
       passes.back().q_end = q;
       passes.back().tile_end = tiles.size();
+      // pageable source: the copy is staged before the call returns, so the local vector may go out of scope
+      KB2E_CUDA(c, cudaMemcpyAsync(s->q_int, qi.data(), qi.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
    }
-   KB2E_CUDA(c, cudaMemcpyAsync(s->q_int, qi.data(), qi.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
    if ((int64_t)tiles.size() > s->tile_cap) {
-      cudaFree(s->tiles);
+      pool_free(c, s->tiles);
       s->tiles = nullptr;
-      KB2E_CUDA(c, cudaMalloc(&s->tiles, tiles.size() * sizeof(int4)));
+      KB2E_CUDA(c, pool_alloc(c, &s->tiles, tiles.size() * sizeof(int4)));
       s->tile_cap = (int64_t)tiles.size();
    }
-   KB2E_CUDA(c, cudaMemcpyAsync(s->tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
-   lap("query arrays (host) + H2D");
+   if (!tiles.empty())
+      KB2E_CUDA(c, cudaMemcpyAsync(s->tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+   lap("query arrays + H2D");
 
    RankArgs a;
    memset(&a, 0, sizeof(a));
@@ -668,20 +769,24 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    KB2E_CUDA(c, cudaFuncSetAttribute(rank_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
    KB2E_CUDA(c, cudaFuncSetAttribute(rank_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
-   const bool use_tc = tc_supported(c);
    if (use_tc) {
       rc = tc_init(c, &s->tc);
       if (rc) return rc;
       rc = tc_prepare_candidates(c, &s->tc);
       if (rc) return rc;
    }
-   float main_ms = 0.f;
+   while (s->pass_ev.size() < 2 * passes.size()) {
+      cudaEvent_t e;
+      KB2E_CUDA(c, cudaEventCreate(&e));
+      s->pass_ev.push_back(e);
+   }
    lap("tensor-core operand prep");
+   // Everything below is enqueued without a host wait; the one synchronisation is at the end of the call.
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
    for (size_t p = 0; p < passes.size(); p++) {
       const Pass& ps = passes[p];
-      const unsigned ntiles = (unsigned)(ps.tile_end - ps.tile_begin);
-      if (ntiles == 0) continue;
+      const long long pq = ps.q_end - ps.q_begin;
+      if (pq == 0) continue;
       if (per_rel) {
          rc = project(c, ps.rels);
          if (rc) return rc;
@@ -692,85 +797,85 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       a.tiles = s->tiles + ps.tile_begin;
       a.q_begin = ps.q_begin;
       a.q_end = ps.q_end;
-      // enough CTAs to fill the machine twice even when a pass has few query tiles; per-thread
-      // counters are 16-bit, so a split never covers more than 32768 candidate steps
-      const int steps = (c->nE + kRankThreads - 1) / kRankThreads;
-      long long splits = std::max<long long>(1, (2ll * c->num_sms + ntiles - 1) / ntiles);
-      splits = std::max<long long>(splits, (steps + 32767) / 32768);
-      splits = std::min<long long>(splits, steps);
-      a.splits = (int)splits;
-      const long long pq = ps.q_end - ps.q_begin;
       if (l2) etrue_kernel<1><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
       else etrue_kernel<0><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
-      bool exact_pass = true;
       if (use_tc) {
          // tensor-core pre-filter + exact recheck of the undecided band (rank_tc.cu)
-         bool overflow = false;
          rc = tc_run(c, &s->tc, a.q_fixed + ps.q_begin, a.q_rel + ps.q_begin, a.q_side + ps.q_begin, a.q_etrue + ps.q_begin,
-                     pq, s->q_cnt + ps.q_begin, &overflow);
+                     pq, s->q_cnt + ps.q_begin);
          if (rc) return rc;
-         if (!overflow) {
-            exact_pass = false;
-            main_ms += s->tc.last_ms;
-            c->rstats.rechecked += s->tc.last_band;
-            c->rstats.launches += 3;
-            if (s->tc.last_band) {
-               // band entries hold query indices relative to the pass window
-               recheck_kernel<1><<<nblk(s->tc.last_band, 128), 128, 0, c->stream>>>(
-                  s->tc.band, s->tc.last_band, c->ent64, c->rel64, a.q_fixed + ps.q_begin, a.q_truth + ps.q_begin,
-                  a.q_rel + ps.q_begin, a.q_side + ps.q_begin, a.q_etrue + ps.q_begin, s->q_cnt + ps.q_begin, nq, c->D);
-            }
-            KB2E_CUDA(c, cudaEventRecord(s->m0, c->stream));
-            KB2E_CUDA(c, cudaEventRecord(s->m1, c->stream));
-         } else {
-            // band list overflowed (degenerate tables): fall back to the exact kernel for this pass
-            KB2E_CUDA(c, cudaMemsetAsync(s->q_cnt + ps.q_begin, 0, (size_t)pq * sizeof(int32_t), c->stream));
-            KB2E_CUDA(c, cudaMemsetAsync(s->q_cnt + nq + ps.q_begin, 0, (size_t)pq * sizeof(int32_t), c->stream));
-         }
-      }
-      if (exact_pass) {
-         KB2E_CUDA(c, cudaEventRecord(s->m0, c->stream));
+         // band entries hold query indices relative to the pass window
+         recheck_kernel<1><<<4 * c->num_sms, 128, 0, c->stream>>>(
+            s->tc.band, s->tc.scalars + 1, s->tc.band_cap, c->ent64, c->rel64, a.q_fixed + ps.q_begin, a.q_truth + ps.q_begin,
+            a.q_rel + ps.q_begin, a.q_side + ps.q_begin, a.q_etrue + ps.q_begin, s->q_cnt + ps.q_begin, nq, c->D);
+         c->rstats.launches += 4;
+      } else {
+         const unsigned ntiles = (unsigned)(ps.tile_end - ps.tile_begin);
+         // enough CTAs to fill the machine twice even when a pass has few query tiles; per-thread
+         // counters are 16-bit, so a split never covers more than 32768 candidate steps
+         const int steps = (c->nE + kRankThreads - 1) / kRankThreads;
+         long long splits = std::max<long long>(1, (2ll * c->num_sms + ntiles - 1) / ntiles);
+         splits = std::max<long long>(splits, (steps + 32767) / 32768);
+         splits = std::min<long long>(splits, steps);
+         a.splits = (int)splits;
+         KB2E_CUDA(c, cudaEventRecord(s->pass_ev[2 * p], c->stream));
          if (l2) rank_exact_kernel<1><<<dim3(ntiles, (unsigned)splits), kRankThreads, smem, c->stream>>>(a);
          else rank_exact_kernel<0><<<dim3(ntiles, (unsigned)splits), kRankThreads, smem, c->stream>>>(a);
-         KB2E_CUDA(c, cudaEventRecord(s->m1, c->stream));
+         KB2E_CUDA(c, cudaEventRecord(s->pass_ev[2 * p + 1], c->stream));
       }
-      {
-         const unsigned fb = nblk(pq * kFilterLanes, 128);
+      if (s->n_ent) {
+         KB2E_CUDA(c, cudaMemsetAsync(s->chunk_count, 0, sizeof(unsigned int), c->stream));
+         filter_plan_kernel<<<nblk(pq, 256), 256, 0, c->stream>>>(a, s->seg_end, s->chunks, s->chunk_count, s->chunk_cap);
+         const unsigned fb = 8 * c->num_sms;   // persistent: 8 x 256 threads per SM, one chunk per warp at a time
          if (per_rel) {
-            if (l2) filter_kernel<1, false><<<fb, 128, 0, c->stream>>>(a, c->ent64);
-            else filter_kernel<0, false><<<fb, 128, 0, c->stream>>>(a, c->ent64);
+            if (l2) filter_pairs_kernel<1, false><<<fb, 256, 0, c->stream>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
+            else filter_pairs_kernel<0, false><<<fb, 256, 0, c->stream>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
          } else {
-            if (l2) filter_kernel<1, true><<<fb, 128, 0, c->stream>>>(a, c->ent64);
-            else filter_kernel<0, true><<<fb, 128, 0, c->stream>>>(a, c->ent64);
+            if (l2) filter_pairs_kernel<1, true><<<fb, 256, 0, c->stream>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
+            else filter_pairs_kernel<0, true><<<fb, 256, 0, c->stream>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
          }
       }
       KB2E_CUDA(c, cudaGetLastError());
-      // the projected slots are reused by the next pass
-      KB2E_CUDA(c, cudaEventSynchronize(s->m1));
-      float ms = 0.f;
-      KB2E_CUDA(c, cudaEventElapsedTime(&ms, s->m0, s->m1));
-      if (exact_pass) main_ms += ms;
-      c->rstats.launches += per_rel ? 4 : 3;
+      c->rstats.launches += per_rel ? 5 : 4;
    }
    finalize_kernel<<<nblk(nq, 256), 256, 0, c->stream>>>(s->q_cnt, s->q_int + 5 * nq, nq, s->out, s->sums);
    KB2E_CUDA(c, cudaGetLastError());
    KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-   std::vector<int32_t> out(4 * (size_t)nq);
+   // results go straight into the caller's buffers (a true DMA when they are pinned)
    unsigned long long hs[4];
-   KB2E_CUDA(c, cudaMemcpyAsync(out.data(), s->out, out.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+   int32_t* dst[4] = {raw_rank, filt_rank, raw_ties, filt_ties};
+   for (int k = 0; k < 4; k++)
+      if (dst[k]) KB2E_CUDA(c, cudaMemcpyAsync(dst[k], s->out + (size_t)k * nq, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(hs, s->sums, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
    lap("kernels + D2H");
+   if (use_tc) {
+      bool overflow = false;
+      rc = tc_collect(c, &s->tc, &overflow);
+      if (rc) return rc;
+      if (overflow) {
+         // the band list was too small (degenerate tables): redo the call with the exact kernel only
+         const uint32_t saved = c->cfg.flags;
+         c->cfg.flags |= KB2E_FLAG_RANK_EXACT_ONLY;
+         rc = rank_run(c, first, count, raw_rank, filt_rank, raw_ties, filt_ties, sums);
+         c->cfg.flags = saved;
+         return rc;
+      }
+      c->rstats.main_kernel_ms += s->tc.last_ms;
+      c->rstats.rechecked += s->tc.last_band;
+   } else {
+      for (size_t p = 0; p < passes.size(); p++) {
+         if (passes[p].q_end == passes[p].q_begin) continue;
+         float pms = 0.f;
+         KB2E_CUDA(c, cudaEventElapsedTime(&pms, s->pass_ev[2 * p], s->pass_ev[2 * p + 1]));
+         c->rstats.main_kernel_ms += pms;
+      }
+   }
    float ms = 0.f;
    KB2E_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
    c->rstats.kernel_ms += ms;
-   c->rstats.main_kernel_ms += main_ms;
    c->rstats.queries += (uint64_t)nq;
    c->rstats.launches += 2;
-   if (raw_rank) memcpy(raw_rank, out.data(), (size_t)nq * sizeof(int32_t));
-   if (filt_rank) memcpy(filt_rank, out.data() + nq, (size_t)nq * sizeof(int32_t));
-   if (raw_ties) memcpy(raw_ties, out.data() + 2 * nq, (size_t)nq * sizeof(int32_t));
-   if (filt_ties) memcpy(filt_ties, out.data() + 3 * nq, (size_t)nq * sizeof(int32_t));
    if (sums) for (int k = 0; k < 4; k++) sums[k] = (int64_t)hs[k];
    return KB2E_OK;
 }
@@ -800,11 +905,13 @@ int rank_score64(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t*
 void rank_free(kb2e_ctx* c) {
    RankState* s = c->rank;
    if (!s) return;
-   cudaFree(s->seg_key); cudaFree(s->seg_val); cudaFree(s->nbr); cudaFree(s->ent_key); cudaFree(s->ct0); cudaFree(s->pt);
-   cudaFree(s->q_int); cudaFree(s->q_etrue); cudaFree(s->q_cnt); cudaFree(s->tiles); cudaFree(s->slot_rel);
-   cudaFree(s->sums); cudaFree(s->out);
-   if (s->m0) { cudaEventDestroy(s->m0); cudaEventDestroy(s->m1); }
-   tc_free(&s->tc);
+   pool_free(c, s->seg_key); pool_free(c, s->seg_val); pool_free(c, s->seg_end); pool_free(c, s->nbr); pool_free(c, s->ent_key);
+   pool_free(c, s->chunks); pool_free(c, s->chunk_count); pool_free(c, s->ct0); pool_free(c, s->pt);
+   pool_free(c, s->q_int); pool_free(c, s->q_etrue); pool_free(c, s->q_cnt); pool_free(c, s->tiles); pool_free(c, s->slot_rel);
+   pool_free(c, s->sums); pool_free(c, s->out);
+   for (cudaEvent_t e : s->pass_ev) cudaEventDestroy(e);
+   pool_free(c, s->ids);
+   tc_free(c, &s->tc);
    delete s;
    c->rank = nullptr;
 }

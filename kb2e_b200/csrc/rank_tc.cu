@@ -345,13 +345,13 @@ bool tc_supported(const kb2e_ctx* c) {
 int tc_prepare_candidates(kb2e_ctx* c, TcState* s) {
    const int n_pad = ((c->nE + tc::BN - 1) / tc::BN) * tc::BN;
    if (n_pad != s->n_pad) {
-      cudaFree(s->c_hi); cudaFree(s->c_lo);
+      pool_free(c, s->c_hi); pool_free(c, s->c_lo);
       s->c_hi = s->c_lo = nullptr;
-      KB2E_CUDA(c, cudaMalloc(&s->c_hi, (size_t)n_pad * tc::kRowChunks * 16));
-      KB2E_CUDA(c, cudaMalloc(&s->c_lo, (size_t)n_pad * tc::kRowChunks * 16));
+      KB2E_CUDA(c, pool_alloc(c, &s->c_hi, (size_t)n_pad * tc::kRowChunks * 16));
+      KB2E_CUDA(c, pool_alloc(c, &s->c_lo, (size_t)n_pad * tc::kRowChunks * 16));
       s->n_pad = n_pad;
    }
-   if (!s->scalars) KB2E_CUDA(c, cudaMalloc(&s->scalars, 4 * sizeof(unsigned int)));
+   if (!s->scalars) KB2E_CUDA(c, pool_alloc(c, &s->scalars, 4 * sizeof(unsigned int)));
    KB2E_CUDA(c, cudaMemsetAsync(s->scalars, 0, 4 * sizeof(unsigned int), c->stream));
    tc::prep_candidates_kernel<<<nblk2((long long)n_pad * 32, 256), 256, 0, c->stream>>>(
       c->ent64, c->nE, n_pad, c->D, (__nv_bfloat16*)s->c_hi, (__nv_bfloat16*)s->c_lo, s->scalars);
@@ -360,18 +360,18 @@ int tc_prepare_candidates(kb2e_ctx* c, TcState* s) {
 }
 
 int tc_run(kb2e_ctx* c, TcState* s, const int32_t* q_fixed, const int32_t* q_rel, const int32_t* q_side, const double* q_etrue,
-           long long nq, int32_t* q_less, bool* overflow) {
+           long long nq, int32_t* q_less) {
    const long long q_pad = ((nq + tc::MT * tc::BM - 1) / (tc::MT * tc::BM)) * (tc::MT * tc::BM);
    if (q_pad > s->q_cap) {
-      cudaFree(s->u_hi); cudaFree(s->u_lo); cudaFree(s->thr_lo); cudaFree(s->thr_hi); cudaFree(s->band);
+      pool_free(c, s->u_hi); pool_free(c, s->u_lo); pool_free(c, s->thr_lo); pool_free(c, s->thr_hi); pool_free(c, s->band);
       s->u_hi = s->u_lo = nullptr; s->thr_lo = s->thr_hi = nullptr; s->band = nullptr;
       s->q_cap = 0;
-      KB2E_CUDA(c, cudaMalloc(&s->u_hi, (size_t)q_pad * tc::kRowChunks * 16));
-      KB2E_CUDA(c, cudaMalloc(&s->u_lo, (size_t)q_pad * tc::kRowChunks * 16));
-      KB2E_CUDA(c, cudaMalloc(&s->thr_lo, (size_t)q_pad * sizeof(float)));
-      KB2E_CUDA(c, cudaMalloc(&s->thr_hi, (size_t)q_pad * sizeof(float)));
+      KB2E_CUDA(c, pool_alloc(c, &s->u_hi, (size_t)q_pad * tc::kRowChunks * 16));
+      KB2E_CUDA(c, pool_alloc(c, &s->u_lo, (size_t)q_pad * tc::kRowChunks * 16));
+      KB2E_CUDA(c, pool_alloc(c, &s->thr_lo, (size_t)q_pad * sizeof(float)));
+      KB2E_CUDA(c, pool_alloc(c, &s->thr_hi, (size_t)q_pad * sizeof(float)));
       s->band_cap = (unsigned int)std::min<long long>(std::max<long long>(1 << 20, 64 * q_pad), 1ll << 28);
-      KB2E_CUDA(c, cudaMalloc(&s->band, (size_t)s->band_cap * sizeof(int2)));
+      KB2E_CUDA(c, pool_alloc(c, &s->band, (size_t)s->band_cap * sizeof(int2)));
       s->q_cap = q_pad;
    }
    unsigned int* band_count = s->scalars + 1;
@@ -402,14 +402,16 @@ int tc_run(kb2e_ctx* c, TcState* s, const int32_t* q_fixed, const int32_t* q_rel
    tc::rank_l2_tc_kernel<<<dim3(mtiles, (unsigned)splits), tc::THREADS, tc::SMEM_BYTES, c->stream>>>(a);
    KB2E_CUDA(c, cudaEventRecord(s->e1, c->stream));
    KB2E_CUDA(c, cudaGetLastError());
-   unsigned int count = 0;
-   KB2E_CUDA(c, cudaMemcpyAsync(&count, band_count, sizeof(count), cudaMemcpyDeviceToHost, c->stream));
-   KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   KB2E_CUDA(c, cudaMemcpyAsync(s->host_count, band_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+   return KB2E_OK;
+}
+
+int tc_collect(kb2e_ctx* c, TcState* s, bool* overflow) {
    float ms = 0.f;
    KB2E_CUDA(c, cudaEventElapsedTime(&ms, s->e0, s->e1));
    s->last_ms = ms;
-   s->last_band = count;
-   *overflow = count > s->band_cap;
+   s->last_band = *s->host_count;
+   *overflow = s->last_band > s->band_cap;
    return KB2E_OK;
 }
 
@@ -417,14 +419,15 @@ int tc_init(kb2e_ctx* c, TcState* s) {
    if (!s->e0) {
       KB2E_CUDA(c, cudaEventCreate(&s->e0));
       KB2E_CUDA(c, cudaEventCreate(&s->e1));
+      KB2E_CUDA(c, cudaMallocHost(&s->host_count, sizeof(unsigned int)));
    }
    return KB2E_OK;
 }
 
-void tc_free(TcState* s) {
-   cudaFree(s->c_hi); cudaFree(s->c_lo); cudaFree(s->u_hi); cudaFree(s->u_lo);
-   cudaFree(s->thr_lo); cudaFree(s->thr_hi); cudaFree(s->band); cudaFree(s->scalars);
-   if (s->e0) { cudaEventDestroy(s->e0); cudaEventDestroy(s->e1); }
+void tc_free(kb2e_ctx* c, TcState* s) {
+   pool_free(c, s->c_hi); pool_free(c, s->c_lo); pool_free(c, s->u_hi); pool_free(c, s->u_lo);
+   pool_free(c, s->thr_lo); pool_free(c, s->thr_hi); pool_free(c, s->band); pool_free(c, s->scalars);
+   if (s->e0) { cudaEventDestroy(s->e0); cudaEventDestroy(s->e1); cudaFreeHost(s->host_count); }
    *s = TcState();
 }
 

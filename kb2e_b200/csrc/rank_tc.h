@@ -41,6 +41,7 @@ struct TcState {
    unsigned int band_cap = 0;
    unsigned int* scalars = nullptr;  // [0] max |c| (float bits), [1] band count
    cudaEvent_t e0 = nullptr, e1 = nullptr;
+   unsigned int* host_count = nullptr;   // pinned: band count of the last tc_run, valid after tc_collect
    float last_ms = 0.f;
    unsigned int last_band = 0;
 };
@@ -48,8 +49,11 @@ struct TcState {
 bool tc_supported(const kb2e_ctx* c);
 int tc_init(kb2e_ctx* c, TcState* s);
 int tc_prepare_candidates(kb2e_ctx* c, TcState* s);
+// tc_run only enqueues work (no host synchronisation); after the stream has been synchronised, tc_collect reads the
+// kernel time and the size of the undecided band (overflow: the band list was too small -> rerun the pass exactly).
 int tc_run(kb2e_ctx* c, TcState* s, const int32_t* q_fixed, const int32_t* q_rel, const int32_t* q_side, const double* q_etrue,
-           long long nq, int32_t* q_less, bool* overflow);
-void tc_free(TcState* s);
+           long long nq, int32_t* q_less);
+int tc_collect(kb2e_ctx* c, TcState* s, bool* overflow);
+void tc_free(kb2e_ctx* c, TcState* s);
 
 }  // namespace kb2e

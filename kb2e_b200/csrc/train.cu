@@ -545,36 +545,36 @@ static inline unsigned blocks_for(long long n, int threads) { return (unsigned)(
 int train_alloc(kb2e_ctx* c) {
    if (c->tab) return KB2E_OK;
    size_t rows = (size_t)c->nE + c->nR;
-   KB2E_CUDA(c, cudaMalloc(&c->tab, rows * c->P * sizeof(float)));
-   KB2E_CUDA(c, cudaMalloc(&c->dtab, rows * c->P * sizeof(float)));
+   KB2E_CUDA(c, pool_alloc(c, &c->tab, rows * c->P * sizeof(float)));
+   KB2E_CUDA(c, pool_alloc(c, &c->dtab, rows * c->P * sizeof(float)));
    KB2E_CUDA(c, cudaMemsetAsync(c->tab, 0, rows * c->P * sizeof(float), c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->dtab, 0, rows * c->P * sizeof(float), c->stream));
-   KB2E_CUDA(c, cudaMalloc(&c->flag, (size_t)c->nE + 2 * (size_t)c->nR));
+   KB2E_CUDA(c, pool_alloc(c, &c->flag, (size_t)c->nE + 2 * (size_t)c->nR));
    KB2E_CUDA(c, cudaMemsetAsync(c->flag, 0, (size_t)c->nE + 2 * (size_t)c->nR, c->stream));
    if (c->cfg.model != KB2E_MODEL_TRANSE) {
       c->w_row = c->cfg.model == KB2E_MODEL_TRANSH ? (size_t)c->P : (size_t)c->D * c->P;
-      KB2E_CUDA(c, cudaMalloc(&c->w, (size_t)c->nR * c->w_row * sizeof(float)));
-      KB2E_CUDA(c, cudaMalloc(&c->dw, (size_t)c->nR * c->w_row * sizeof(float)));
+      KB2E_CUDA(c, pool_alloc(c, &c->w, (size_t)c->nR * c->w_row * sizeof(float)));
+      KB2E_CUDA(c, pool_alloc(c, &c->dw, (size_t)c->nR * c->w_row * sizeof(float)));
       KB2E_CUDA(c, cudaMemsetAsync(c->w, 0, (size_t)c->nR * c->w_row * sizeof(float), c->stream));
       KB2E_CUDA(c, cudaMemsetAsync(c->dw, 0, (size_t)c->nR * c->w_row * sizeof(float), c->stream));
-      KB2E_CUDA(c, cudaMalloc(&c->rmin, (size_t)c->nE * sizeof(int)));
-      KB2E_CUDA(c, cudaMalloc(&c->rmax, (size_t)c->nE * sizeof(int)));
+      KB2E_CUDA(c, pool_alloc(c, &c->rmin, (size_t)c->nE * sizeof(int)));
+      KB2E_CUDA(c, pool_alloc(c, &c->rmax, (size_t)c->nE * sizeof(int)));
       fill_int_kernel<<<blocks_for(c->nE, 256), 256, 0, c->stream>>>(c->rmin, c->nE, 0x7fffffff);
       fill_int_kernel<<<blocks_for(c->nE, 256), 256, 0, c->stream>>>(c->rmax, c->nE, -1);
    }
-   KB2E_CUDA(c, cudaMalloc(&c->barrier, 64));
-   KB2E_CUDA(c, cudaMalloc(&c->counters, 8 * sizeof(unsigned long long)));
+   KB2E_CUDA(c, pool_alloc(c, &c->barrier, 64));
+   KB2E_CUDA(c, pool_alloc(c, &c->counters, 8 * sizeof(unsigned long long)));
    KB2E_CUDA(c, cudaMemsetAsync(c->counters, 0, 8 * sizeof(unsigned long long), c->stream));
-   KB2E_CUDA(c, cudaMalloc(&c->pr, (size_t)c->nR * sizeof(double)));
+   KB2E_CUDA(c, pool_alloc(c, &c->pr, (size_t)c->nR * sizeof(double)));
    KB2E_CUDA(c, cudaGetLastError());
    return KB2E_OK;
 }
 
 void train_free(kb2e_ctx* c) {
-   cudaFree(c->tab); cudaFree(c->dtab); cudaFree(c->w); cudaFree(c->dw); cudaFree(c->flag);
-   cudaFree(c->rmin); cudaFree(c->rmax); cudaFree(c->triples); cudaFree(c->stage); cudaFree(c->hash); cudaFree(c->pr);
-   cudaFree(c->barrier); cudaFree(c->loss_dev); cudaFree(c->counters); cudaFree(c->pairs_dev);
-   cudaFree(c->ent64); cudaFree(c->rel64); cudaFree(c->w64);
+   pool_free(c, c->tab); pool_free(c, c->dtab); pool_free(c, c->w); pool_free(c, c->dw); pool_free(c, c->flag);
+   pool_free(c, c->rmin); pool_free(c, c->rmax); pool_free(c, c->triples); pool_free(c, c->stage); pool_free(c, c->hash); pool_free(c, c->pr);
+   pool_free(c, c->barrier); pool_free(c, c->loss_dev); pool_free(c, c->counters); pool_free(c, c->pairs_dev);
+   pool_free(c, c->ent64); pool_free(c, c->rel64); pool_free(c, c->w64);
    train_lazy_free(c);
 }
 
@@ -585,18 +585,18 @@ int train_set_triples(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int
    if (n == 0) return KB2E_OK;
    // device buffers are kept across calls (capacity only grows): no allocation on the steady path
    if (n > c->triples_cap) {
-      cudaFree(c->triples); cudaFree(c->stage);
+      pool_free(c, c->triples); pool_free(c, c->stage);
       c->triples = nullptr; c->stage = nullptr; c->triples_cap = 0;
-      KB2E_CUDA(c, cudaMalloc(&c->stage, 3 * (size_t)n * sizeof(int32_t)));
-      KB2E_CUDA(c, cudaMalloc(&c->triples, (size_t)n * sizeof(int4)));
+      KB2E_CUDA(c, pool_alloc(c, &c->stage, 3 * (size_t)n * sizeof(int32_t)));
+      KB2E_CUDA(c, pool_alloc(c, &c->triples, (size_t)n * sizeof(int4)));
       c->triples_cap = n;
    }
    uint64_t slots = 1024;
    while (slots < 2 * (uint64_t)n) slots <<= 1;
    if (slots > c->hash_cap) {
-      cudaFree(c->hash);
+      pool_free(c, c->hash);
       c->hash = nullptr; c->hash_cap = 0;
-      KB2E_CUDA(c, cudaMalloc(&c->hash, slots * sizeof(uint64_t)));
+      KB2E_CUDA(c, pool_alloc(c, &c->hash, slots * sizeof(uint64_t)));
       c->hash_cap = slots;
    }
    c->hash_mask = slots - 1;
@@ -654,7 +654,7 @@ static double** table64_slot(kb2e_ctx* c, int t) {
 double* table64(kb2e_ctx* c, int t) {
    double** slot = table64_slot(c, t);
    if (!*slot) {
-      if (cudaMalloc(slot, (size_t)table_rows(c, t) * c->D * sizeof(double)) != cudaSuccess) return nullptr;
+      if (pool_alloc(c, slot, (size_t)table_rows(c, t) * c->D * sizeof(double)) != cudaSuccess) return nullptr;
    }
    return *slot;
 }
@@ -785,8 +785,8 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    TrainArgs a;
    if (n_epochs <= 0) return KB2E_OK;
    if (n_epochs > c->loss_cap) {
-      cudaFree(c->loss_dev);
-      KB2E_CUDA(c, cudaMalloc(&c->loss_dev, (size_t)n_epochs * sizeof(double)));
+      pool_free(c, c->loss_dev);
+      KB2E_CUDA(c, pool_alloc(c, &c->loss_dev, (size_t)n_epochs * sizeof(double)));
       c->loss_cap = n_epochs;
    }
    fill_args(c, a);
@@ -830,7 +830,7 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    const char* trace_path = lazy ? nullptr : getenv("KB2E_TRAIN_TRACE");
    unsigned long long* trace_dev = nullptr;
    if (trace_path) {
-      KB2E_CUDA(c, cudaMalloc(&trace_dev, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long)));
+      KB2E_CUDA(c, pool_alloc(c, &trace_dev, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long)));
       KB2E_CUDA(c, cudaMemsetAsync(trace_dev, 0, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long), c->stream));
       a.trace = trace_dev;
    }
@@ -854,7 +854,7 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    if (trace_dev) {
       std::vector<unsigned long long> tr((size_t)c->num_sms * kTraceSlots);
       cudaMemcpy(tr.data(), trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-      cudaFree(trace_dev);
+      pool_free(c, trace_dev);
       if (FILE* f = fopen(trace_path, "w")) {
          for (int b = 0; b < c->num_sms; b++) {
             for (int k = 0; k < kTraceSlots; k++) fprintf(f, "%llu%c", tr[(size_t)b * kTraceSlots + k], k + 1 == kTraceSlots ? '\n' : ' ');

@@ -301,11 +301,11 @@ int train_lazy_launch(kb2e_ctx* c, const TrainArgs& base, int lps, int nv, int* 
    const size_t R = (size_t)c->nE + c->nR;
    const size_t tab_bytes = R * c->P * sizeof(float);
    if (!lb->V1) {
-      KB2E_CUDA(c, cudaMalloc(&lb->V1, tab_bytes));
-      KB2E_CUDA(c, cudaMalloc(&lb->D1, tab_bytes));
-      KB2E_CUDA(c, cudaMalloc(&lb->D2, tab_bytes));
-      KB2E_CUDA(c, cudaMalloc(&lb->T, 3 * R * sizeof(uint32_t)));
-      KB2E_CUDA(c, cudaMalloc(&lb->L, R * sizeof(uint32_t)));
+      KB2E_CUDA(c, pool_alloc(c, &lb->V1, tab_bytes));
+      KB2E_CUDA(c, pool_alloc(c, &lb->D1, tab_bytes));
+      KB2E_CUDA(c, pool_alloc(c, &lb->D2, tab_bytes));
+      KB2E_CUDA(c, pool_alloc(c, &lb->T, 3 * R * sizeof(uint32_t)));
+      KB2E_CUDA(c, pool_alloc(c, &lb->L, R * sizeof(uint32_t)));
       KB2E_CUDA(c, cudaMemsetAsync(lb->D1, 0, tab_bytes, c->stream));
       KB2E_CUDA(c, cudaMemsetAsync(lb->D2, 0, tab_bytes, c->stream));
    }
@@ -335,7 +335,7 @@ int train_lazy_launch(kb2e_ctx* c, const TrainArgs& base, int lps, int nv, int* 
 
 void train_lazy_free(kb2e_ctx* c) {
    if (!c->lazy) return;
-   cudaFree(c->lazy->V1); cudaFree(c->lazy->D1); cudaFree(c->lazy->D2); cudaFree(c->lazy->T); cudaFree(c->lazy->L);
+   pool_free(c, c->lazy->V1); pool_free(c, c->lazy->D1); pool_free(c, c->lazy->D2); pool_free(c, c->lazy->T); pool_free(c, c->lazy->L);
    delete c->lazy;
    c->lazy = nullptr;
 }

@@ -1,4 +1,5 @@
 set -x
-python -m pytest tests/test_gpu_train.py -m gpu -x -q -k partitioned 2>&1 | tail -3
-KB2E_TRAIN_TRACE=gpurun_out/dtrace3 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py --shape scaled --epochs 1 2>&1 | tail -4
-python tools/trace_report.py gpurun_out/dtrace3.0 11 | head -13
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python tools/probe.py --model transe --dim 100 --distance 1 --epochs 2 --test 59071 2>&1 | tail -2
+python tools/probe.py --model transe --dim 50 --distance 0 --method 0 --epochs 5 --test 59071 2>&1 | tail -3
+python tools/e2e_probe.py 2>&1 | grep iteration
