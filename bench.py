@@ -19,7 +19,8 @@ same JSON line with its own value / e2e / roofline / cpu_baseline.
 Multi-GPU (--gpus N under torchrun): training at FB15k shape does not shard ("replicas only",
 DESIGN.md): every rank trains its own replica (different -seed), value = N x pairs / max time.
 Ranking shards the test triples across ranks (tables + filter replicated) and all-reduces the four
-int64 sums over NCCL.
+int64 sums over NCCL.  At N > 1 the `partitioned` block adds BASELINE configs[4]: entity-partitioned
+TransE at the scaled shape (4 M entities x 200, 100 M triples), one timed epoch for the whole job.
 
 --impl reference times the UNMODIFIED reference (oracle/_ref, compiled from /root/reference by
 oracle/Makefile) on the host cores of this box: one epoch of its bfgs() per step; evalCorruption on
@@ -260,22 +261,30 @@ def run_product(args):
         p_ee, p_re = keep2[6][1], keep2[7][1]
         p_out = [k[1] for k in keep2[8:12]]
         ev_e2e = []
-        for it in range(1 + KE):
-            barrier()
-            t0 = time.perf_counter()
-            with kb2e_b200.Context(CFG["model"], CFG["dim"], nE, nR, method=CFG["method"], distance=CFG["distance"], device=local) as e2:
-                e2.upload(TABLE_ENTITY, p_ee)
+        with kb2e_b200.Context(CFG["model"], CFG["dim"], nE, nR, method=CFG["method"], distance=CFG["distance"], device=local) as e2:
+            for it in range(1 + KE):
+                barrier()
+                t0 = time.perf_counter()
+                e2.upload(TABLE_ENTITY, p_ee)          # H2D: fp64 tables
                 e2.upload(TABLE_RELATION, p_re)
-                e2.set_test_triples(p_test)
-                e2.add_filter_triples(p_filt)
-                full = e2.rank(lo, hi - lo, out=p_out)
-            dt = (time.perf_counter() - t0) * 1e3
-            if it >= 1:
-                ev_e2e.append(max_over_ranks(dt))
+                e2.set_test_triples(p_test)            # H2D: test triples
+                e2.clear_filter_triples()
+                e2.add_filter_triples(p_filt)          # H2D: train + valid; the hashed CSR is rebuilt on the device
+                full = e2.rank(lo, hi - lo, out=p_out)  # D2H: per-query raw / filtered ranks and tie counts
+                dt = (time.perf_counter() - t0) * 1e3
+                if it >= 1:
+                    ev_e2e.append(max_over_ranks(dt))
         ev_e2e_value = nq * KE / (sum(ev_e2e) * 1e-3)
         ev_h2d = int(ent_eval.nbytes + rel_eval.nbytes + 3 * p_test[0].nbytes + 3 * p_filt[0].nbytes)
         ev_d2h = int(4 * 4 * 2 * (hi - lo) + 32)
         ev_launches = int(r1["launches"] - r0["launches"])
+        # ---- entity-partitioned training at the scaled shape (BASELINE configs[4]), N > 1 only ---------------
+        part = None
+        if world > 1 and not args.no_partitioned:
+            try:
+                part = run_partitioned(rank, world, local, max_over_ranks, sum_over_ranks)
+            except Exception as exc:  # the headline line must survive a failure here
+                part = {"error": repr(exc)}
     clk = clocks.summary()
 
     if rank != 0:
@@ -311,13 +320,16 @@ def run_product(args):
                      "algorithmic_bytes_per_launch": abytes / max(launches, 1),
                      "note": "algorithmic bytes (SURVEY 8d) / CUDA-event time of the persistent launch; tables are L2-resident, so DRAM traffic is far below the algorithmic bytes"},
         "cpu_baseline": cpu_train,
+        "partitioned": part,
         "eval": {
             "metric": "eval_queries_per_s", "value": ev_value, "unit": "queries/s", "ms_per_step": sum(ev_ms) / KE, "steps": KE,
             "queries_per_step": nq, "candidates": nE, "scaling": "strong",
             "raw_mean_rank": float(sums[0]) / nq, "filtered_mean_rank": float(sums[1]) / nq,
             "raw_hits10": float(sums[2]) / nq, "filtered_hits10": float(sums[3]) / nq,
             "e2e": {"value": ev_e2e_value, "unit": "queries/s", "h2d_bytes_per_step": ev_h2d, "d2h_bytes_per_step": ev_d2h,
-                    "what": "kb2e_create + kb2e_upload x2 + set_test/add_filter + kb2e_rank with per-query ranks copied back"},
+                    "ms_per_step": sum(ev_e2e) / KE,
+                    "what": "per step, on one long-lived context: kb2e_upload x2 (fp64 tables) + kb2e_set_test_triples + kb2e_add_filter_triples "
+                            "(train + valid; filter CSR rebuilt on the device) + kb2e_rank with per-query ranks copied back; pinned host buffers"},
             "roofline": {"bound": "tensor", "achieved": ranking_flops / (main_ms * 1e-3) / 1e12, "peak": tensor_peak,
                          "unit": "TFLOP/s", "frac": ranking_flops / (main_ms * 1e-3) / 1e12 / tensor_peak, "traffic": profile_traffic("rank"),
                          "peak_source": peak_src + ", bf16 burst", "main_kernel_ms": main_ms,
@@ -333,6 +345,41 @@ def run_product(args):
     ctx.close(); ev.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_partitioned(rank, world, local, max_over_ranks, sum_over_ranks):
+    """BASELINE configs[4]: TransE squared-L2 size=200 on 4 M entities / 100 M (random) triples, entity rows
+    partitioned over the ranks, relation rows replicated (kb2e_b200/csrc/train_dist.cu).  One timed epoch =
+    100 batches x 1,000,000 pairs for the whole job (strong scaling: total work fixed)."""
+    from kb2e_b200 import kg
+    from kb2e_b200.partitioned import PartitionedTrainer
+    nE, nR, ntr, _, _, _ = kg.SHAPES["scaled"]
+    dim = 200
+    rng = np.random.default_rng(1)   # same seed on every rank: identical synthetic triples (throughput only)
+    train = (rng.integers(0, nE, ntr, dtype=np.int32), rng.integers(0, nE, ntr, dtype=np.int32), rng.integers(0, nR, ntr, dtype=np.int32))
+    pt = PartitionedTrainer(dim, nE, nR, rank, world, local, method=0, distance=1, batches=100, rate=0.01, margin=1.0, seed=1)
+    try:
+        pt.set_training_set(train, None, None)
+        del train
+        pt.init_embeddings()
+        pt.train_epochs(0, 1)        # warm-up epoch
+        s0 = pt.ctx.train_stats()
+        loss = pt.train_epochs(1, 1)
+        s1 = pt.ctx.train_stats()
+        ms = max_over_ranks(s1["kernel_ms"] - s0["kernel_ms"])
+        cnt = sum_over_ranks([s1["samples"] - s0["samples"], s1["active"] - s0["active"],
+                              s1["touched_ent"] - s0["touched_ent"] + s1["touched_rel"] - s0["touched_rel"]])
+        n, active, touched = (float(x) for x in cnt)
+        abytes, alpha = algorithmic_bytes(n, active, touched, dim)
+        return {"metric": "train_triples_per_s", "value": n / (ms * 1e-3), "unit": "triples/s", "n_gpus": world, "scaling": "strong",
+                "ms_per_epoch": ms, "alpha": alpha, "algorithmic_GBps_total": abytes / (ms * 1e-3) / 1e9,
+                "config": {"workload": "TransE L2 size=200, 4,000,000 entities x 1,345 relations, 100,000,000 random triples, batches=100 "
+                                       "(1,000,000 pairs per batch), entity rows partitioned by id mod N, relation rows replicated",
+                           "exchange": "row requests, rows and updates as posted peer stores / vector REDs over NVLink (CUDA IPC peer memory); no NCCL on the data path",
+                           "timing": "CUDA events around the persistent launch of one epoch, max over ranks; 1 warm-up epoch"},
+                "loss": float(loss[0])}
+    finally:
+        pt.close()
 
 
 def profile_traffic(which):
@@ -428,6 +475,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kb2e_b200", choices=["kb2e_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-partitioned", action="store_true", help="skip the entity-partitioned scaled-shape run at N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -71,6 +71,7 @@ struct kb2e_ctx {
    struct RankState* rank = nullptr;
    DistState* dist = nullptr;  // entity-partitioned multi-GPU training (train_dist.cu)
    kb2e::LazyBuffers* lazy = nullptr;  // second value buffer, extra delta buffers, stamps (train_lazy.cu)
+   uint32_t* pend = nullptr;           // [3][nE + nR] per-row reference counters of the one-barrier kernel (train_fused.cu)
    kb2e_rank_stats rstats{};
 };
 
@@ -116,6 +117,10 @@ double* table64(kb2e_ctx* ctx, int table);
 bool train_lazy_wanted(const kb2e_ctx* ctx, long long batchsize, int lps, int nv);
 int train_lazy_launch(kb2e_ctx* ctx, const TrainArgs& base, int lps, int nv, int* threads_out);
 void train_lazy_free(kb2e_ctx* ctx);
+
+// train_fused.cu
+bool train_fused_wanted(const kb2e_ctx* ctx, long long batchsize, int lps, int threads);
+int train_fused_launch(kb2e_ctx* ctx, const TrainArgs& base, int lps, int nv, int threads);
 
 // train_transr.cu
 int train_transr_launch(kb2e_ctx* ctx, const TrainArgs& base, int* threads_out);

@@ -70,6 +70,11 @@ struct RankState {
    std::vector<cudaEvent_t> pass_ev;   // two per pass, around the all-candidates kernel
    int32_t* ids = nullptr;        // h | t | r columns of the known triples (test first), kept for the device query builder
    size_t ids_n = 0;
+   uint64_t* key_tmp = nullptr;   // sort scratch (grow-only, like every buffer of the filter set)
+   int32_t* val_tmp = nullptr;
+   char* cub_tmp = nullptr;
+   size_t cap_seg_key = 0, cap_seg_val = 0, cap_seg_end = 0, cap_ent_key = 0, cap_nbr = 0, cap_ids = 0, cap_key_tmp = 0,
+          cap_val_tmp = 0, cap_cub_tmp = 0, cap_chunks = 0;
    kb2e::TcState tc;
 };
 
@@ -518,13 +523,22 @@ static int ensure_state(kb2e_ctx* c) {
    return KB2E_OK;
 }
 
+// All buffers of the filter set are grow-only (capacities in RankState): rebuilding the CSR for a new test / filter
+// set of the same size -- the per-step pattern of an evaluation loop -- allocates nothing.
+template <typename T>
+static int grow(kb2e_ctx* c, T** p, size_t* cap, size_t need) {
+   if (need <= *cap && *p) return KB2E_OK;
+   pool_free(c, *p);
+   *p = nullptr;
+   *cap = 0;
+   KB2E_CUDA(c, pool_alloc(c, p, std::max<size_t>(1, need) * sizeof(T)));
+   *cap = std::max<size_t>(1, need);
+   return KB2E_OK;
+}
+
 static int build_filter(kb2e_ctx* c) {
    RankState* s = c->rank;
    if (!c->filter_dirty && s->seg_key) return KB2E_OK;
-   pool_free(c, s->seg_key); pool_free(c, s->seg_val); pool_free(c, s->seg_end); pool_free(c, s->nbr); pool_free(c, s->ent_key);
-   pool_free(c, s->ids); pool_free(c, s->chunks);
-   s->seg_key = nullptr; s->seg_val = nullptr; s->seg_end = nullptr; s->nbr = nullptr; s->ent_key = nullptr; s->ids = nullptr;
-   s->ids_n = 0; s->chunks = nullptr; s->chunk_cap = 0;
    // known triples = test + filter (common/evaluation.cpp:59-61)
    const size_t nt = c->test_h.size(), nf = c->filt_h.size(), n = nt + nf;
    if (2 * n >= (1ull << 32)) return fail(c, KB2E_ERR_LIMIT, "filter set larger than 2^31 triples");
@@ -532,21 +546,19 @@ static int build_filter(kb2e_ctx* c) {
    uint64_t slots = 1024;
    while (slots < 4 * n) slots <<= 1;  // <= 2n segments, load <= 0.5
    s->seg_mask = slots - 1;
-   KB2E_CUDA(c, pool_alloc(c, &s->seg_key, slots * sizeof(uint64_t)));
-   KB2E_CUDA(c, pool_alloc(c, &s->seg_val, slots * sizeof(uint32_t)));
-   KB2E_CUDA(c, pool_alloc(c, &s->seg_end, slots * sizeof(uint32_t)));
+   int rc;
+   if ((rc = grow(c, &s->seg_key, &s->cap_seg_key, slots)) || (rc = grow(c, &s->seg_val, &s->cap_seg_val, slots)) ||
+       (rc = grow(c, &s->seg_end, &s->cap_seg_end, slots)) || (rc = grow(c, &s->ent_key, &s->cap_ent_key, 2 * n)) ||
+       (rc = grow(c, &s->nbr, &s->cap_nbr, 2 * n)) || (rc = grow(c, &s->ids, &s->cap_ids, 3 * n)) ||
+       (rc = grow(c, &s->key_tmp, &s->cap_key_tmp, 2 * n)) || (rc = grow(c, &s->val_tmp, &s->cap_val_tmp, 2 * n)))
+      return rc;
    if (!s->chunk_count) KB2E_CUDA(c, pool_alloc(c, &s->chunk_count, 2 * sizeof(unsigned long long)));
-   KB2E_CUDA(c, pool_alloc(c, &s->ent_key, std::max<size_t>(1, 2 * n) * sizeof(uint64_t)));
-   KB2E_CUDA(c, pool_alloc(c, &s->nbr, std::max<size_t>(1, 2 * n) * sizeof(int32_t)));
+   s->ids_n = n;
    KB2E_CUDA(c, cudaMemsetAsync(s->seg_key, 0xff, slots * sizeof(uint64_t), c->stream));
    if (n == 0) { c->filter_dirty = false; return KB2E_OK; }
-   int32_t* ids = nullptr;      // h | t | r columns of test then filter triples
-   uint64_t* key_tmp = nullptr;
-   int32_t* val_tmp = nullptr;
-   void* cub_tmp = nullptr;
-   KB2E_CUDA(c, pool_alloc(c, &ids, 3 * n * sizeof(int32_t)));
-   KB2E_CUDA(c, pool_alloc(c, &key_tmp, 2 * n * sizeof(uint64_t)));
-   KB2E_CUDA(c, pool_alloc(c, &val_tmp, 2 * n * sizeof(int32_t)));
+   int32_t* ids = s->ids;      // h | t | r columns of test then filter triples
+   uint64_t* key_tmp = s->key_tmp;
+   int32_t* val_tmp = s->val_tmp;
    const std::vector<int32_t>* cols[3][2] = {{&c->test_h, &c->filt_h}, {&c->test_t, &c->filt_t}, {&c->test_r, &c->filt_r}};
    for (int k = 0; k < 3; k++) {
       if (nt) KB2E_CUDA(c, cudaMemcpyAsync(ids + k * n, cols[k][0]->data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -557,9 +569,9 @@ static int build_filter(kb2e_ctx* c) {
    size_t bytes1 = 0, bytes2 = 0;
    cub::DeviceRadixSort::SortPairs(nullptr, bytes1, val_tmp, s->nbr, key_tmp, s->ent_key, (int)(2 * n), 0, kEntityBits, c->stream);
    cub::DeviceRadixSort::SortPairs(nullptr, bytes2, s->ent_key, key_tmp, s->nbr, val_tmp, (int)(2 * n), 0, 41, c->stream);
-   KB2E_CUDA(c, pool_alloc(c, &cub_tmp, std::max(bytes1, bytes2)));
-   KB2E_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, bytes1, val_tmp, s->nbr, key_tmp, s->ent_key, (int)(2 * n), 0, kEntityBits, c->stream));
-   KB2E_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, bytes2, s->ent_key, key_tmp, s->nbr, val_tmp, (int)(2 * n), 0, 41, c->stream));
+   if ((rc = grow(c, &s->cub_tmp, &s->cap_cub_tmp, std::max(bytes1, bytes2)))) return rc;
+   KB2E_CUDA(c, cub::DeviceRadixSort::SortPairs(s->cub_tmp, bytes1, val_tmp, s->nbr, key_tmp, s->ent_key, (int)(2 * n), 0, kEntityBits, c->stream));
+   KB2E_CUDA(c, cub::DeviceRadixSort::SortPairs(s->cub_tmp, bytes2, s->ent_key, key_tmp, s->nbr, val_tmp, (int)(2 * n), 0, 41, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(s->ent_key, key_tmp, 2 * n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(s->nbr, val_tmp, 2 * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
    segment_hash_kernel<<<nblk((long long)(2 * n), 256), 256, 0, c->stream>>>(s->ent_key, s->n_ent, s->seg_key, s->seg_val, s->seg_mask);
@@ -573,12 +585,9 @@ static int build_filter(kb2e_ctx* c) {
    KB2E_CUDA(c, cudaGetLastError());
    KB2E_CUDA(c, cudaMemcpyAsync(&total, total_dev, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
-   pool_free(c, key_tmp); pool_free(c, val_tmp); pool_free(c, cub_tmp);
    if (total >= (1ull << 31)) return fail(c, KB2E_ERR_LIMIT, "filter pass needs more than 2^31 work items");
    s->chunk_cap = (unsigned int)std::max<unsigned long long>(1, total);
-   KB2E_CUDA(c, pool_alloc(c, &s->chunks, (size_t)s->chunk_cap * sizeof(int4)));
-   s->ids = ids;
-   s->ids_n = n;
+   if ((rc = grow(c, &s->chunks, &s->cap_chunks, (size_t)s->chunk_cap))) return rc;
    c->filter_dirty = false;
    return KB2E_OK;
 }
@@ -906,7 +915,8 @@ void rank_free(kb2e_ctx* c) {
    RankState* s = c->rank;
    if (!s) return;
    pool_free(c, s->seg_key); pool_free(c, s->seg_val); pool_free(c, s->seg_end); pool_free(c, s->nbr); pool_free(c, s->ent_key);
-   pool_free(c, s->chunks); pool_free(c, s->chunk_count); pool_free(c, s->ct0); pool_free(c, s->pt);
+   pool_free(c, s->chunks); pool_free(c, s->chunk_count); pool_free(c, s->key_tmp); pool_free(c, s->val_tmp); pool_free(c, s->cub_tmp);
+   pool_free(c, s->ct0); pool_free(c, s->pt);
    pool_free(c, s->q_int); pool_free(c, s->q_etrue); pool_free(c, s->q_cnt); pool_free(c, s->tiles); pool_free(c, s->slot_rel);
    pool_free(c, s->sums); pool_free(c, s->out);
    for (cudaEvent_t e : s->pass_ev) cudaEventDestroy(e);

@@ -575,6 +575,7 @@ void train_free(kb2e_ctx* c) {
    pool_free(c, c->rmin); pool_free(c, c->rmax); pool_free(c, c->triples); pool_free(c, c->stage); pool_free(c, c->hash); pool_free(c, c->pr);
    pool_free(c, c->barrier); pool_free(c, c->loss_dev); pool_free(c, c->counters); pool_free(c, c->pairs_dev);
    pool_free(c, c->ent64); pool_free(c, c->rel64); pool_free(c, c->w64);
+   pool_free(c, c->pend);
    train_lazy_free(c);
 }
 
@@ -820,6 +821,9 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    int lazy_lps = lps, lazy_nv = nv;
    if (c->cfg.model == KB2E_MODEL_TRANSE && nv == 1 && lps == 32 && c->P <= 64) { lazy_lps = 16; }
    const bool lazy = train_lazy_wanted(c, a.batchsize, lazy_lps, lazy_nv);
+   // ... or, for batches that need at most half of the resident groups, fold every row where its last sample
+   // finishes (train_fused.cu)
+   const bool fused = !lazy && !transr && train_fused_wanted(c, a.batchsize, lps, threads);
    if (!transr) {
       int per_sm = 0;
       KB2E_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0));
@@ -841,6 +845,9 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
       if (rc) return rc;
    } else if (lazy) {
       int rc = train_lazy_launch(c, a, lazy_lps, lazy_nv, &threads);
+      if (rc) return rc;
+   } else if (fused) {
+      int rc = train_fused_launch(c, a, lps, nv, threads);
       if (rc) return rc;
    } else {
       KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(threads), params, 0, c->stream));

@@ -9,10 +9,13 @@
 // reach only ~190 GB/s (315 GB/s through a cuMem fd-shared mapping, 570 GB/s inside one process), and
 // remote loads also queue behind posted writes.  So nothing is ever loaded across NVLink: every
 // transfer is a posted write issued by the side that holds the data.
-//   phase 1a  rank g takes the samples k = g (mod G) of the batch (the counter RNG makes the sample set
-//             independent of G), one sample per thread, and for every row it does not own writes an
+//   phase 1a  every rank walks ALL samples of the batch, one per thread (Philox + one triple fetch: the
+//             counter RNG makes the sample set independent of G and cheap to re-derive) and keeps those
+//             whose positive head it owns -- the head row is then always local, which cuts the rows that
+//             cross NVLink from 3(G-1)/G to 2(G-1)/G per sample.  Kept samples are appended to a local
+//             list (one atomic per warp); for the tail / corrupting rows it does not own it writes an
 //             8-byte request (local row index, launch-unique stamp) into the owner's request table at
-//             the slot (sample, h|t|c) -- no atomics: the slot IS the return address
+//             the slot (list position, t|c) -- the slot IS the return address
 //   barrier   (local grid barrier + cross-GPU barrier on peer-mapped counters, system-scope atomics)
 //   phase 1s  every owner scans the request tables of its peers (coalesced stamp test + ballot) and
 //             writes each requested row into the requester's row cache
@@ -30,6 +33,8 @@
 // Semantics are identical to the single-GPU kernel (same samples, same deferred renormalisation), so
 // results agree up to the order of float additions.  Loss and counters are per rank (the host adds them).
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -55,7 +60,9 @@ struct DistArgs {
    long long req_cap;                  // 3 x the largest per-rank share of a batch
    float* stage;                       // local: updates for rows owned by peers, [nE + nR][P] (global row ids)
    uint8_t* sflag;                     // local: stamps of the staged rows, [nE + nR]
-   int4* pairs;                        // local: (h, t, r, c | corruptTail << 31) per sample
+   int4* pairs;                        // local: (h, t, r, c | corruptTail << 31) per kept sample
+   uint32_t* share;                    // local: [0], [1] kept samples of the even / odd batch, [2] overflow flag
+   long long max_share;                // capacity of pairs (and of the request slots / 3)
    uint32_t stamp_base;                // launch-unique high bits of the request stamps
    uint32_t* local_bar;
    int rank, world, wshift;
@@ -188,8 +195,6 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
    float* drel = reinterpret_cast<float*>(me + a.off_drel);
    const uint8_t* rflag = me + a.off_rflag;
    const long long RL = a.rows_local;
-   // this rank's share of a batch: global samples k = rank, rank + world, ...
-   const long long my_count = (b.batchsize - a.rank + a.world - 1) >> a.wshift;
    uint32_t ltarget = 0, xtarget = a.xbase;
    uint32_t active_acc = 0, tent_acc = 0, trel_acc = 0;
    int trace_slot = 0;
@@ -213,17 +218,42 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
          const uint8_t stamp = (uint8_t)(gb % 255u + 1u);
          const int rstamp = (int)(a.stamp_base + rel_batch + 1u);   // unique per batch and per launch, never 0
          KB2E_DTRACE();
-         // ---- phase 1a: one sample per thread: draw, record, request the rows owned by peers ----
-         for (long long j = t0; j < my_count; j += T) {
-            const Pair s = draw_pair(b, (uint32_t)(j * a.world + a.rank), gb);
-            a.pairs[j] = make_int4(s.h, s.t, s.r, s.c | (s.corruptTail ? 0x80000000 : 0));
+         // ---- phase 1a: walk the batch, keep the samples whose head lives here, request their remote rows ----
+         uint32_t* my_cnt = a.share + (rel_batch & 1u);
+         for (long long k0 = 0; k0 < b.batchsize; k0 += T) {
+            const long long k = k0 + t0;
+            bool mine = false;
+            if (k < b.batchsize) {
+               int h;
+               if (b.pairs != nullptr) {
+                  h = __ldg(b.pairs + 6ll * k);
+               } else {
+                  uint32_t x[4];
+                  philox4x32((uint32_t)k, gb, 0u, 0u, b.seed_lo, b.seed_hi, x);
+                  h = __ldg(b.triples + mulhi64(((uint64_t)x[0] << 32) | x[1], (uint64_t)b.n_train)).x;
+               }
+               mine = (h & (a.world - 1)) == a.rank;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, mine);
+            uint32_t base = 0;
+            if (lane == 0 && m) base = atomicAdd(my_cnt, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (mine) {
+               const long long j = (long long)base + __popc(m & ((1u << lane) - 1u));
+               if (j < a.max_share) {
+                  const Pair s = draw_pair(b, (uint32_t)k, gb);
+                  a.pairs[j] = make_int4(s.h, s.t, s.r, s.c | (s.corruptTail ? 0x80000000 : 0));
 #pragma unroll
-            for (int w = 0; w < 3; w++) {
-               const int e = w == 0 ? s.h : (w == 1 ? s.t : s.c);
-               const int g = e & (a.world - 1);
-               if (g != a.rank) {
-                  int2* req = reinterpret_cast<int2*>(a.arena[g] + a.off_req) + (size_t)a.rank * a.req_cap + 3 * j + w;
-                  *req = make_int2(e >> a.wshift, rstamp);
+                  for (int w = 1; w < 3; w++) {
+                     const int e = w == 1 ? s.t : s.c;
+                     const int g = e & (a.world - 1);
+                     if (g != a.rank) {
+                        int2* req = reinterpret_cast<int2*>(a.arena[g] + a.off_req) + (size_t)a.rank * a.req_cap + 3 * j + w;
+                        *req = make_int2(e >> a.wshift, rstamp);
+                     }
+                  }
+               } else {
+                  a.share[2] = 1u;   // more heads on this rank than the buffers were sized for: reported by the host
                }
             }
          }
@@ -257,6 +287,11 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
          cross_barrier(a, ltarget, xtarget);
          KB2E_DTRACE();
          // ---- phase 1b: score + accumulate, everything local ----
+         const long long my_count = min((long long)__ldcg(my_cnt), a.max_share);
+         if (blockIdx.x == 0 && threadIdx.x == 0) {
+            a.share[(rel_batch & 1u) ^ 1u] = 0u;   // the next batch's counter
+            atomicAdd(b.counters + 4, (unsigned long long)my_count);
+         }
          for (long long j = g0; j < my_count; j += G) {
             const int4 pr = __ldcg(a.pairs + j);
             Pair s;
@@ -267,11 +302,23 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
          cross_barrier(a, ltarget, xtarget);
          KB2E_DTRACE();
          // ---- phase 2a: push the staged rows to their owners (remote writes only) ----
+         // The scan runs owner-major (all staged rows of peer 0 in local-row order, then peer 1, ...): a group's
+         // contiguous share then targets ONE peer with ascending addresses instead of hopping between all peers.
          {
+            const long long rows_max = (b.nE + a.world - 1) >> a.wshift;
+            const long long ent_span = rows_max << a.wshift;
+            auto row_of = [&](long long v) -> long long {   // virtual scan index -> global row id (-1: padding)
+               if (v >= ent_span) return (long long)b.nE + (v - ent_span);
+               const long long g = v / rows_max, l = v - g * rows_max;
+               const long long r = (l << a.wshift) + g;
+               return r < b.nE ? r : -1;
+            };
             long long first, end;
-            group_range(0, (long long)b.nE + b.nR, g0, G, first, end);
-            for_stamped_rows<LPS>(first, end, gl, gmask, lane, [&](long long r) { return __ldcg(a.sflag + r) == stamp; },
-                                  [&](long long r0, long long r1) {
+            group_range(0, ent_span + b.nR, g0, G, first, end);
+            for_stamped_rows<LPS>(first, end, gl, gmask, lane,
+                                  [&](long long v) { const long long r = row_of(v); return r >= 0 && __ldcg(a.sflag + r) == stamp; },
+                                  [&](long long v0, long long v1) {
+               const long long r0 = row_of(v0), r1 = v1 >= 0 ? row_of(v1) : -1;
                float4 d0[NV], d1[NV], z[NV];
 #pragma unroll
                for (int q = 0; q < NV; q++) z[q] = f4(0.f);
@@ -436,6 +483,8 @@ struct DistState {
    float* stage = nullptr;
    uint8_t* sflag = nullptr;
    int4* pairs = nullptr;
+   uint32_t* share = nullptr;
+   unsigned long long samples_seen = 0;   // value of counters[4] after the previous launch
    uint32_t launches = 0;
    unsigned char* peers[kMaxPeers] = {};
    bool connected = false;
@@ -475,7 +524,13 @@ int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) 
    d->off_rflag = off; off = align_up(off + (size_t)c->nR, 256);
    d->off_xbar = off; off = align_up(off + 64, 256);
    // exchange buffers: this rank's request table (one region per requester) and its row cache
-   d->max_share = (c->n_train / c->cfg.batches + world - 1) / world;
+   // samples are dealt by the owner of their head, so a rank's share of a batch is binomial(batch, 1/world):
+   // mean + 8 sigma + slack (an overflow is detected by the kernel and reported, never silent)
+   {
+      const long long batch = c->n_train / c->cfg.batches;
+      const double mean = (double)batch / world;
+      d->max_share = world == 1 ? batch : std::min<long long>(batch, (long long)(mean + 8.0 * sqrt(mean) + 1024.0));
+   }
    d->req_cap = 3 * d->max_share;
    d->off_req = off; off = align_up(off + (size_t)world * d->req_cap * sizeof(int2), 256);
    d->off_cache = off; off = align_up(off + (world > 1 ? (size_t)d->req_cap * c->P * sizeof(float) : 0), 256);
@@ -487,7 +542,8 @@ int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) 
    KB2E_CUDA(c, cudaMemset(d->stage, 0, stage_rows * c->P * sizeof(float)));
    KB2E_CUDA(c, cudaMalloc(&d->sflag, stage_rows));
    KB2E_CUDA(c, cudaMemset(d->sflag, 0, stage_rows));
-   KB2E_CUDA(c, cudaMalloc(&d->pairs, (size_t)d->max_share * sizeof(int4)));
+   KB2E_CUDA(c, cudaMalloc(&d->pairs, (size_t)std::max<long long>(1, d->max_share) * sizeof(int4)));
+   KB2E_CUDA(c, cudaMalloc(&d->share, 4 * sizeof(uint32_t)));
    cudaIpcMemHandle_t h;
    KB2E_CUDA(c, cudaIpcGetMemHandle(&h, d->arena));
    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -588,8 +644,14 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    a.off_drel = d->off_drel; a.off_rflag = d->off_rflag; a.off_xbar = d->off_xbar;
    a.off_req = d->off_req; a.off_cache = d->off_cache; a.req_cap = d->req_cap;
    a.stage = d->stage; a.sflag = d->sflag; a.pairs = d->pairs;
-   if ((b.batchsize + d->world - 1) / d->world > d->max_share)
-      return fail(c, KB2E_ERR_ARG, "kb2e_dist_train_epochs: the batch grew after kb2e_dist_setup; set the train triples before kb2e_dist_setup");
+   {
+      const double mean = (double)b.batchsize / d->world;
+      const long long need = d->world == 1 ? b.batchsize : std::min<long long>(b.batchsize, (long long)(mean + 8.0 * sqrt(mean) + 1024.0));
+      if (need > d->max_share)
+         return fail(c, KB2E_ERR_ARG, "kb2e_dist_train_epochs: the batch grew after kb2e_dist_setup; set the train triples before kb2e_dist_setup");
+   }
+   a.share = d->share; a.max_share = d->max_share;
+   KB2E_CUDA(c, cudaMemsetAsync(d->share, 0, 4 * sizeof(uint32_t), c->stream));
    if ((uint64_t)c->cfg.batches * (uint64_t)n_epochs >= (1u << 20))
       return fail(c, KB2E_ERR_LIMIT, "kb2e_dist_train_epochs: at most 2^20 batches per call");
    // request stamps: (launch number << 20) | batch-in-launch + 1: an entry left by an earlier launch can never match
@@ -626,9 +688,11 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(kDistThreads), params, 0, c->stream));
    KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
    std::vector<double> loss(n_epochs);
-   unsigned long long cnt[3];
+   unsigned long long cnt[5];
+   uint32_t share_host[4] = {0, 0, 0, 0};
    KB2E_CUDA(c, cudaMemcpyAsync(loss.data(), c->loss_dev, (size_t)n_epochs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(cnt, c->counters, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+   KB2E_CUDA(c, cudaMemcpyAsync(share_host, d->share, sizeof(share_host), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
    if (trace_dev) {
       std::vector<unsigned long long> tr((size_t)c->num_sms * kTraceSlots);
@@ -645,8 +709,11 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    KB2E_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
    c->tstats.kernel_ms += ms;
    c->tstats.launches += 1;
-   const long long my = (b.batchsize - d->rank + d->world - 1) / d->world;
-   c->tstats.samples += (uint64_t)my * (uint64_t)b.batches * (uint64_t)n_epochs;
+   c->tstats.samples += cnt[4] - d->samples_seen;   // samples whose head this rank owns (counted by the kernel)
+   d->samples_seen = cnt[4];
+   if (share_host[2])
+      return fail(c, KB2E_ERR_LIMIT, "kb2e_dist_train_epochs: the heads of a batch are too unevenly spread over the ranks for the exchange buffers "
+                                     "(more than mean + 8 sigma on this rank); samples were dropped -- results of this call are invalid");
    c->tstats.active = cnt[0];
    c->tstats.touched_ent = cnt[1];
    c->tstats.touched_rel = cnt[2];
@@ -664,6 +731,7 @@ void kb2e_dist_teardown(kb2e_ctx* c) {
    cudaFree(d->stage);
    cudaFree(d->sflag);
    cudaFree(d->pairs);
+   cudaFree(d->share);
    delete d;
    c->dist = nullptr;
 }
