@@ -19,8 +19,9 @@ same JSON line with its own value / e2e / roofline / cpu_baseline.
 Multi-GPU (--gpus N under torchrun): training at FB15k shape does not shard ("replicas only",
 DESIGN.md): every rank trains its own replica (different -seed), value = N x pairs / max time.
 Ranking shards the test triples across ranks (tables + filter replicated) and all-reduces the four
-int64 sums over NCCL.  At N > 1 the `partitioned` block adds BASELINE configs[4]: entity-partitioned
-TransE at the scaled shape (4 M entities x 200, 100 M triples), one timed epoch for the whole job.
+int64 sums over NCCL.  The `partitioned` block adds BASELINE configs[4] (TransE at the scaled shape,
+4 M entities x 200, 100 M triples, one timed epoch for the whole job): at N > 1 the entity-partitioned
+trainer, at N = 1 the single-GPU kernel with the roofline fraction of that genuinely HBM-bound shape.
 
 --impl reference times the UNMODIFIED reference (oracle/_ref, compiled from /root/reference by
 oracle/Makefile) on the host cores of this box: one epoch of its bfgs() per step; evalCorruption on
@@ -280,9 +281,12 @@ def run_product(args):
         ev_launches = int(r1["launches"] - r0["launches"])
         # ---- entity-partitioned training at the scaled shape (BASELINE configs[4]), N > 1 only ---------------
         part = None
-        if world > 1 and not args.no_partitioned:
+        if not args.no_partitioned:
             try:
-                part = run_partitioned(rank, world, local, max_over_ranks, sum_over_ranks)
+                if world > 1:
+                    part = run_partitioned(rank, world, local, max_over_ranks, sum_over_ranks)
+                else:
+                    part = run_scaled_single(local, hbm_peak, peak_src)
             except Exception as exc:  # the headline line must survive a failure here
                 part = {"error": repr(exc)}
     clk = clocks.summary()
@@ -345,6 +349,41 @@ def run_product(args):
     ctx.close(); ev.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_scaled_single(local, hbm_peak, peak_src):
+    """BASELINE configs[4] on ONE GPU (the whole 3.2 GB table in one HBM): the same persistent kernel as the headline,
+    at the one shape where the training step is genuinely HBM-bound.  It is the N = 1 point of the `partitioned` strong-
+    scaling series and carries its own roofline fraction, measured live (CUDA events, algorithmic bytes of SURVEY 8d)."""
+    import kb2e_b200
+    from kb2e_b200 import kg
+    nE, nR, ntr, _, _, _ = kg.SHAPES["scaled"]
+    dim = 200
+    rng = np.random.default_rng(1)
+    train = (rng.integers(0, nE, ntr, dtype=np.int32), rng.integers(0, nE, ntr, dtype=np.int32), rng.integers(0, nR, ntr, dtype=np.int32))
+    with kb2e_b200.Context("transe", dim, nE, nR, method=0, distance=1, batches=100, rate=0.01, margin=1.0, seed=1, device=local) as ctx:
+        ctx.set_train_triples(train)
+        del train
+        ctx.set_bern(None, None)
+        ctx.init_embeddings()
+        ctx.train_epochs(0, 1)       # warm-up epoch
+        s0 = ctx.train_stats()
+        loss = ctx.train_epochs(1, 1)
+        s1 = ctx.train_stats()
+    ms = s1["kernel_ms"] - s0["kernel_ms"]
+    n = s1["samples"] - s0["samples"]
+    touched = (s1["touched_ent"] - s0["touched_ent"]) + (s1["touched_rel"] - s0["touched_rel"])
+    abytes, alpha = algorithmic_bytes(n, s1["active"] - s0["active"], touched, dim)
+    achieved = abytes / (ms * 1e-3) / 1e9
+    return {"metric": "train_triples_per_s", "value": n / (ms * 1e-3), "unit": "triples/s", "n_gpus": 1, "scaling": "strong",
+            "ms_per_epoch": ms, "alpha": alpha,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": profile_traffic("scaled"), "peak_source": peak_src, "kernel": "kb2e::train_kernel<TransE,32,2,768>",
+                         "note": "traffic = dram bytes of one 100-batch launch from the committed ncu capture (profiles/r01_ncu_full_summary.txt)"},
+            "config": {"workload": "TransE L2 size=200, 4,000,000 entities x 1,345 relations, 100,000,000 random triples, batches=100 "
+                                   "(1,000,000 pairs per batch), single GPU: the N = 1 point of the partitioned series",
+                       "timing": "CUDA events around the persistent launch of one epoch; 1 warm-up epoch"},
+            "loss": float(loss[0])}
 
 
 def run_partitioned(rank, world, local, max_over_ranks, sum_over_ranks):
@@ -475,7 +514,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kb2e_b200", choices=["kb2e_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-partitioned", action="store_true", help="skip the entity-partitioned scaled-shape run at N > 1")
+    ap.add_argument("--no-partitioned", action="store_true", help="skip the scaled-shape (BASELINE configs[4]) run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -37,6 +37,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "rank_f32.h"
 #include "rank_tc.h"
 
 struct RankState {
@@ -76,6 +77,7 @@ struct RankState {
    size_t cap_seg_key = 0, cap_seg_val = 0, cap_seg_end = 0, cap_ent_key = 0, cap_nbr = 0, cap_ids = 0, cap_key_tmp = 0,
           cap_val_tmp = 0, cap_cub_tmp = 0, cap_chunks = 0;
    kb2e::TcState tc;
+   kb2e::F32State f32;
 };
 
 namespace kb2e {
@@ -675,6 +677,9 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    const bool l2 = c->cfg.model != KB2E_MODEL_TRANSH && c->cfg.distance == KB2E_DISTANCE_L2;
    const int64_t nq = 2 * count;
    const bool use_tc = tc_supported(c);
+   // every other model / distance: fp32 CUDA-core pre-filter + exact recheck (rank_f32.cu) unless the exact kernel is forced
+   const bool use_f32 = !use_tc && !(c->cfg.flags & KB2E_FLAG_RANK_EXACT_ONLY);
+   const int tile_q = use_f32 ? kF32QueriesPerTile : kQT;
 
    rc = ensure_query_buffers(c, nq);
    if (rc) return rc;
@@ -692,7 +697,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       passes[0].q_end = nq;
       passes[0].tile_begin = 0;
       if (!use_tc)
-         for (int64_t q = 0; q < nq; q += kQT) tiles.push_back(make_int4((int)q, (int)std::min<int64_t>(kQT, nq - q), 0, 0));
+         for (int64_t q = 0; q < nq; q += tile_q) tiles.push_back(make_int4((int)q, (int)std::min<int64_t>(tile_q, nq - q), 0, 0));
       passes[0].tile_end = tiles.size();
    } else {
       // query order: grouped by relation (slot) for TransH/TransR
@@ -737,7 +742,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
             cur_slot = (int)passes.back().rels.size() - 1;
          }
          for (int side = 0; side < 2; side++) {
-            if (q - tile_start == kQT) close_tile(q);
+            if (q - tile_start == tile_q) close_tile(q);
             qf[q] = side == 0 ? t : h;  // the entity that stays
             qt[q] = side == 0 ? h : t;  // the true answer among the candidates
             qr[q] = r;
@@ -790,6 +795,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       s->pass_ev.push_back(e);
    }
    lap("tensor-core operand prep");
+   bool f32_started = false;
    // Everything below is enqueued without a host wait; the one synchronisation is at the end of the call.
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
    for (size_t p = 0; p < passes.size(); p++) {
@@ -817,6 +823,15 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
          recheck_kernel<1><<<4 * c->num_sms, 128, 0, c->stream>>>(
             s->tc.band, s->tc.scalars + 1, s->tc.band_cap, c->ent64, c->rel64, a.q_fixed + ps.q_begin, a.q_truth + ps.q_begin,
             a.q_rel + ps.q_begin, a.q_side + ps.q_begin, a.q_etrue + ps.q_begin, s->q_cnt + ps.q_begin, nq, c->D);
+         c->rstats.launches += 4;
+      } else if (use_f32) {
+         const unsigned ntiles = (unsigned)(ps.tile_end - ps.tile_begin);
+         rc = f32_prepare(c, &s->f32, a.ct, per_rel ? ps.rels.size() : 1, s->ld, nq, !f32_started);
+         f32_started = true;
+         if (rc) return rc;
+         rc = f32_run(c, &s->f32, l2, a.ct, s->ld, s->q_int, nq, s->q_etrue, ps.q_begin, ps.q_end, a.tiles, ntiles, s->q_cnt,
+                      s->pass_ev[2 * p], s->pass_ev[2 * p + 1]);
+         if (rc) return rc;
          c->rstats.launches += 4;
       } else {
          const unsigned ntiles = (unsigned)(ps.tile_end - ps.tile_begin);
@@ -873,6 +888,17 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       c->rstats.main_kernel_ms += s->tc.last_ms;
       c->rstats.rechecked += s->tc.last_band;
    } else {
+      if (use_f32) {
+         if (s->f32.host_count[1]) {
+            // a band list overflowed (degenerate tables): redo the call with the exact kernel only
+            const uint32_t saved = c->cfg.flags;
+            c->cfg.flags |= KB2E_FLAG_RANK_EXACT_ONLY;
+            rc = rank_run(c, first, count, raw_rank, filt_rank, raw_ties, filt_ties, sums);
+            c->cfg.flags = saved;
+            return rc;
+         }
+         c->rstats.rechecked += s->f32.host_count[2];
+      }
       for (size_t p = 0; p < passes.size(); p++) {
          if (passes[p].q_end == passes[p].q_begin) continue;
          float pms = 0.f;
@@ -922,6 +948,7 @@ void rank_free(kb2e_ctx* c) {
    for (cudaEvent_t e : s->pass_ev) cudaEventDestroy(e);
    pool_free(c, s->ids);
    tc_free(c, &s->tc);
+   f32_free(c, &s->f32);
    delete s;
    c->rank = nullptr;
 }

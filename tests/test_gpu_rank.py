@@ -159,3 +159,45 @@ def test_tensor_core_prefilter_equals_exact_kernel(gpu_lib, oracle, D, nE, n_tes
     lo, hi, flo, fhi = oracle.rank(0, 1, ent, rel, None, test[:40], np.concatenate([filt, test[40:]]))
     assert np.array_equal(out["tc"]["raw"][:80], lo) and np.array_equal(out["tc"]["filt"][:80], flo)
     assert np.array_equal(out["tc"]["raw_ties"][:80], hi - lo)
+
+
+@pytest.mark.parametrize("model,dist,D,nE", [(0, 0, 50, 2100), (1, 0, 100, 1300), (2, 0, 20, 900), (2, 1, 33, 700)])
+def test_fp32_prefilter_equals_exact_kernel(gpu_lib, model, dist, D, nE):
+    """TransE L1 / TransH / TransR: the fp32 CUDA-core pre-filter with its rigorous error bound + exact fp64 recheck of the
+    undecided band (rank_f32.cu) must give the very same integer ranks and tie counts as the exact fp64 kernel, including
+    on clustered embeddings (near-ties everywhere), exact duplicates (true ties) and several relations per pass."""
+    from kb2e_b200.api import FLAG_RANK_EXACT_ONLY
+    nR, n_test = 6, 160
+    rng = np.random.default_rng(100 * model + D)
+    centers = rng.normal(0, 1 / np.sqrt(D), (30, D))
+    ent = centers[rng.integers(0, 30, nE)] + rng.normal(0, 2e-5, (nE, D))
+    ent[: nE // 2] = rng.normal(0, 1 / np.sqrt(D), (nE // 2, D))
+    ent = np.round(ent, 6)
+    ent[nE - 1] = ent[1]
+    ent[nE - 2] = ent[nE // 2 + 3]
+    rel = np.round(rng.normal(0, 0.3 / np.sqrt(D), (nR, D)), 6)
+    w = None
+    if model == 1:
+        w = rng.normal(0, 1, (nR, D))
+        w = np.round(w / np.linalg.norm(w, axis=1, keepdims=True), 6)
+    if model == 2:
+        w = np.round(np.tile(np.eye(D), (nR, 1, 1)) + rng.normal(0, 0.05, (nR, D, D)), 6)
+    tri = np.stack([rng.integers(0, nE, n_test + 400), rng.integers(0, nE, n_test + 400), rng.integers(0, nR, n_test + 400)], 1).astype(np.int32)
+    tri[:5, 0] = 1
+    tri[5:9, 1] = nE // 2 + 3
+    test, filt = tri[:n_test], tri[n_test:]
+    out = {}
+    for name, flags in (("f32", 0), ("exact", FLAG_RANK_EXACT_ONLY)):
+        with make_ctx(model, D, nE, nR, distance=dist, flags=flags) as ctx:
+            upload_tables(ctx, ent, rel, w)
+            ctx.set_test_triples(test)
+            ctx.add_filter_triples(filt)
+            out[name] = ctx.rank()
+            out[name + "_window"] = ctx.rank(first=7, count=50)
+            out[name + "_stats"] = ctx.rank_stats()
+    for k in ("raw", "filt", "raw_ties", "filt_ties", "sums"):
+        assert np.array_equal(out["f32"][k], out["exact"][k]), k
+        assert np.array_equal(out["f32_window"][k], out["exact_window"][k]), k
+    assert (out["exact"]["raw_ties"] > 0).any()
+    assert out["f32_stats"]["rechecked"] > 0 and out["exact_stats"]["rechecked"] == 0
+    assert out["f32_stats"]["rechecked"] < 0.3 * 2 * (n_test + 50) * nE
