@@ -24,9 +24,12 @@
 //             accumulates the update with local vector REDs: rows it owns into its delta table, rows
 //             owned by a peer into a local staging table; stamps them
 //   barrier
-//   phase 2a  staged rows are added into the owner's delta table with red.global.add.v4.f32 over NVLink
-//             and the owner's stamp is set
+//   phase 2a  staged rows are appended to the owner's inbox (one compact region per sender, slots reserved with
+//             one local atomic per 32 scanned rows): sequential posted stores instead of random remote REDs,
+//             which ran at only ~190 GB/s per GPU in the 8-GPU all-to-all; the entry counts travel with the barrier
 //   barrier
+//   phase 2a' every owner adds its inbox entries into its delta table with LOCAL vector REDs and stamps the rows
+//   (local grid barrier)
 //   phase 2b  every owner publishes its stamped rows (row += delta, normalise once); the owner of a
 //             relation row also writes the new row into every replica
 //   barrier
@@ -56,8 +59,11 @@ struct DistArgs {
    // arena layout: tab [rows_local][P] | dtab [rows_local][P] | flag [rows_local] |
    //               rel [nR][P] (replica) | drel [nR][P] | rflag [nR] | cross-GPU counter |
    //               req [world][req_cap] int2 (written by the peers) | cache [req_cap][P] (written by the peers)
-   size_t off_tab, off_dtab, off_flag, off_rel, off_drel, off_rflag, off_xbar, off_req, off_cache;
+   //               inbox [world][inbox_cap][4 + P] (written by the peers) | inbox_cnt [world] (written by the peers)
+   size_t off_tab, off_dtab, off_flag, off_rel, off_drel, off_rflag, off_xbar, off_req, off_cache, off_inbox, off_inbox_cnt;
    long long req_cap;                  // 3 x the largest per-rank share of a batch
+   long long inbox_cap;                // staged-row entries one sender may append per batch
+   uint32_t* push_cnt;                 // local: [world] entries appended to each owner's inbox in this batch
    float* stage;                       // local: updates for rows owned by peers, [nE + nR][P] (global row ids)
    uint8_t* sflag;                     // local: stamps of the staged rows, [nE + nR]
    int4* pairs;                        // local: (h, t, r, c | corruptTail << 31) per kept sample
@@ -95,23 +101,34 @@ __device__ __forceinline__ float* rel_delta(const DistArgs& a, int r, uint8_t*& 
    return a.stage + ((size_t)a.base.nE + r) * a.base.P;
 }
 
-// all CTAs of this GPU, then all GPUs, then all CTAs again (release / acquire at system scope)
-__device__ __forceinline__ void cross_barrier(const DistArgs& a, uint32_t& ltarget, uint32_t& xtarget) {
+// all CTAs of this GPU, then all GPUs, then all CTAs again (release / acquire at system scope).  publish: after this
+// GPU's CTAs have all arrived, its per-owner inbox counts are written to the owners before the cross-GPU signal.
+__device__ __forceinline__ void cross_barrier(const DistArgs& a, uint32_t& ltarget, uint32_t& xtarget, bool publish = false) {
    __threadfence_system();   // this thread's peer stores / REDs are performed before it arrives
    grid_barrier(a.local_bar, ltarget);
-   if (blockIdx.x == 0 && threadIdx.x == 0) {
-      xtarget += (uint32_t)a.world;
-      asm volatile("fence.acq_rel.sys;" ::: "memory");
-      for (int g = 0; g < a.world; g++) {
-         uint32_t* p = reinterpret_cast<uint32_t*>(a.arena[g] + a.off_xbar);
-         asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p), "r"(1u) : "memory");
+   if (blockIdx.x == 0) {
+      if (publish) {
+         if ((int)threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(a.arena[threadIdx.x] + a.off_inbox_cnt) + a.rank;
+            *dst = __ldcg(a.push_cnt + threadIdx.x);
+            __threadfence_system();
+         }
+         __syncthreads();
       }
-      const uint32_t* mine = reinterpret_cast<const uint32_t*>(a.arena[a.rank] + a.off_xbar);
-      uint32_t v;
-      do {
-         asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-      } while ((int32_t)(v - xtarget) < 0);
-      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      if (threadIdx.x == 0) {
+         xtarget += (uint32_t)a.world;
+         asm volatile("fence.acq_rel.sys;" ::: "memory");
+         for (int g = 0; g < a.world; g++) {
+            uint32_t* p = reinterpret_cast<uint32_t*>(a.arena[g] + a.off_xbar);
+            asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p), "r"(1u) : "memory");
+         }
+         const uint32_t* mine = reinterpret_cast<const uint32_t*>(a.arena[a.rank] + a.off_xbar);
+         uint32_t v;
+         do {
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+         } while ((int32_t)(v - xtarget) < 0);
+         asm volatile("fence.acq_rel.sys;" ::: "memory");
+      }
    }
    grid_barrier(a.local_bar, ltarget);
 }
@@ -292,6 +309,7 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
             a.share[(rel_batch & 1u) ^ 1u] = 0u;   // the next batch's counter
             atomicAdd(b.counters + 4, (unsigned long long)my_count);
          }
+         if (blockIdx.x == 0 && (int)threadIdx.x < a.world) a.push_cnt[threadIdx.x] = 0u;   // this batch's inbox appends
          for (long long j = g0; j < my_count; j += G) {
             const int4 pr = __ldcg(a.pairs + j);
             Pair s;
@@ -301,53 +319,91 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
          KB2E_DTRACE();
          cross_barrier(a, ltarget, xtarget);
          KB2E_DTRACE();
-         // ---- phase 2a: push the staged rows to their owners (remote writes only) ----
-         // The scan runs owner-major (all staged rows of peer 0 in local-row order, then peer 1, ...): a group's
-         // contiguous share then targets ONE peer with ascending addresses instead of hopping between all peers.
+         // ---- phase 2a: append the staged rows to their owners' inboxes (sequential posted stores) ----
          {
+            const int S = P + 4;   // entry: 16-byte header (target row) + the row
             const long long rows_max = (b.nE + a.world - 1) >> a.wshift;
-            const long long ent_span = rows_max << a.wshift;
-            auto row_of = [&](long long v) -> long long {   // virtual scan index -> global row id (-1: padding)
-               if (v >= ent_span) return (long long)b.nE + (v - ent_span);
-               const long long g = v / rows_max, l = v - g * rows_max;
-               const long long r = (l << a.wshift) + g;
-               return r < b.nE ? r : -1;
-            };
-            long long first, end;
-            group_range(0, ent_span + b.nR, g0, G, first, end);
-            for_stamped_rows<LPS>(first, end, gl, gmask, lane,
-                                  [&](long long v) { const long long r = row_of(v); return r >= 0 && __ldcg(a.sflag + r) == stamp; },
-                                  [&](long long v0, long long v1) {
-               const long long r0 = row_of(v0), r1 = v1 >= 0 ? row_of(v1) : -1;
-               float4 d0[NV], d1[NV], z[NV];
+            const int gshift = (lane / LPS) * LPS;
+            float4 z[NV];
 #pragma unroll
-               for (int q = 0; q < NV; q++) z[q] = f4(0.f);
-               load_row<LPS, NV>(a.stage + (size_t)r0 * P, P, gl, d0);
-               if (r1 >= 0) load_row<LPS, NV>(a.stage + (size_t)r1 * P, P, gl, d1);
-               auto push = [&](long long r, float4 (&d)[NV]) {
-                  float* dst;
-                  uint8_t* dflag;
-                  if (r < b.nE) {
-                     unsigned char* owner = a.arena[r & (a.world - 1)];
-                     const size_t l = (size_t)(r >> a.wshift);
-                     dst = reinterpret_cast<float*>(owner + a.off_dtab) + l * P;
-                     dflag = owner + a.off_flag + l;
-                  } else {
-                     const long long rr = r - b.nE;
-                     unsigned char* owner = a.arena[rr & (a.world - 1)];
-                     dst = reinterpret_cast<float*>(owner + a.off_drel) + (size_t)rr * P;
-                     dflag = owner + a.off_rflag + rr;
+            for (int q = 0; q < NV; q++) z[q] = f4(0.f);
+            auto append = [&](int owner, long long idx, long long r, int hdr) {
+               float4 d[NV];
+               load_row<LPS, NV>(a.stage + (size_t)r * P, P, gl, d);
+               if (idx < a.inbox_cap) {
+                  float* ent = reinterpret_cast<float*>(a.arena[owner] + a.off_inbox) + ((size_t)a.rank * a.inbox_cap + idx) * S;
+                  if (gl == 0) *reinterpret_cast<int4*>(ent) = make_int4(hdr, 0, 0, 0);
+                  store_row<LPS, NV>(ent + 4, P, gl, d);
+               } else if (gl == 0) {
+                  a.share[2] = 1u;   // more staged rows for one owner than the inbox holds: reported by the host
+               }
+               store_row<LPS, NV>(a.stage + (size_t)r * P, P, gl, z);
+            };
+            for (int o = 0; o < a.world; o++) {
+               if (o == a.rank) continue;   // own rows never pass through the staging table
+               for (long long l0 = g0 * LPS; l0 < rows_max; l0 += G * LPS) {
+                  const long long l = l0 + gl;
+                  const long long r = (l << a.wshift) + o;
+                  const bool f = l < rows_max && r < b.nE && __ldcg(a.sflag + r) == stamp;
+                  uint32_t m = (__ballot_sync(gmask, f) >> gshift) & (LPS == 32 ? 0xffffffffu : ((1u << LPS) - 1u));
+                  if (!m) continue;
+                  uint32_t base = 0;
+                  if (gl == 0) base = atomicAdd(a.push_cnt + o, (uint32_t)__popc(m));
+                  base = __shfl_sync(gmask, base, gshift);
+                  for (int k = 0; m; k++) {
+                     const int bit = __ffs(m) - 1;
+                     m &= m - 1;
+                     const long long lr = l0 + bit;
+                     append(o, (long long)base + k, (lr << a.wshift) + o, (int)lr);
                   }
-                  red_row<LPS, NV>(dst, P, gl, d);   // several senders may add into the same owner row
-                  if (gl == 0) *dflag = stamp;
-                  store_row<LPS, NV>(a.stage + (size_t)r * P, P, gl, z);
-               };
-               push(r0, d0);
-               if (r1 >= 0) push(r1, d1);
-            });
+               }
+            }
+            // relation rows (few): one slot at a time
+            for (long long rr = g0; rr < b.nR; rr += G) {
+               const int o = (int)(rr & (a.world - 1));
+               if (o == a.rank || __ldcg(a.sflag + b.nE + rr) != stamp) continue;
+               uint32_t idx = 0;
+               if (gl == 0) idx = atomicAdd(a.push_cnt + o, 1u);
+               idx = __shfl_sync(gmask, idx, gshift);
+               append(o, (long long)idx, (long long)b.nE + rr, -1 - (int)rr);
+            }
          }
          KB2E_DTRACE();
-         cross_barrier(a, ltarget, xtarget);
+         cross_barrier(a, ltarget, xtarget, true);
+         KB2E_DTRACE();
+         // ---- phase 2a': add the inbox entries into the own delta tables (local REDs), stamp the rows ----
+         if (a.world > 1) {
+            const int S = P + 4;
+            const uint32_t* cnts = reinterpret_cast<const uint32_t*>(me + a.off_inbox_cnt);
+            for (int src = 0; src < a.world; src++) {
+               if (src == a.rank) continue;
+               const long long n = min((long long)__ldcg(cnts + src), a.inbox_cap);
+               const float* box = reinterpret_cast<const float*>(me + a.off_inbox) + (size_t)src * a.inbox_cap * S;
+               for (long long e = g0; e < n; e += 2 * G) {
+                  const long long e1 = e + G;
+                  const float* ent0 = box + (size_t)e * S;
+                  const float* ent1 = box + (size_t)(e1 < n ? e1 : e) * S;
+                  const int h0 = __ldcg(reinterpret_cast<const int*>(ent0));
+                  const int h1 = __ldcg(reinterpret_cast<const int*>(ent1));
+                  float4 d0[NV], d1[NV];
+                  load_row<LPS, NV>(ent0 + 4, P, gl, d0);
+                  load_row<LPS, NV>(ent1 + 4, P, gl, d1);
+                  auto absorb = [&](int hdr, float4 (&d)[NV]) {
+                     if (hdr >= 0) {
+                        red_row<LPS, NV>(dtab + (size_t)hdr * P, P, gl, d);
+                        if (gl == 0) me[a.off_flag + hdr] = stamp;
+                     } else {
+                        const int rr = -1 - hdr;
+                        red_row<LPS, NV>(drel + (size_t)rr * P, P, gl, d);
+                        if (gl == 0) me[a.off_rflag + rr] = stamp;
+                     }
+                  };
+                  absorb(h0, d0);
+                  if (e1 < n) absorb(h1, d1);
+               }
+            }
+            grid_barrier(a.local_bar, ltarget);   // every absorbed update has landed before the publish reads the deltas
+         }
          KB2E_DTRACE();
          // ---- phase 2b: own entity rows: row += delta, normalise once, publish ----
          {
@@ -477,7 +533,10 @@ struct DistState {
    long long rows_local = 0;
    unsigned char* arena = nullptr;
    size_t arena_bytes = 0;
-   size_t off_tab = 0, off_dtab = 0, off_flag = 0, off_rel = 0, off_drel = 0, off_rflag = 0, off_xbar = 0, off_req = 0, off_cache = 0;
+   size_t off_tab = 0, off_dtab = 0, off_flag = 0, off_rel = 0, off_drel = 0, off_rflag = 0, off_xbar = 0, off_req = 0, off_cache = 0,
+          off_inbox = 0, off_inbox_cnt = 0;
+   long long inbox_cap = 0;
+   uint32_t* push_cnt = nullptr;
    long long req_cap = 0;        // request / cache slots per requester: 3 x the largest per-rank share of a batch
    long long max_share = 0;
    float* stage = nullptr;
@@ -534,6 +593,12 @@ int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) 
    d->req_cap = 3 * d->max_share;
    d->off_req = off; off = align_up(off + (size_t)world * d->req_cap * sizeof(int2), 256);
    d->off_cache = off; off = align_up(off + (world > 1 ? (size_t)d->req_cap * c->P * sizeof(float) : 0), 256);
+   // inbox: per sender, the staged rows it may append in one batch.  A sender stages at most 2 remote rows per kept
+   // sample (tail, corrupting entity), spread evenly over the world - 1 other owners: mean + 50 % + slack, never more
+   // than the worst case (an overflow is detected by the kernel and reported)
+   d->inbox_cap = world == 1 ? 0 : std::min<long long>(2 * d->max_share + c->nR, (long long)(3.0 * d->max_share / world) + c->nR + 4096);
+   d->off_inbox = off; off = align_up(off + (size_t)world * d->inbox_cap * (c->P + 4) * sizeof(float), 256);
+   d->off_inbox_cnt = off; off = align_up(off + (size_t)world * sizeof(uint32_t), 256);
    d->arena_bytes = off;
    KB2E_CUDA(c, cudaMalloc(&d->arena, d->arena_bytes));
    KB2E_CUDA(c, cudaMemset(d->arena, 0, d->arena_bytes));
@@ -544,6 +609,8 @@ int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) 
    KB2E_CUDA(c, cudaMemset(d->sflag, 0, stage_rows));
    KB2E_CUDA(c, cudaMalloc(&d->pairs, (size_t)std::max<long long>(1, d->max_share) * sizeof(int4)));
    KB2E_CUDA(c, cudaMalloc(&d->share, 4 * sizeof(uint32_t)));
+   KB2E_CUDA(c, cudaMalloc(&d->push_cnt, kMaxPeers * sizeof(uint32_t)));
+   KB2E_CUDA(c, cudaMemset(d->push_cnt, 0, kMaxPeers * sizeof(uint32_t)));
    cudaIpcMemHandle_t h;
    KB2E_CUDA(c, cudaIpcGetMemHandle(&h, d->arena));
    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -643,6 +710,7 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    a.off_tab = d->off_tab; a.off_dtab = d->off_dtab; a.off_flag = d->off_flag; a.off_rel = d->off_rel;
    a.off_drel = d->off_drel; a.off_rflag = d->off_rflag; a.off_xbar = d->off_xbar;
    a.off_req = d->off_req; a.off_cache = d->off_cache; a.req_cap = d->req_cap;
+   a.off_inbox = d->off_inbox; a.off_inbox_cnt = d->off_inbox_cnt; a.inbox_cap = d->inbox_cap; a.push_cnt = d->push_cnt;
    a.stage = d->stage; a.sflag = d->sflag; a.pairs = d->pairs;
    {
       const double mean = (double)b.batchsize / d->world;
@@ -712,8 +780,8 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    c->tstats.samples += cnt[4] - d->samples_seen;   // samples whose head this rank owns (counted by the kernel)
    d->samples_seen = cnt[4];
    if (share_host[2])
-      return fail(c, KB2E_ERR_LIMIT, "kb2e_dist_train_epochs: the heads of a batch are too unevenly spread over the ranks for the exchange buffers "
-                                     "(more than mean + 8 sigma on this rank); samples were dropped -- results of this call are invalid");
+      return fail(c, KB2E_ERR_LIMIT, "kb2e_dist_train_epochs: the heads (or the remote rows) of a batch are too unevenly spread over the ranks for the "
+                                     "exchange buffers; samples or updates were dropped -- results of this call are invalid");
    c->tstats.active = cnt[0];
    c->tstats.touched_ent = cnt[1];
    c->tstats.touched_rel = cnt[2];
@@ -732,6 +800,7 @@ void kb2e_dist_teardown(kb2e_ctx* c) {
    cudaFree(d->sflag);
    cudaFree(d->pairs);
    cudaFree(d->share);
+   cudaFree(d->push_cnt);
    delete d;
    c->dist = nullptr;
 }

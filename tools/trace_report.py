@@ -3,7 +3,9 @@ import sys
 import numpy as np
 t = np.loadtxt(sys.argv[1], dtype=np.uint64).astype(np.int64)
 stamps = int(sys.argv[2]) if len(sys.argv) > 2 else 5   # stamps per batch (5 for TransE, 5 for H too)
-names = {2: ["phase1 + fold", "barrier"],
+names = {12: ["1a sample+request", "barrier", "1s serve", "barrier", "1b compute", "barrier", "2a push", "barrier", "2a' absorb",
+              "2b entities", "2b relations", "barrier"],
+         2: ["phase1 + fold", "barrier"],
          11: ["1a sample+request", "barrier", "1s serve", "barrier", "1b compute", "barrier", "2a push", "barrier", "2b entities",
               "2b relations", "barrier"],
          6: ["phase1", "barrier", "2a relations", "barrier", "2b entities", "barrier"],
