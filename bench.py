@@ -300,7 +300,7 @@ def run_product(args):
     # ---- CPU baseline (rank 0, N=1 only): the reference itself on this box's host cores --------------
     cpu_train = cpu_eval = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_train, cpu_eval = reference_sample(train, valid, test, nE, nR, ent_eval, rel_eval, train_epochs=1, eval_triples=100)
+        cpu_train, cpu_eval = reference_sample(train, valid, test, nE, nR, ent_eval, rel_eval, train_epochs=5, eval_triples=800)  # ~10 s + ~10 s of CPU work
 
     ranking_flops = 2.0 * (2 * (hi - lo)) * nE * CFG["dim"]  # this rank's shard: the roofline is per GPU
     traffic = profile_traffic("train")
