@@ -28,7 +28,8 @@ namespace kb2e {
 namespace f32 {
 
 constexpr int QT = 32;         // queries per tile
-constexpr int THREADS = 256;   // one candidate per thread and step
+constexpr int THREADS = 256;
+constexpr int CPT = 2;         // candidates per thread and step
 
 // ---- operand preparation ---------------------------------------------------------------------------------
 // candidates: fp64 transposed [slot][D][ld] -> fp32, plus the slot's max |C|_1 and max |C|_2^2 (fp64, as ordered bits)
@@ -105,7 +106,7 @@ __global__ void prep_queries_kernel(const double* __restrict__ ct, const double*
 
 // ---- the all-candidates kernel -----------------------------------------------------------------------------
 // grid.x = query tiles (<= QT queries of one slot), grid.y = candidate splits.  The tile's w vectors sit in shared memory
-// as [D][QT] so that one 16-byte broadcast load feeds four running sums; each thread owns one candidate per step.
+// as [D][QT] so that one 16-byte broadcast load feeds four running sums per candidate; each thread owns CPT candidates per step.
 template <int L2>
 __global__ void __launch_bounds__(THREADS) rank_f32_kernel(const F32Args a) {
    extern __shared__ float s_w[];   // [D][QT]
@@ -127,49 +128,67 @@ __global__ void __launch_bounds__(THREADS) rank_f32_kernel(const F32Args a) {
       s_cnt[q] = 0;
    }
    __syncthreads();
-   const int steps = (a.nE + THREADS - 1) / THREADS;
+   // CPT candidates per thread and step: every 16-byte broadcast load of four query values then feeds 4 * CPT running
+   // sums.  With one candidate per thread the kernel was bound by the shared-memory pipe (8 LDS.128 per 64 FP32
+   // operations), not by FP32 issue.
+   const int steps = (a.nE + THREADS * CPT - 1) / (THREADS * CPT);
    const int s_begin = (int)((long long)steps * blockIdx.y / a.splits);
    const int s_end = (int)((long long)steps * (blockIdx.y + 1) / a.splits);
    int cnt[QT];
 #pragma unroll
    for (int q = 0; q < QT; q++) cnt[q] = 0;
    for (int step = s_begin; step < s_end; step++) {
-      const int c = step * THREADS + threadIdx.x;
-      const bool valid = c < a.nE;
-      const int cc = valid ? c : 0;
-      float acc[QT];
+      int c[CPT];
+      bool valid[CPT];
+      const float* col[CPT];
 #pragma unroll
-      for (int q = 0; q < QT; q++) acc[q] = 0.f;
+      for (int k = 0; k < CPT; k++) {
+         c[k] = (step * CPT + k) * THREADS + threadIdx.x;
+         valid[k] = c[k] < a.nE;
+         col[k] = ct + (valid[k] ? c[k] : 0);
+      }
+      float acc[CPT][QT];
+#pragma unroll
+      for (int k = 0; k < CPT; k++)
+#pragma unroll
+         for (int q = 0; q < QT; q++) acc[k][q] = 0.f;
 #pragma unroll 2
       for (int i = 0; i < D; i++) {
-         const float ci = __ldg(ct + (size_t)i * ld + cc);
+         float ci[CPT];
+#pragma unroll
+         for (int k = 0; k < CPT; k++) ci[k] = __ldg(col[k] + (size_t)i * ld);
          const float4* w4 = reinterpret_cast<const float4*>(s_w + i * QT);
 #pragma unroll
          for (int g = 0; g < QT / 4; g++) {
             const float4 w = w4[g];
-            if (L2) {
-               const float r0 = w.x - ci, r1 = w.y - ci, r2 = w.z - ci, r3 = w.w - ci;
-               acc[4 * g + 0] = fmaf(r0, r0, acc[4 * g + 0]);
-               acc[4 * g + 1] = fmaf(r1, r1, acc[4 * g + 1]);
-               acc[4 * g + 2] = fmaf(r2, r2, acc[4 * g + 2]);
-               acc[4 * g + 3] = fmaf(r3, r3, acc[4 * g + 3]);
-            } else {
-               acc[4 * g + 0] += fabsf(w.x - ci);
-               acc[4 * g + 1] += fabsf(w.y - ci);
-               acc[4 * g + 2] += fabsf(w.z - ci);
-               acc[4 * g + 3] += fabsf(w.w - ci);
+#pragma unroll
+            for (int k = 0; k < CPT; k++) {
+               if (L2) {
+                  const float r0 = w.x - ci[k], r1 = w.y - ci[k], r2 = w.z - ci[k], r3 = w.w - ci[k];
+                  acc[k][4 * g + 0] = fmaf(r0, r0, acc[k][4 * g + 0]);
+                  acc[k][4 * g + 1] = fmaf(r1, r1, acc[k][4 * g + 1]);
+                  acc[k][4 * g + 2] = fmaf(r2, r2, acc[k][4 * g + 2]);
+                  acc[k][4 * g + 3] = fmaf(r3, r3, acc[k][4 * g + 3]);
+               } else {
+                  acc[k][4 * g + 0] += fabsf(w.x - ci[k]);
+                  acc[k][4 * g + 1] += fabsf(w.y - ci[k]);
+                  acc[k][4 * g + 2] += fabsf(w.z - ci[k]);
+                  acc[k][4 * g + 3] += fabsf(w.w - ci[k]);
+               }
             }
          }
       }
-      if (valid) {
+#pragma unroll
+      for (int k = 0; k < CPT; k++) {
+         if (!valid[k]) continue;
 #pragma unroll
          for (int q = 0; q < QT; q++) {
-            const float s = acc[q];
+            const float s = acc[k][q];
             if (s < s_lo[q]) {
                cnt[q]++;
             } else if (s <= s_hi[q]) {
                const unsigned int slot = atomicAdd(a.band_count, 1u);
-               if (slot < a.band_cap) a.band[slot] = make_int2(q0 + q, c);
+               if (slot < a.band_cap) a.band[slot] = make_int2(q0 + q, c[k]);
                else a.band_count[1] = 1u;   // overflow: the caller redoes the call with the exact kernel
             }
          }
@@ -272,7 +291,7 @@ int f32_run(kb2e_ctx* c, F32State* s, bool l2, const double* ct, int ld, const i
    a.ct32 = s->ct32; a.wq = s->wq; a.thr_lo = s->thr_lo; a.thr_hi = s->thr_hi; a.tiles = tiles;
    a.q_less = q_cnt; a.band = s->band; a.band_count = s->band_count; a.band_cap = s->band_cap;
    a.nE = c->nE; a.D = c->D; a.ld = ld;
-   const int steps = (c->nE + f32::THREADS - 1) / f32::THREADS;
+   const int steps = (c->nE + f32::THREADS * f32::CPT - 1) / (f32::THREADS * f32::CPT);
    long long splits = std::max<long long>(1, (2ll * c->num_sms + ntiles - 1) / ntiles);
    splits = std::min<long long>(splits, steps);
    a.splits = (int)splits;

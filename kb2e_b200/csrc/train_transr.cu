@@ -55,40 +55,17 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Stage M (global, [D][P]) into sM ([D][pitch]); SUM: stage M + dM instead and zero dM (publish of a relation).
-template <bool SUM>
-__device__ __forceinline__ void stage_matrix(const RArgs& a, const float* M, float* dM, float* sM, int lane) {
+// Stage M (global, [D][P]) into sM ([D][pitch]) with asynchronous 16-byte copies; the caller waits
+// (cp_async_wait_all + __syncwarp) before reading.
+__device__ __forceinline__ void stage_matrix(const RArgs& a, const float* M, float* sM, int lane) {
    const int P4 = a.base.P >> 2;
    const int nF = a.base.D * P4;
-   if (!SUM) {
-      // asynchronous copies: the caller waits (cp_async_wait_all + __syncwarp) before reading
-      if (a.pitch == a.base.P) {
-         for (int f = lane; f < nF; f += 32) cp_async16(sM + 4 * f, M + 4 * (size_t)f);
-      } else {
-         for (int f = lane; f < nF; f += 32) {
-            const int j = (int)__umulhi((uint32_t)f, a.p4_magic);
-            cp_async16(sM + j * a.pitch + 4 * (f - j * P4), M + 4 * (size_t)f);
-         }
-      }
-      return;
-   }
-   constexpr int U = 4;
-   for (int f0 = lane; f0 < nF; f0 += 32 * U) {
-      float4 v[U], w[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-         const int f = f0 + 32 * u;
-         v[u] = f < nF ? ld_cg4(M + 4 * (size_t)f) : f4(0.f);
-         w[u] = f < nF ? ld_cg4(dM + 4 * (size_t)f) : f4(0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-         const int f = f0 + 32 * u;
-         if (f < nF) {
-            const int j = (int)__umulhi((uint32_t)f, a.p4_magic);
-            *reinterpret_cast<float4*>(sM + j * a.pitch + 4 * (f - j * P4)) = v[u] + w[u];
-            st_cg4(dM + 4 * (size_t)f, f4(0.f));
-         }
+   if (a.pitch == a.base.P) {
+      for (int f = lane; f < nF; f += 32) cp_async16(sM + 4 * f, M + 4 * (size_t)f);
+   } else {
+      for (int f = lane; f < nF; f += 32) {
+         const int j = (int)__umulhi((uint32_t)f, a.p4_magic);
+         cp_async16(sM + j * a.pitch + 4 * (f - j * P4), M + 4 * (size_t)f);
       }
    }
 }
@@ -155,7 +132,7 @@ __device__ __forceinline__ void transr_pair(const RArgs& ra, const Pair s, float
       cp_async16(sV + S_C * P + lane * 4, a.tab + (size_t)s.c * P + lane * 4);
       cp_async16(sV + S_R * P + lane * 4, a.tab + ((size_t)a.nE + s.r) * P + lane * 4);
    }
-   stage_matrix<false>(ra, M, nullptr, sM, lane);
+   stage_matrix(ra, M, sM, lane);
    cp_async_wait_all();
    __syncwarp();
    float y[3][NE];
@@ -355,7 +332,7 @@ __device__ __forceinline__ void transr_constraint(const RArgs& ra, int r, float*
    const float* M = a.w + (size_t)r * a.w_row;
    float* dM = a.dw + (size_t)r * a.w_row;
    float* sG = sV + S_GP * P;   // 6 * P4 floats (slots S_GP, S_GN): g10 g20 g21 g30 g31 g32 per chunk
-   stage_matrix<false>(ra, M, nullptr, sM, lane);
+   stage_matrix(ra, M, sM, lane);
    cp_async_wait_all();
    __syncwarp();
    bool have_gram = false;
