@@ -1,0 +1,3 @@
+set -x
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python -m pytest tests -m gpu -q 2>&1 | tail -2
