@@ -128,20 +128,23 @@ __global__ void project_transr_kernel(const double* __restrict__ ct0, const doub
    int c = blockIdx.x * blockDim.x + threadIdx.x;
    if (c >= nE) return;
    double* out = pt + (size_t)slot * D * ld;
-   for (int i0 = 0; i0 < D; i0 += 4) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+   // eight output dims per pass over j: one (L1-cached) load of e_j feeds eight multiply-adds; every output is still the
+   // plain left-to-right sum over j, so the values are bit-identical to the reference's
+   constexpr int W = 8;
+   for (int i0 = 0; i0 < D; i0 += W) {
+      double acc[W];
+#pragma unroll
+      for (int k = 0; k < W; k++) acc[k] = 0.0;
       for (int j = 0; j < D; j++) {
-         double e = ct0[(size_t)j * ld + c];
+         const double e = ct0[(size_t)j * ld + c];
          const double* m = sM + j * D + i0;
-         a0 = __dadd_rn(a0, __dmul_rn(m[0], e));
-         if (i0 + 1 < D) a1 = __dadd_rn(a1, __dmul_rn(m[1], e));
-         if (i0 + 2 < D) a2 = __dadd_rn(a2, __dmul_rn(m[2], e));
-         if (i0 + 3 < D) a3 = __dadd_rn(a3, __dmul_rn(m[3], e));
+#pragma unroll
+         for (int k = 0; k < W; k++)
+            if (i0 + k < D) acc[k] = __dadd_rn(acc[k], __dmul_rn(m[k], e));
       }
-      out[(size_t)i0 * ld + c] = a0;
-      if (i0 + 1 < D) out[(size_t)(i0 + 1) * ld + c] = a1;
-      if (i0 + 2 < D) out[(size_t)(i0 + 2) * ld + c] = a2;
-      if (i0 + 3 < D) out[(size_t)(i0 + 3) * ld + c] = a3;
+#pragma unroll
+      for (int k = 0; k < W; k++)
+         if (i0 + k < D) out[(size_t)(i0 + k) * ld + c] = acc[k];
    }
 }
 
