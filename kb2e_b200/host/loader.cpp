@@ -2,6 +2,9 @@
 
 #include <sys/stat.h>
 
+#include <algorithm>
+#include <charconv>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -89,12 +92,26 @@ bool loadTripleFile(const std::string& path, const IdMap& entityIdMap, const IdM
    return true;
 }
 
+// Embedding tables are the bulk of the text the programs read and write (FB15k shape, size 100: 1.6 M numbers per
+// file).  std::from_chars / std::to_chars are correctly rounded like strtod / printf -- the same doubles in, the same
+// bytes out ("%.6lf\t" cells, common/trainer.cpp:113) -- at a fraction of the cost; anything they do not take
+// (hex floats, inf / nan spellings, values too long for the cell buffer) goes through the C library as before.
 bool loadTable(const std::string& path, size_t rows, size_t cols, std::vector<double>& out) {
    std::string text;
    if (!slurp(path, text)) return false;
    out.resize(rows * cols);
    const char* p = text.c_str();
+   const char* end = p + text.size();
    for (size_t i = 0; i < rows * cols; i++) {
+      while (p < end && isSpace(*p)) p++;
+      const char* q = (p < end && *p == '+') ? p + 1 : p;   // strtod takes a leading '+', from_chars does not
+      double v = 0.0;
+      std::from_chars_result r = std::from_chars(q, end, v);
+      if (r.ec == std::errc() && r.ptr != q && !(r.ptr < end && (*r.ptr == 'x' || *r.ptr == 'X'))) {
+         out[i] = v;
+         p = r.ptr;
+         continue;
+      }
       char* stop = NULL;
       out[i] = strtod(p, &stop);  // same conversion fscanf("%lf") performs
       if (stop == p) return false;
@@ -106,12 +123,24 @@ bool loadTable(const std::string& path, size_t rows, size_t cols, std::vector<do
 bool writeTable(const std::string& path, size_t rows, size_t cols, const double* data) {
    FILE* f = fopen(path.c_str(), "w");
    if (!f) return false;
-   std::vector<char> line(cols * 32 + 2);
+   std::string line;
+   char cell[400];
    for (size_t i = 0; i < rows; i++) {
-      size_t at = 0;
-      for (size_t j = 0; j < cols; j++) at += (size_t)snprintf(&line[at], 32, "%.6lf\t", data[i * cols + j]);
-      line[at++] = '\n';
-      fwrite(line.data(), 1, at, f);
+      line.clear();
+      for (size_t j = 0; j < cols; j++) {
+         const double v = data[i * cols + j];
+         std::to_chars_result r{cell, std::errc::value_too_large};
+         if (std::isfinite(v)) r = std::to_chars(cell, cell + sizeof(cell), v, std::chars_format::fixed, 6);
+         if (r.ec == std::errc()) {
+            line.append(cell, (size_t)(r.ptr - cell));
+         } else {
+            int n = snprintf(cell, sizeof(cell), "%.6lf", v);
+            line.append(cell, (size_t)std::min<int>(n, (int)sizeof(cell) - 1));
+         }
+         line.push_back('\t');
+      }
+      line.push_back('\n');
+      fwrite(line.data(), 1, line.size(), f);
    }
    fclose(f);
    return true;
