@@ -846,11 +846,13 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    } else if (lazy) {
       int rc = train_lazy_launch(c, a, lazy_lps, lazy_nv, &threads);
       if (rc) return rc;
-   } else if (fused) {
-      int rc = train_fused_launch(c, a, lps, nv, threads);
-      if (rc) return rc;
    } else {
-      KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(threads), params, 0, c->stream));
+      int rc = fused ? train_fused_launch(c, a, lps, nv, threads) : KB2E_ERR_LIMIT;
+      if (rc == KB2E_ERR_LIMIT) {   // not a small batch, or no fused instantiation for this shape: the two-barrier kernel
+         KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(threads), params, 0, c->stream));
+      } else if (rc) {
+         return rc;
+      }
    }
    KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
    std::vector<double> loss(n_epochs);

@@ -232,6 +232,7 @@ bool train_fused_wanted(const kb2e_ctx* c, long long batchsize, int lps, int thr
    const char* env = getenv("KB2E_TRAIN_FUSED");   // 0: never, 1: whenever a batch fits in one pass (tuning aid)
    if (env && atoi(env) == 0) return false;
    if (c->cfg.model != KB2E_MODEL_TRANSE) return false;
+   if (threads != 1024 && threads != 768 && threads != 512) return false;   // KB2E_TRAIN_THREADS override without an instantiation
    const long long groups = (long long)c->num_sms * (threads / lps);
    if (env && atoi(env) == 1) return batchsize <= groups;
    return 2 * batchsize <= groups;
@@ -250,7 +251,7 @@ int train_fused_launch(kb2e_ctx* c, const TrainArgs& base, int lps, int nv, int 
    KB2E_FUSED(8, 2, 768) KB2E_FUSED(16, 2, 768) KB2E_FUSED(32, 2, 768)
    KB2E_FUSED(8, 4, 512) KB2E_FUSED(16, 4, 512) KB2E_FUSED(32, 4, 512)
 #undef KB2E_FUSED
-   if (!k) return fail(c, KB2E_ERR_LIMIT, "no fused training kernel for this shape");
+   if (!k) return KB2E_ERR_LIMIT;   // no instantiation for this (lanes, vectors, threads): the caller falls back to train_kernel
    void* params[] = {&a};
    KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(threads), params, 0, c->stream));
    return KB2E_OK;
