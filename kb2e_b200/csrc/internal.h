@@ -10,7 +10,7 @@
 #include "../../include/kb2e_b200.h"
 
 struct DistState;
-namespace kb2e { struct LazyBuffers; struct TrainArgs; }
+namespace kb2e { struct TrainArgs; }
 
 struct kb2e_ctx {
    kb2e_config cfg;
@@ -70,7 +70,6 @@ struct kb2e_ctx {
    bool filter_dirty = true;
    struct RankState* rank = nullptr;
    DistState* dist = nullptr;  // entity-partitioned multi-GPU training (train_dist.cu)
-   kb2e::LazyBuffers* lazy = nullptr;  // second value buffer, extra delta buffers, stamps (train_lazy.cu)
    uint32_t* pend = nullptr;           // [3][nE + nR] per-row reference counters of the one-barrier kernel (train_fused.cu)
    kb2e_rank_stats rstats{};
 };
@@ -112,11 +111,6 @@ int narrow_table(kb2e_ctx* ctx, int table);   // fp64 -> fp32
 int ensure32(kb2e_ctx* ctx);                  // every table of the model current in fp32 (training)
 int ensure64(kb2e_ctx* ctx);                  // ... in fp64 (ranking)
 double* table64(kb2e_ctx* ctx, int table);
-
-// train_lazy.cu
-bool train_lazy_wanted(const kb2e_ctx* ctx, long long batchsize, int lps, int nv);
-int train_lazy_launch(kb2e_ctx* ctx, const TrainArgs& base, int lps, int nv, int* threads_out);
-void train_lazy_free(kb2e_ctx* ctx);
 
 // train_fused.cu
 bool train_fused_wanted(const kb2e_ctx* ctx, long long batchsize, int lps, int threads);

@@ -576,7 +576,6 @@ void train_free(kb2e_ctx* c) {
    pool_free(c, c->barrier); pool_free(c, c->loss_dev); pool_free(c, c->counters); pool_free(c, c->pairs_dev);
    pool_free(c, c->ent64); pool_free(c, c->rel64); pool_free(c, c->w64);
    pool_free(c, c->pend);
-   train_lazy_free(c);
 }
 
 int train_set_triples(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t* r, int64_t n) {
@@ -817,13 +816,9 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
       k = pick_kernel<KB2E_MODEL_TRANSH>(lps, nv, threads);
    }
    if (!k && !transr) return fail(c, KB2E_ERR_LIMIT, "no training kernel for this embedding size");
-   // small batches (FB15k / WN18 shape): one barrier per batch instead of two (train_lazy.cu)
-   int lazy_lps = lps, lazy_nv = nv;
-   if (c->cfg.model == KB2E_MODEL_TRANSE && nv == 1 && lps == 32 && c->P <= 64) { lazy_lps = 16; }
-   const bool lazy = train_lazy_wanted(c, a.batchsize, lazy_lps, lazy_nv);
-   // ... or, for batches that need at most half of the resident groups, fold every row where its last sample
-   // finishes (train_fused.cu)
-   const bool fused = !lazy && !transr && train_fused_wanted(c, a.batchsize, lps, threads);
+   // batches that need at most half of the resident groups: one barrier per batch, every row folded where its last
+   // sample finishes (train_fused.cu)
+   const bool fused = !transr && train_fused_wanted(c, a.batchsize, lps, threads);
    if (!transr) {
       int per_sm = 0;
       KB2E_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0));
@@ -831,7 +826,7 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    }
    KB2E_CUDA(c, cudaMemsetAsync(c->barrier, 0, 64, c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->loss_dev, 0, (size_t)n_epochs * sizeof(double), c->stream));
-   const char* trace_path = lazy ? nullptr : getenv("KB2E_TRAIN_TRACE");
+   const char* trace_path = getenv("KB2E_TRAIN_TRACE");
    unsigned long long* trace_dev = nullptr;
    if (trace_path) {
       KB2E_CUDA(c, pool_alloc(c, &trace_dev, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long)));
@@ -842,9 +837,6 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
    if (transr) {
       int rc = train_transr_launch(c, a, &threads);
-      if (rc) return rc;
-   } else if (lazy) {
-      int rc = train_lazy_launch(c, a, lazy_lps, lazy_nv, &threads);
       if (rc) return rc;
    } else {
       int rc = fused ? train_fused_launch(c, a, lps, nv, threads) : KB2E_ERR_LIMIT;
