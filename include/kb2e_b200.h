@@ -21,7 +21,9 @@
  *   kb2e_add_filter_triples         EmbeddingEvaluation::loadTriples / add (common/evaluation.cpp:41-72)
  *   kb2e_rank                       EmbeddingEvaluation::run + evalCorruption (common/evaluation.cpp:124-251)
  *   kb2e_sample_batch,
- *   kb2e_train_batch_pairs          test hooks onto the sampler and onto one batch of train_kb calls
+ *   kb2e_train_batch_pairs,
+ *   kb2e_train_batch_deltas         test hooks onto the sampler, onto one batch of train_kb calls, and onto the
+ *                                   accumulation half of gradientUpdate alone
  *
  * Threading: one context per host thread; a context owns one CUDA device, its own stream and all
  * device memory.  Multi-GPU = one process (context) per GPU; ranks shard queries through
@@ -58,6 +60,10 @@ extern "C" {
 /* flags */
 #define KB2E_FLAG_RANK_EXACT_ONLY 1u /* rank with the exact fp64 kernel only (no fp32 / tensor-core pre-filter) */
 #define KB2E_FLAG_TRANSR_NO_QUIRK 2u /* do not replicate transr/trainer.cpp:187 (constraint on entity[relation]) */
+/* Sampler indices with the DISTRIBUTION of the reference's randMax (common/utils.cpp:113-120: the wrapped 32-bit
+ * product of two rand() values modulo x -- e.g. 75 % even indices) instead of uniform ones; still the counter RNG.
+ * For trained-model parity with the shipped reference; needs n_train < 2^31. */
+#define KB2E_FLAG_SAMPLER_RANDMAX 4u
 
 typedef struct kb2e_ctx kb2e_ctx;
 
@@ -92,6 +98,8 @@ typedef struct kb2e_rank_stats {
    uint64_t launches;
    double kernel_ms;      /* CUDA-event time of all ranking kernels */
    double main_kernel_ms; /* of which: the all-candidates scoring kernel(s) */
+   double project_ms;        /* TransR: operand preparation + tensor-core projection, all passes */
+   double project_kernel_ms; /* TransR: the tensor-core projection kernel alone (last pass of each call) */
 } kb2e_rank_stats;
 
 int kb2e_create(const kb2e_config* cfg, kb2e_ctx** out);
@@ -157,6 +165,17 @@ void kb2e_dist_teardown(kb2e_ctx* ctx);
 int kb2e_sample_batch(kb2e_ctx* ctx, int32_t epoch, int32_t batch, int64_t count, int32_t* pairs_out);
 /* One batch made of the given (pos, neg) pairs instead of sampled ones, through the same kernel. */
 int kb2e_train_batch_pairs(kb2e_ctx* ctx, const int32_t* pairs, int64_t n, double* loss, int64_t* n_active);
+/* The same pairs through the same kernel, stopped after the accumulation phase: returns the summed PRE-normalisation
+ * updates -- what <model>::Trainer::gradientUpdate adds to *_next_ before its norm() calls (transe/trainer.cpp:37-41,
+ * transh/trainer.cpp:25-45, transr/trainer.cpp:158-172) -- as [num_entities][dim], [num_relations][dim] and the
+ * KB2E_TABLE_WEIGHTS shape (any may be NULL).  The tables themselves are left untouched. */
+int kb2e_train_batch_deltas(kb2e_ctx* ctx, const int32_t* pairs, int64_t n, double* d_entity, double* d_relation,
+                            double* d_weights, double* loss, int64_t* n_active);
+
+/* TransR: the tensor-core (bf16 hi/lo split, fp32 accumulate) projection M_r^T e of every entity under `relation` as
+ * the ranking pre-filter computes it, proj[num_entities][dim], and the relative error bound the ranking assumes for it:
+ * |proj[c][i] - exact| <= *eps_rel * sum_j |e_cj| |M_r[j][i]| (transr/transr.cpp:20-25 is the exact form). */
+int kb2e_debug_transr_projection(kb2e_ctx* ctx, int32_t relation, float* proj, double* eps_rel);
 
 #ifdef __cplusplus
 }

@@ -11,12 +11,13 @@ MODELS = {"transe": 0, "transh": 1, "transr": 2}
 TABLE_ENTITY, TABLE_RELATION, TABLE_WEIGHTS = 0, 1, 2
 FLAG_RANK_EXACT_ONLY = 1
 FLAG_TRANSR_NO_QUIRK = 2
+FLAG_SAMPLER_RANDMAX = 4
 
 SYMBOLS = [
     "kb2e_create", "kb2e_destroy", "kb2e_last_error", "kb2e_stream", "kb2e_set_train_triples", "kb2e_set_bern",
     "kb2e_init_embeddings", "kb2e_upload", "kb2e_download", "kb2e_train_epochs", "kb2e_get_train_stats",
     "kb2e_score", "kb2e_set_test_triples", "kb2e_add_filter_triples", "kb2e_rank", "kb2e_get_rank_stats",
-    "kb2e_sample_batch", "kb2e_train_batch_pairs",
+    "kb2e_sample_batch", "kb2e_train_batch_pairs", "kb2e_train_batch_deltas", "kb2e_debug_transr_projection",
     "kb2e_dist_setup", "kb2e_dist_connect", "kb2e_dist_init_embeddings", "kb2e_dist_upload", "kb2e_dist_download",
     "kb2e_dist_train_epochs", "kb2e_dist_teardown",
 ]
@@ -40,7 +41,8 @@ class TrainStats(C.Structure):
 
 class RankStats(C.Structure):
     _fields_ = [("queries", C.c_uint64), ("rechecked", C.c_uint64), ("launches", C.c_uint64),
-                ("kernel_ms", C.c_double), ("main_kernel_ms", C.c_double)]
+                ("kernel_ms", C.c_double), ("main_kernel_ms", C.c_double), ("project_ms", C.c_double),
+                ("project_kernel_ms", C.c_double)]
 
 
 _lib = None
@@ -229,6 +231,26 @@ class Context:
                                                     C.byref(active)), "kb2e_train_batch_pairs")
         return loss.value, active.value
 
+    def debug_transr_projection(self, relation):
+        """(tensor-core projection of every entity under `relation` [nE][dim] float32, relative error bound)."""
+        out = np.empty((self.nE, self.dim), dtype=np.float32)
+        eps = C.c_double(0)
+        self._check(self.lib.kb2e_debug_transr_projection(self.ptr, int(relation), _p(out, C.c_float), C.byref(eps)),
+                    "kb2e_debug_transr_projection")
+        return out, eps.value
+
+    def train_batch_deltas(self, pairs):
+        """The summed pre-normalisation updates of the pairs (tables untouched): (d_ent, d_rel, d_w, loss, n_active)."""
+        p = _i32(pairs).reshape(-1, 6)
+        de = np.zeros((self.nE, self.dim), dtype=np.float64)
+        dr = np.zeros((self.nR, self.dim), dtype=np.float64)
+        dw = np.zeros(self.table_shape(TABLE_WEIGHTS), dtype=np.float64) if self.model != 0 else None
+        loss = C.c_double(0)
+        active = C.c_int64(0)
+        self._check(self.lib.kb2e_train_batch_deltas(self.ptr, _p(p, C.c_int32), C.c_int64(len(p)), _p(de, C.c_double),
+                                                     _p(dr, C.c_double), _p(dw, C.c_double), C.byref(loss), C.byref(active)),
+                    "kb2e_train_batch_deltas")
+        return de, dr, dw, loss.value, active.value
 
     # ---- entity-partitioned multi-GPU training (one Context per process per GPU) ----
     def dist_setup(self, rank, world):

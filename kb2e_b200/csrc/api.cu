@@ -264,6 +264,12 @@ int kb2e_rank(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int3
    return rank_run(c, first, count, raw_rank, filt_rank, raw_ties, filt_ties, sums);
 }
 
+int kb2e_debug_transr_projection(kb2e_ctx* c, int32_t relation, float* proj, double* eps_rel) {
+   KB2E_ENTER(c);
+   if (!proj) return fail(c, KB2E_ERR_ARG, "kb2e_debug_transr_projection: null buffer");
+   return rank_debug_transr_projection(c, relation, proj, eps_rel);
+}
+
 int kb2e_sample_batch(kb2e_ctx* c, int32_t epoch, int32_t batch, int64_t count, int32_t* pairs_out) {
    KB2E_ENTER(c);
    if (count <= 0 || !pairs_out) return fail(c, KB2E_ERR_ARG, "kb2e_sample_batch: bad arguments");
@@ -279,9 +285,8 @@ int kb2e_sample_batch(kb2e_ctx* c, int32_t epoch, int32_t batch, int64_t count, 
    return rc;
 }
 
-int kb2e_train_batch_pairs(kb2e_ctx* c, const int32_t* pairs, int64_t n, double* loss, int64_t* n_active) {
-   KB2E_ENTER(c);
-   if (n <= 0 || !pairs) return fail(c, KB2E_ERR_ARG, "kb2e_train_batch_pairs: bad arguments");
+static int stage_pairs(kb2e_ctx* c, const char* who, const int32_t* pairs, int64_t n) {
+   if (n <= 0 || !pairs) return fail(c, KB2E_ERR_ARG, std::string(who) + ": bad arguments");
    for (int64_t i = 0; i < n; i++) {
       const int32_t* p = pairs + 6 * i;
       if (p[0] < 0 || p[0] >= c->nE || p[1] < 0 || p[1] >= c->nE || p[3] < 0 || p[3] >= c->nE || p[4] < 0 || p[4] >= c->nE ||
@@ -293,16 +298,40 @@ int kb2e_train_batch_pairs(kb2e_ctx* c, const int32_t* pairs, int64_t n, double*
    if (n > c->pairs_cap) {
       pool_free(c, c->pairs_dev);
       c->pairs_dev = nullptr;
+      c->pairs_cap = 0;
       KB2E_CUDA(c, pool_alloc(c, &c->pairs_dev, 6 * (size_t)n * sizeof(int32_t)));
       c->pairs_cap = n;
    }
    KB2E_CUDA(c, cudaMemcpyAsync(c->pairs_dev, pairs, 6 * (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+   return KB2E_OK;
+}
+
+int kb2e_train_batch_pairs(kb2e_ctx* c, const int32_t* pairs, int64_t n, double* loss, int64_t* n_active) {
+   KB2E_ENTER(c);
+   int rc = stage_pairs(c, "kb2e_train_batch_pairs", pairs, n);
+   if (rc) return rc;
    const uint64_t before = c->tstats.active;
    double l = 0.0;
-   // each hooked batch advances the global batch counter so the relation-flag parity alternates
    rc = train_run(c, c->hook_batches, 1, c->pairs_dev, n, &l);
    if (rc) return rc;
    c->hook_batches++;
+   if (loss) *loss = l;
+   if (n_active) *n_active = (int64_t)(c->tstats.active - before);
+   return KB2E_OK;
+}
+
+int kb2e_train_batch_deltas(kb2e_ctx* c, const int32_t* pairs, int64_t n, double* d_entity, double* d_relation, double* d_weights,
+                            double* loss, int64_t* n_active) {
+   KB2E_ENTER(c);
+   int rc = stage_pairs(c, "kb2e_train_batch_deltas", pairs, n);
+   if (rc) return rc;
+   const uint64_t before = c->tstats.active;
+   double l = 0.0;
+   rc = train_run(c, c->hook_batches, 1, c->pairs_dev, n, &l, /*phase1_only=*/true);
+   if (rc) return rc;
+   c->hook_batches++;
+   rc = train_take_deltas(c, d_entity, d_relation, d_weights);
+   if (rc) return rc;
    if (loss) *loss = l;
    if (n_active) *n_active = (int64_t)(c->tstats.active - before);
    return KB2E_OK;

@@ -32,7 +32,7 @@ struct kb2e_ctx {
    float* w = nullptr;
    float* dw = nullptr;
    size_t w_row = 0;           // elements per relation in w
-   uint8_t* flag = nullptr;    // [nE + nR] row touched in the current batch
+   uint32_t* flag = nullptr;   // [nE + nR] stamp (global batch + 1) of the last batch that touched the row
    int* rmin = nullptr;        // [nE] lowest / highest relation id that touched the entity row (TransH/R)
    int* rmax = nullptr;
    bool v32[3] = {false, false, false};  // per table (entity, relation, weights): fp32 copy is current
@@ -55,7 +55,8 @@ struct kb2e_ctx {
    unsigned long long* counters = nullptr;  // [0] active [1] touched_ent [2] touched_rel
    int32_t* pairs_dev = nullptr;
    int64_t pairs_cap = 0;
-   int hook_batches = 0;      // batches run through kb2e_train_batch_pairs (keeps flag parity alternating)
+   int hook_batches = 0;      // batches run through kb2e_train_batch_pairs (each gets its own sampler / global-batch index)
+   uint32_t stamp_base = 0;   // batches launched so far: row stamps of a launch are stamp_base + 1 ... (never reused)
    kb2e_train_stats tstats{};
 
    // ---- fp64 tables for ranking (exact copies of what was uploaded, or widened fp32 state) -----
@@ -102,7 +103,9 @@ int train_alloc(kb2e_ctx* ctx);
 void train_free(kb2e_ctx* ctx);
 int train_set_triples(kb2e_ctx* ctx, const int32_t* h, const int32_t* t, const int32_t* r, int64_t n);
 int train_init_embeddings(kb2e_ctx* ctx);
-int train_run(kb2e_ctx* ctx, int first_epoch, int n_epochs, const int32_t* pairs_dev, int64_t n_pairs, double* loss_out);
+int train_run(kb2e_ctx* ctx, int first_epoch, int n_epochs, const int32_t* pairs_dev, int64_t n_pairs, double* loss_out,
+              bool phase1_only = false);
+int train_take_deltas(kb2e_ctx* ctx, double* d_ent, double* d_rel, double* d_w);
 int train_sample(kb2e_ctx* ctx, int epoch, int batch, int64_t count, int32_t* pairs_dev);
 int train_score32(kb2e_ctx* ctx, const int32_t* h_dev, const int32_t* t_dev, const int32_t* r_dev, int64_t n, double* out_dev);
 int num_tables(const kb2e_ctx* ctx);
@@ -124,5 +127,6 @@ int rank_run(kb2e_ctx* ctx, int64_t first, int64_t count, int32_t* raw_rank, int
              int32_t* raw_ties, int32_t* filt_ties, int64_t sums[4]);
 int rank_score64(kb2e_ctx* ctx, const int32_t* h_dev, const int32_t* t_dev, const int32_t* r_dev, int64_t n, double* out_dev);
 void rank_free(kb2e_ctx* ctx);
+int rank_debug_transr_projection(kb2e_ctx* ctx, int relation, float* out, double* eps_rel);
 
 }  // namespace kb2e

@@ -39,6 +39,7 @@
 #include "internal.h"
 #include "rank_f32.h"
 #include "rank_tc.h"
+#include "rank_transr.h"
 
 struct RankState {
    // filter set as a hashed CSR, built on the device: entries sorted by (segment key, neighbour);
@@ -78,6 +79,7 @@ struct RankState {
           cap_val_tmp = 0, cap_cub_tmp = 0, cap_chunks = 0;
    kb2e::TcState tc;
    kb2e::F32State f32;
+   kb2e::TrpState trp;
 };
 
 namespace kb2e {
@@ -682,6 +684,8 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    const bool use_tc = tc_supported(c);
    // every other model / distance: fp32 CUDA-core pre-filter + exact recheck (rank_f32.cu) unless the exact kernel is forced
    const bool use_f32 = !use_tc && !(c->cfg.flags & KB2E_FLAG_RANK_EXACT_ONLY);
+   // TransR: candidates projected by the tensor cores (fp32, bounded error), exact projections only on demand (rank_transr.cu)
+   const bool use_trp = use_f32 && trp_supported(c);
    const int tile_q = use_f32 ? kF32QueriesPerTile : kQT;
 
    rc = ensure_query_buffers(c, nq);
@@ -708,7 +712,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       std::iota(order.begin(), order.end(), first);
       std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return c->test_r[x] < c->test_r[y]; });
       // slots per pass bounded by a memory budget for the projected matrices
-      const size_t slot_bytes = (size_t)c->D * s->ld * sizeof(double);
+      const size_t slot_bytes = (size_t)c->D * s->ld * (use_trp ? sizeof(float) : sizeof(double));
       const size_t budget = (size_t)16 << 30;
       const size_t max_slots = std::max<size_t>(1, budget / slot_bytes);
       // query arrays (SoA, nq each): fixed entity, true answer, relation, side, slot, original index
@@ -797,6 +801,15 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       KB2E_CUDA(c, cudaEventCreate(&e));
       s->pass_ev.push_back(e);
    }
+   if (use_trp) {
+      rc = trp_prepare_entities(c, &s->trp);
+      if (rc) return rc;
+      while (s->pass_ev.size() < 4 * passes.size()) {   // + two per pass around the tensor-core projection
+         cudaEvent_t e;
+         KB2E_CUDA(c, cudaEventCreate(&e));
+         s->pass_ev.push_back(e);
+      }
+   }
    lap("tensor-core operand prep");
    bool f32_started = false;
    // Everything below is enqueued without a host wait; the one synchronisation is at the end of the call.
@@ -805,7 +818,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       const Pass& ps = passes[p];
       const long long pq = ps.q_end - ps.q_begin;
       if (pq == 0) continue;
-      if (per_rel) {
+      if (per_rel && !use_trp) {
          rc = project(c, ps.rels);
          if (rc) return rc;
          a.ct = s->pt;
@@ -815,9 +828,29 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       a.tiles = s->tiles + ps.tile_begin;
       a.q_begin = ps.q_begin;
       a.q_end = ps.q_end;
-      if (l2) etrue_kernel<1><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
+      if (use_trp) {
+         const unsigned ntiles = (unsigned)(ps.tile_end - ps.tile_begin);
+         rc = f32_ensure(c, &s->f32, ps.rels.size(), s->ld, nq, !f32_started);
+         f32_started = true;
+         if (rc) return rc;
+         KB2E_CUDA(c, cudaEventRecord(s->pass_ev[2 * passes.size() + 2 * p], c->stream));
+         rc = trp_project(c, &s->trp, ps.rels, s->ld, s->f32.ct32);                               // tcgen05: P_r = E M_r, all slots
+         if (rc) return rc;
+         KB2E_CUDA(c, cudaEventRecord(s->pass_ev[2 * passes.size() + 2 * p + 1], c->stream));
+         rc = trp_queries(c, &s->trp, l2, s->q_int, nq, ps.q_begin, ps.q_end, s->q_etrue);         // exact V[q], E_true[q]
+         if (rc) return rc;
+         rc = trp_thresholds(c, &s->trp, &s->f32, l2, s->q_int, nq, ps.q_begin, ps.q_end, s->q_etrue);
+         if (rc) return rc;
+         rc = f32_main(c, &s->f32, l2, s->ld, a.tiles, ntiles, s->q_cnt, s->pass_ev[2 * p], s->pass_ev[2 * p + 1]);
+         if (rc) return rc;
+         rc = trp_recheck(c, &s->trp, &s->f32, l2, s->q_int, nq, s->q_etrue, s->q_cnt);
+         if (rc) return rc;
+         c->rstats.launches += 6;
+      } else if (l2) etrue_kernel<1><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
       else etrue_kernel<0><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
-      if (use_tc) {
+      if (use_trp) {
+         // scored above
+      } else if (use_tc) {
          // tensor-core pre-filter + exact recheck of the undecided band (rank_tc.cu)
          rc = tc_run(c, &s->tc, a.q_fixed + ps.q_begin, a.q_rel + ps.q_begin, a.q_side + ps.q_begin, a.q_etrue + ps.q_begin,
                      pq, s->q_cnt + ps.q_begin);
@@ -854,7 +887,10 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
          KB2E_CUDA(c, cudaMemsetAsync(s->chunk_count, 0, sizeof(unsigned int), c->stream));
          filter_plan_kernel<<<nblk(pq, 256), 256, 0, c->stream>>>(a, s->seg_end, s->chunks, s->chunk_count, s->chunk_cap);
          const unsigned fb = 8 * c->num_sms;   // persistent: 8 x 256 threads per SM, one chunk per warp at a time
-         if (per_rel) {
+         if (use_trp) {
+            rc = trp_filter(c, &s->trp, l2, s->q_int, nq, s->q_etrue, s->nbr, s->chunks, s->chunk_count, s->chunk_cap, s->q_cnt);
+            if (rc) return rc;
+         } else if (per_rel) {
             if (l2) filter_pairs_kernel<1, false><<<fb, 256, 0, c->stream>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
             else filter_pairs_kernel<0, false><<<fb, 256, 0, c->stream>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
          } else {
@@ -907,6 +943,15 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
          float pms = 0.f;
          KB2E_CUDA(c, cudaEventElapsedTime(&pms, s->pass_ev[2 * p], s->pass_ev[2 * p + 1]));
          c->rstats.main_kernel_ms += pms;
+         if (use_trp) {
+            // operand preparation + tensor-core projection of every pass; the projection kernel alone for the last pass
+            KB2E_CUDA(c, cudaEventElapsedTime(&pms, s->pass_ev[2 * passes.size() + 2 * p], s->pass_ev[2 * passes.size() + 2 * p + 1]));
+            c->rstats.project_ms += pms;
+            if (p + 1 == passes.size()) {
+               KB2E_CUDA(c, cudaEventElapsedTime(&pms, s->trp.e0, s->trp.e1));
+               c->rstats.project_kernel_ms += pms;
+            }
+         }
       }
    }
    float ms = 0.f;
@@ -940,6 +985,16 @@ int rank_score64(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t*
    return KB2E_OK;
 }
 
+int rank_debug_transr_projection(kb2e_ctx* c, int relation, float* out, double* eps_rel) {
+   if (c->cfg.model != KB2E_MODEL_TRANSR || c->D > 128) return fail(c, KB2E_ERR_ARG, "TransR with an embedding size up to 128 only");
+   if (relation < 0 || relation >= c->nR) return fail(c, KB2E_ERR_ARG, "relation out of range");
+   int rc = ensure_state(c);
+   if (rc) return rc;
+   rc = ensure64(c);
+   if (rc) return rc;
+   return trp_debug_project(c, &c->rank->trp, relation, out, eps_rel);
+}
+
 void rank_free(kb2e_ctx* c) {
    RankState* s = c->rank;
    if (!s) return;
@@ -952,6 +1007,7 @@ void rank_free(kb2e_ctx* c) {
    pool_free(c, s->ids);
    tc_free(c, &s->tc);
    f32_free(c, &s->f32);
+   trp_free(c, &s->trp);
    delete s;
    c->rank = nullptr;
 }

@@ -237,7 +237,8 @@ __global__ void recheck_ct_kernel(const int2* __restrict__ band, const unsigned 
 // ---- host ------------------------------------------------------------------------------------------------
 static inline unsigned nblk3(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
-int f32_prepare(kb2e_ctx* c, F32State* s, const double* ct, size_t slots, int ld, long long nq, bool first_pass) {
+// Buffers only (grow-only): the fp32 candidate matrices of `slots` slots, the per-slot maxima and the per-query arrays.
+int f32_ensure(kb2e_ctx* c, F32State* s, size_t slots, int ld, long long nq, bool first_pass) {
    const size_t need_ct = slots * (size_t)c->D * ld;
    if (need_ct > s->ct32_cap) {
       pool_free(c, s->ct32);
@@ -266,27 +267,21 @@ int f32_prepare(kb2e_ctx* c, F32State* s, const double* ct, size_t slots, int ld
       KB2E_CUDA(c, cudaMallocHost(&s->host_count, 4 * sizeof(unsigned int)));
    }
    if (first_pass) KB2E_CUDA(c, cudaMemsetAsync(s->band_count, 0, 4 * sizeof(unsigned int), c->stream));   // overflow flag, call total
+   return KB2E_OK;
+}
+
+int f32_prepare(kb2e_ctx* c, F32State* s, const double* ct, size_t slots, int ld, long long nq, bool first_pass) {
+   int rc = f32_ensure(c, s, slots, ld, nq, first_pass);
+   if (rc) return rc;
    KB2E_CUDA(c, cudaMemsetAsync(s->slot_max, 0, slots * 2 * sizeof(unsigned long long), c->stream));
    f32::prep_candidates_kernel<<<dim3(nblk3(ld, 256), (unsigned)slots), 256, 0, c->stream>>>(ct, s->ct32, c->nE, c->D, ld, s->slot_max);
    KB2E_CUDA(c, cudaGetLastError());
    return KB2E_OK;
 }
 
-int f32_run(kb2e_ctx* c, F32State* s, bool l2, const double* ct, int ld, const int32_t* q_int, long long nq_total, const double* q_etrue,
-            long long q_begin, long long q_end, const int4* tiles, unsigned ntiles, int32_t* q_cnt, cudaEvent_t e0, cudaEvent_t e1) {
-   const int32_t* q_fixed = q_int;
-   const int32_t* q_truth = q_int + nq_total;
-   const int32_t* q_rel = q_int + 2 * nq_total;
-   const int32_t* q_side = q_int + 3 * nq_total;
-   const int32_t* q_slot = q_int + 4 * nq_total;
-   const long long pq = q_end - q_begin;
+// The all-candidates kernel alone, on s->ct32 / s->wq / s->thr_* as they stand (band list reset first).
+int f32_main(kb2e_ctx* c, F32State* s, bool l2, int ld, const int4* tiles, unsigned ntiles, int32_t* q_cnt, cudaEvent_t e0, cudaEvent_t e1) {
    KB2E_CUDA(c, cudaMemsetAsync(s->band_count, 0, sizeof(unsigned int), c->stream));
-   if (l2)
-      f32::prep_queries_kernel<1><<<nblk3(pq * 32, 256), 256, 0, c->stream>>>(ct, c->rel64, q_fixed, q_rel, q_side, q_slot, q_etrue, s->slot_max,
-                                                                             q_begin, q_end, c->D, ld, s->wq, s->thr_lo, s->thr_hi);
-   else
-      f32::prep_queries_kernel<0><<<nblk3(pq * 32, 256), 256, 0, c->stream>>>(ct, c->rel64, q_fixed, q_rel, q_side, q_slot, q_etrue, s->slot_max,
-                                                                             q_begin, q_end, c->D, ld, s->wq, s->thr_lo, s->thr_hi);
    F32Args a;
    a.ct32 = s->ct32; a.wq = s->wq; a.thr_lo = s->thr_lo; a.thr_hi = s->thr_hi; a.tiles = tiles;
    a.q_less = q_cnt; a.band = s->band; a.band_count = s->band_count; a.band_cap = s->band_cap;
@@ -303,6 +298,26 @@ int f32_run(kb2e_ctx* c, F32State* s, bool l2, const double* ct, int ld, const i
    if (l2) f32::rank_f32_kernel<1><<<dim3(ntiles, (unsigned)splits), f32::THREADS, smem, c->stream>>>(a);
    else f32::rank_f32_kernel<0><<<dim3(ntiles, (unsigned)splits), f32::THREADS, smem, c->stream>>>(a);
    KB2E_CUDA(c, cudaEventRecord(e1, c->stream));
+   KB2E_CUDA(c, cudaGetLastError());
+   return KB2E_OK;
+}
+
+int f32_run(kb2e_ctx* c, F32State* s, bool l2, const double* ct, int ld, const int32_t* q_int, long long nq_total, const double* q_etrue,
+            long long q_begin, long long q_end, const int4* tiles, unsigned ntiles, int32_t* q_cnt, cudaEvent_t e0, cudaEvent_t e1) {
+   const int32_t* q_fixed = q_int;
+   const int32_t* q_truth = q_int + nq_total;
+   const int32_t* q_rel = q_int + 2 * nq_total;
+   const int32_t* q_side = q_int + 3 * nq_total;
+   const int32_t* q_slot = q_int + 4 * nq_total;
+   const long long pq = q_end - q_begin;
+   if (l2)
+      f32::prep_queries_kernel<1><<<nblk3(pq * 32, 256), 256, 0, c->stream>>>(ct, c->rel64, q_fixed, q_rel, q_side, q_slot, q_etrue, s->slot_max,
+                                                                             q_begin, q_end, c->D, ld, s->wq, s->thr_lo, s->thr_hi);
+   else
+      f32::prep_queries_kernel<0><<<nblk3(pq * 32, 256), 256, 0, c->stream>>>(ct, c->rel64, q_fixed, q_rel, q_side, q_slot, q_etrue, s->slot_max,
+                                                                             q_begin, q_end, c->D, ld, s->wq, s->thr_lo, s->thr_hi);
+   int rc = f32_main(c, s, l2, ld, tiles, ntiles, q_cnt, e0, e1);
+   if (rc) return rc;
    if (l2)
       f32::recheck_ct_kernel<1><<<4 * c->num_sms, 128, 0, c->stream>>>(s->band, s->band_count, s->band_cap, ct, c->rel64, q_fixed, q_truth, q_rel,
                                                                        q_side, q_slot, q_etrue, q_cnt, nq_total, c->D, ld);

@@ -38,6 +38,10 @@ struct F32State {
 
 constexpr int kF32QueriesPerTile = 32;
 
+// Grow-only buffers for `slots` fp32 candidate matrices and nq queries (first_pass also clears the call-wide counters).
+int f32_ensure(kb2e_ctx* c, F32State* s, size_t slots, int ld, long long nq, bool first_pass);
+// The all-candidates kernel alone on the prepared s->ct32 / s->wq / s->thr_lo / s->thr_hi (rank_transr.cu fills them itself).
+int f32_main(kb2e_ctx* c, F32State* s, bool l2, int ld, const int4* tiles, unsigned ntiles, int32_t* q_cnt, cudaEvent_t e0, cudaEvent_t e1);
 // Convert the pass's candidate matrices (fp64, transposed, `slots` of them) and size the per-call buffers.
 int f32_prepare(kb2e_ctx* c, F32State* s, const double* ct, size_t slots, int ld, long long nq, bool first_pass);
 // Enqueue thresholds + pre-filter + exact recheck for the queries [q_begin, q_end) of one pass (no host synchronisation).

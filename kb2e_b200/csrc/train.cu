@@ -19,6 +19,13 @@
 //   Phases are separated by a grid-wide barrier inside the launch; all table traffic goes through
 //   L2 (.cg) because other SMs rewrite the rows between phases.
 //
+// Touched rows, two ways (template parameter LIST):
+//   scan  every group walks its share of the stamp array in phase 2 (batches that touch most of the table);
+//   list  the FIRST toucher of a row in a batch (atomic exchange of the row's stamp) appends the row to a list in
+//         its CTA's shared memory; phase 2 of a CTA then publishes exactly its own list, one row per group, with no
+//         stamp scan and no dependence on where in the row space the touched rows fall.  At FB15k shape a batch
+//         touches ~4,000 of 16,296 rows: ~27 rows per CTA against 48 groups, so the publish is a single, balanced pass.
+//
 // Work distribution: a "group" of LPS lanes owns one sample (LPS*NV float4 >= row pitch), so a
 // D=50 row uses 16 lanes and a D=100 row 16 lanes x 2 vectors or 32 x 1, whichever lets one batch
 // fit in one pass over the resident groups (148 CTAs x 1024 threads).
@@ -35,9 +42,28 @@
 
 namespace kb2e {
 
+// ---- per-CTA lists of touched rows (LIST kernels) --------------------------------------------------
+// Shared-memory layout (ints): [0] #entity-side rows, [1], [2] #relation-side rows of even / odd stamps, [3] unused,
+// then ent[cap_ent], rel[0][cap_rel], rel[1][cap_rel].  TransE keeps entity and relation rows in the one `ent` list
+// (they are published in the same pass); TransH publishes relation-side rows first, and the soft constraint of an
+// entity row may touch a relation row for the NEXT batch, hence the two relation lists indexed by stamp parity.
+// Entries are row indices in the unified row space (relation r = nE + r).
+struct RowLists {
+   int* count;
+   int* ent;
+   int* rel[2];
+   int cap_ent, cap_rel;
+};
+
+__device__ __forceinline__ void list_push(int* count, int* list, int cap, int row, unsigned long long* counters) {
+   const int slot = atomicAdd(count, 1);
+   if (slot < cap) list[slot] = row;
+   else counters[6] = 1ull;   // cannot happen with the host's capacities; reported as an error if it ever does
+}
+
 // ---- phase 1: one (positive, negative) pair, TransE and TransH -----------------------------------
-template <int MODEL, int LPS, int NV>
-__device__ __forceinline__ void process_pair(const TrainArgs& a, const Pair s, int gl, uint32_t gmask, uint8_t stamp,
+template <int MODEL, int LPS, int NV, bool LIST>
+__device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists& L, const Pair s, int gl, uint32_t gmask, uint32_t stamp,
                                              double& loss_acc, uint32_t& active_acc) {
    const int P = a.P, D = a.D;
    const float* eh = a.tab + (size_t)s.h * P;
@@ -92,6 +118,13 @@ __device__ __forceinline__ void process_pair(const TrainArgs& a, const Pair s, i
    if (gl == 0) {
       loss_acc += (double)(a.margin + ep - en);
       active_acc++;
+   }
+   // LIST: claim the four rows now (test-and-set of their stamps) so that the round trips overlap the REDs below
+   int my_row = 0;
+   bool first = false;
+   if (LIST && gl < 4) {
+      my_row = gl == 0 ? s.h : (gl == 1 ? s.t : (gl == 2 ? s.c : a.nE + s.r));
+      first = atomicExch(a.flag + my_row, stamp) != stamp;
    }
    const float lr = a.lr;
    float4 gp[NV], gn[NV];  // lr * x for the positive / negative triple
@@ -158,13 +191,17 @@ __device__ __forceinline__ void process_pair(const TrainArgs& a, const Pair s, i
    // flag the touched rows (+ relation range per entity for the TransH/TransR constraints)
    if (gl < 3) {
       int e = gl == 0 ? s.h : (gl == 1 ? s.t : s.c);
-      a.flag[e] = stamp;
+      if (!LIST) a.flag[e] = stamp;
       if (MODEL != KB2E_MODEL_TRANSE) {
          atomicMin(a.rmin + e, s.r);
          atomicMax(a.rmax + e, s.r);
       }
    } else if (gl == 3) {
-      a.flag[(size_t)a.nE + s.r] = stamp;
+      if (!LIST) a.flag[(size_t)a.nE + s.r] = stamp;
+   }
+   if (LIST && first) {
+      if (MODEL == KB2E_MODEL_TRANSE || gl < 3) list_push(L.count + 0, L.ent, L.cap_ent, my_row, a.counters);
+      else list_push(L.count + 1 + (stamp & 1u), L.rel[stamp & 1u], L.cap_rel, my_row, a.counters);
    }
 }
 
@@ -202,8 +239,8 @@ __device__ __forceinline__ void finish_relation(const TrainArgs& a, int r, int g
 }
 
 // Entity row e.  transe/trainer.cpp:44-45, transh/trainer.cpp:49-50,57-58.
-template <int MODEL, int LPS, int NV>
-__device__ __forceinline__ void finish_entity(const TrainArgs& a, int e, int gl, uint32_t gmask, uint8_t next_stamp,
+template <int MODEL, int LPS, int NV, bool LIST>
+__device__ __forceinline__ void finish_entity(const TrainArgs& a, const RowLists& L, int e, int gl, uint32_t gmask, uint32_t next_stamp,
                                               float4 (&x)[NV], float4 (&d)[NV]) {
    const int P = a.P;
    float* cur = a.tab + (size_t)e * P;
@@ -227,7 +264,11 @@ __device__ __forceinline__ void finish_entity(const TrainArgs& a, int e, int gl,
 #pragma unroll
             for (int q = 0; q < NV; q++) b[q] = b[q] - b0[q];
             red_row<LPS, NV>(a.dw + (size_t)r * P, P, gl, b);
-            if (gl == 0) a.flag[(size_t)a.nE + r] = next_stamp;
+            if (gl == 0) {
+               if (!LIST) a.flag[(size_t)a.nE + r] = next_stamp;
+               else if (atomicExch(a.flag + a.nE + r, next_stamp) != next_stamp)
+                  list_push(L.count + 1 + (next_stamp & 1u), L.rel[next_stamp & 1u], L.cap_rel, a.nE + r, a.counters);
+            }
          }
       }
    }
@@ -272,15 +313,16 @@ __device__ __forceinline__ void project3(const float* M, int D, int P, int lane,
 // loads, then the arithmetic, so that the L2 round trips overlap.
 template <int MODEL, int LPS, int NV>
 __device__ __forceinline__ void publish_rows(const TrainArgs& a, long long row_begin, long long row_end, long long g0, long long G,
-                                             uint8_t stamp, uint8_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel) {
+                                             uint32_t stamp, uint32_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel) {
    const int P = a.P;
    const int lane = threadIdx.x & 31;
    long long first, end;
    group_range(row_begin, row_end, g0, G, first, end);
+   const RowLists none{};
    auto stamped = [&](long long r) { return __ldcg(a.flag + r) == stamp; };
    auto finish = [&](long long r, float4 (&x)[NV], float4 (&d)[NV]) {
       if (r >= a.nE) { finish_relation<MODEL, LPS, NV>(a, (int)(r - a.nE), gl, gmask, x, d); trel += (gl == 0); }
-      else { finish_entity<MODEL, LPS, NV>(a, (int)r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
+      else { finish_entity<MODEL, LPS, NV, false>(a, none, (int)r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
    };
    for_stamped_rows<LPS>(first, end, gl, gmask, lane, stamped, [&](long long r0, long long r1) {
       float4 x0[NV], d0[NV], x1[NV], d1[NV];
@@ -295,9 +337,44 @@ __device__ __forceinline__ void publish_rows(const TrainArgs& a, long long row_b
    });
 }
 
-template <int MODEL, int LPS, int NV, int THREADS>
+// LIST kernels: the CTA's own list, n rows, one row per group and pass (two rows of a group in flight when the list is
+// longer than the CTA has groups).
+template <int MODEL, int LPS, int NV>
+__device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists& L, const int* list, int n, int group, int groups,
+                                             uint32_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel) {
+   const int P = a.P;
+   auto finish = [&](int r, float4 (&x)[NV], float4 (&d)[NV]) {
+      if (r >= a.nE) { finish_relation<MODEL, LPS, NV>(a, r - a.nE, gl, gmask, x, d); trel += (gl == 0); }
+      else { finish_entity<MODEL, LPS, NV, true>(a, L, r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
+   };
+   for (int i = group; i < n; i += 2 * groups) {
+      const int r0 = list[i];
+      const int r1 = i + groups < n ? list[i + groups] : -1;
+      float4 x0[NV], d0[NV], x1[NV], d1[NV];
+      load_row<LPS, NV>(a.tab + (size_t)r0 * P, P, gl, x0);
+      load_row<LPS, NV>(a.dtab + (size_t)r0 * P, P, gl, d0);
+      if (r1 >= 0) {
+         load_row<LPS, NV>(a.tab + (size_t)r1 * P, P, gl, x1);
+         load_row<LPS, NV>(a.dtab + (size_t)r1 * P, P, gl, d1);
+      }
+      finish(r0, x0, d0);
+      if (r1 >= 0) finish(r1, x1, d1);
+   }
+}
+
+template <int MODEL, int LPS, int NV, int THREADS, bool LIST>
 __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant__ TrainArgs a) {
    __shared__ double s_loss[THREADS / 32];
+   extern __shared__ int s_lists[];
+   RowLists L{};
+   if (LIST) {
+      L.count = s_lists;
+      L.cap_ent = a.cap_ent;
+      L.cap_rel = a.cap_rel;
+      L.ent = s_lists + 4;
+      L.rel[0] = L.ent + a.cap_ent;
+      L.rel[1] = L.rel[0] + a.cap_rel;
+   }
    const int lane = threadIdx.x & 31;
    const int gl = lane % LPS;
    const uint32_t gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << ((lane / LPS) * LPS));
@@ -321,25 +398,58 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
    Pair pre;
    const bool has_first = g0 < a.batchsize;
    if (has_first) pre = draw_pair(a, (uint32_t)g0, gb_first);
+   const int group = threadIdx.x / LPS;
+   if (LIST) {
+      if (threadIdx.x < 4) L.count[threadIdx.x] = 0;
+      __syncthreads();
+      if (MODEL != KB2E_MODEL_TRANSE) {
+         // relation rows the LAST launch's final entity phase marked for this launch's first batch (the perturbation of
+         // w_r carried into the next batch's delta): their stamps are already set, so nobody would list them again
+         const uint32_t s0 = a.stamp_base + 1u;
+         for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.nR; r += gridDim.x * blockDim.x)
+            if (__ldcg(a.flag + a.nE + r) == s0) list_push(L.count + 1 + (s0 & 1u), L.rel[s0 & 1u], L.cap_rel, a.nE + r, a.counters);
+         __syncthreads();
+      }
+   }
 
+   uint32_t rel_batch = 0;
    for (int ep = 0; ep < a.n_epochs; ep++) {
       double loss_acc = 0.0;
-      for (int batch = 0; batch < a.batches; batch++) {
-         const uint32_t gb = gb_first + (uint32_t)ep * (uint32_t)a.batches + (uint32_t)batch;
-         const uint8_t stamp = (uint8_t)(gb % 255u + 1u);
-         const uint8_t next_stamp = (uint8_t)((gb + 1u) % 255u + 1u);
+      for (int batch = 0; batch < a.batches; batch++, rel_batch++) {
+         const uint32_t gb = gb_first + rel_batch;
+         // stamps count the batches this CONTEXT has run (not the caller's epoch numbers), so a stamp never recurs
+         const uint32_t stamp = a.stamp_base + rel_batch + 1u;
+         const uint32_t next_stamp = stamp + 1u;
          KB2E_TRACE();
          // ---- phase 1 ----
-         if (has_first) process_pair<MODEL, LPS, NV>(a, pre, gl, gmask, stamp, loss_acc, active_acc);
+         if (has_first) process_pair<MODEL, LPS, NV, LIST>(a, L, pre, gl, gmask, stamp, loss_acc, active_acc);
          for (long long k = g0 + G; k < a.batchsize; k += G) {
             Pair s = draw_pair(a, (uint32_t)k, gb);
-            process_pair<MODEL, LPS, NV>(a, s, gl, gmask, stamp, loss_acc, active_acc);
+            process_pair<MODEL, LPS, NV, LIST>(a, L, s, gl, gmask, stamp, loss_acc, active_acc);
          }
          KB2E_TRACE();
          grid_barrier(a.barrier, bar_target);
          KB2E_TRACE();
+         if (a.phase1_only) continue;   // kb2e_train_batch_deltas: the caller reads the raw delta tables (one batch per launch)
          // ---- phase 2 ----
-         if (MODEL == KB2E_MODEL_TRANSE) {
+         if (LIST) {
+            if (MODEL == KB2E_MODEL_TRANSE) {
+               publish_list<MODEL, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, next_stamp, gl, gmask,
+                                            tent_acc, trel_acc);
+               KB2E_TRACE();
+            } else {
+               int* nrel = L.count + 1 + (stamp & 1u);
+               publish_list<MODEL, LPS, NV>(a, L, L.rel[stamp & 1u], min(*nrel, L.cap_rel), group, groups_per_block, next_stamp, gl, gmask,
+                                            tent_acc, trel_acc);
+               grid_barrier(a.barrier, bar_target);   // (its leading bar.sync also ends every read of *nrel)
+               if (threadIdx.x == 0) *nrel = 0;
+               KB2E_TRACE();
+               publish_list<MODEL, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, next_stamp, gl, gmask,
+                                            tent_acc, trel_acc);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) L.count[0] = 0;
+         } else if (MODEL == KB2E_MODEL_TRANSE) {
             // no coupling between relation and entity rows: one pass over the whole row space
             publish_rows<MODEL, LPS, NV>(a, 0, R, g0, G, stamp, next_stamp, gl, gmask, tent_acc, trel_acc);
             KB2E_TRACE();
@@ -549,8 +659,8 @@ int train_alloc(kb2e_ctx* c) {
    KB2E_CUDA(c, pool_alloc(c, &c->dtab, rows * c->P * sizeof(float)));
    KB2E_CUDA(c, cudaMemsetAsync(c->tab, 0, rows * c->P * sizeof(float), c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->dtab, 0, rows * c->P * sizeof(float), c->stream));
-   KB2E_CUDA(c, pool_alloc(c, &c->flag, (size_t)c->nE + 2 * (size_t)c->nR));
-   KB2E_CUDA(c, cudaMemsetAsync(c->flag, 0, (size_t)c->nE + 2 * (size_t)c->nR, c->stream));
+   KB2E_CUDA(c, pool_alloc(c, &c->flag, rows * sizeof(uint32_t)));
+   KB2E_CUDA(c, cudaMemsetAsync(c->flag, 0, rows * sizeof(uint32_t), c->stream));
    if (c->cfg.model != KB2E_MODEL_TRANSE) {
       c->w_row = c->cfg.model == KB2E_MODEL_TRANSH ? (size_t)c->P : (size_t)c->D * c->P;
       KB2E_CUDA(c, pool_alloc(c, &c->w, (size_t)c->nR * c->w_row * sizeof(float)));
@@ -721,32 +831,48 @@ static void fill_args(kb2e_ctx* c, TrainArgs& a) {
 typedef void (*TrainKernel)(const TrainArgs);
 
 // One persistent CTA per SM; fewer threads per CTA buy registers (65536 / THREADS per thread) for the
-// shapes that keep more vectors per lane in flight.
-template <int MODEL, int THREADS>
-static TrainKernel pick_kernel_t(int lps, int nv) {
-#define KB2E_PICK(L, N) if (lps == L && nv == N) return train_kernel<MODEL, L, N, THREADS>;
-   KB2E_PICK(8, 1) KB2E_PICK(8, 2) KB2E_PICK(8, 4)
-   KB2E_PICK(16, 1) KB2E_PICK(16, 2) KB2E_PICK(16, 4)
-   KB2E_PICK(32, 1) KB2E_PICK(32, 2) KB2E_PICK(32, 4)
+// shapes that keep more vectors per lane in flight: 1024 threads with one float4 per lane, 768 with two, 512 with
+// four; TransH always 512 (five rows per sample live in registers: 768 threads = 80 registers spill).
+static int threads_for(int model, int nv) {
+   if (nv >= 4) return 512;
+   if (model == KB2E_MODEL_TRANSH) return 512;
+   if (nv == 2) return 768;
+   return 1024;
+}
+
+template <int MODEL, bool LIST>
+static TrainKernel pick_kernel(int lps, int nv) {
+#define KB2E_PICK(L, N, T) if (lps == L && nv == N) return train_kernel<MODEL, L, N, T, LIST>;
+   if (MODEL == KB2E_MODEL_TRANSH) {
+      KB2E_PICK(8, 1, 512) KB2E_PICK(16, 1, 512) KB2E_PICK(32, 1, 512)
+      KB2E_PICK(8, 2, 512) KB2E_PICK(16, 2, 512) KB2E_PICK(32, 2, 512)
+   } else {
+      KB2E_PICK(8, 1, 1024) KB2E_PICK(16, 1, 1024) KB2E_PICK(32, 1, 1024)
+      KB2E_PICK(8, 2, 768) KB2E_PICK(16, 2, 768) KB2E_PICK(32, 2, 768)
+      KB2E_PICK(8, 4, 512) KB2E_PICK(16, 4, 512) KB2E_PICK(32, 4, 512)
+   }
 #undef KB2E_PICK
    return nullptr;
 }
 
-template <int MODEL>
-static TrainKernel pick_kernel(int lps, int nv, int threads) {
-   if (threads == 1024) return pick_kernel_t<MODEL, 1024>(lps, nv);
-   if (threads == 768) return pick_kernel_t<MODEL, 768>(lps, nv);
-   if (threads == 512) return pick_kernel_t<MODEL, 512>(lps, nv);
-   return nullptr;
-}
-
-static int threads_for(int model, int nv) {
-   const char* env = getenv("KB2E_TRAIN_THREADS");
-   if (env) return atoi(env);
-   if (nv >= 4) return 512;
-   if (model == KB2E_MODEL_TRANSH) return 512;   // five rows per sample live in registers: 768 threads (80 registers) spill
-   if (nv == 2) return 768;
-   return 1024;
+// Capacities of the per-CTA touched-row lists (LIST kernels) for a batch of `batchsize` pairs dealt round-robin to
+// `groups` groups per CTA: S pairs per CTA and batch, each can be the first toucher of 3 entity rows and 1 relation row;
+// a published entity row can mark up to two relation rows for the next batch (TransH).  Returns the dynamic shared
+// memory in bytes, or 0 when the scan kernel should be used (lists too large, or a batch that touches most of the table).
+static size_t list_shape(const kb2e_ctx* c, long long batchsize, int groups, int& cap_ent, int& cap_rel) {
+   const char* env = getenv("KB2E_TRAIN_LIST");   // 0: always the scan kernel (tuning aid / A-B measurements)
+   if (env && atoi(env) == 0) return 0;
+   const long long G = (long long)c->num_sms * groups;
+   const long long S = (long long)groups * ((batchsize + G - 1) / G);
+   const bool transe = c->cfg.model == KB2E_MODEL_TRANSE;
+   const long long ce = (transe ? 4 : 3) * S;
+   const long long cr = transe ? 0 : std::min<long long>(c->nR, 7 * S);
+   const size_t bytes = (size_t)(4 + ce + 2 * cr) * sizeof(int);
+   if (bytes > 40 * 1024) return 0;
+   if (4 * batchsize > (long long)c->nE + c->nR && !(env && atoi(env) == 1)) return 0;
+   cap_ent = (int)ce;
+   cap_rel = (int)cr;
+   return bytes;
 }
 
 // Choose lanes-per-sample (LPS) / float4-vectors-per-lane (NV): among the shapes that waste the
@@ -780,18 +906,21 @@ static void choose_shape(const kb2e_ctx* c, long long batchsize, int& lps, int& 
    lps = Ls[pick]; nv = Ns[pick]; threads_out = Ts[pick];
 }
 
-int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_dev, int64_t n_pairs, double* loss_out) {
+int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_dev, int64_t n_pairs, double* loss_out, bool phase1_only) {
    { int rc = ensure32(c); if (rc) return rc; }
    TrainArgs a;
    if (n_epochs <= 0) return KB2E_OK;
    if (n_epochs > c->loss_cap) {
       pool_free(c, c->loss_dev);
+      c->loss_dev = nullptr;
+      c->loss_cap = 0;
       KB2E_CUDA(c, pool_alloc(c, &c->loss_dev, (size_t)n_epochs * sizeof(double)));
       c->loss_cap = n_epochs;
    }
    fill_args(c, a);
    a.first_epoch = first_epoch;
    a.n_epochs = n_epochs;
+   a.phase1_only = phase1_only ? 1 : 0;
    if (pairs_dev) {
       a.pairs = pairs_dev;
       a.batches = 1;
@@ -808,24 +937,36 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    if (nv > 4) return fail(c, KB2E_ERR_LIMIT, "embedding size above 512 is not supported by the training kernel");
    TrainKernel k = nullptr;
    const bool transr = c->cfg.model == KB2E_MODEL_TRANSR;   // own kernel: train_transr.cu
+   size_t list_bytes = 0;
    if (transr) {
       if (c->P > 128) return fail(c, KB2E_ERR_LIMIT, "TransR training supports embedding sizes up to 128");
-   } else if (c->cfg.model == KB2E_MODEL_TRANSE) {
-      k = pick_kernel<KB2E_MODEL_TRANSE>(lps, nv, threads);
    } else {
-      k = pick_kernel<KB2E_MODEL_TRANSH>(lps, nv, threads);
+      list_bytes = list_shape(c, a.batchsize, threads / lps, a.cap_ent, a.cap_rel);
+      if (c->cfg.model == KB2E_MODEL_TRANSE)
+         k = list_bytes ? pick_kernel<KB2E_MODEL_TRANSE, true>(lps, nv) : pick_kernel<KB2E_MODEL_TRANSE, false>(lps, nv);
+      else
+         k = list_bytes ? pick_kernel<KB2E_MODEL_TRANSH, true>(lps, nv) : pick_kernel<KB2E_MODEL_TRANSH, false>(lps, nv);
    }
    if (!k && !transr) return fail(c, KB2E_ERR_LIMIT, "no training kernel for this embedding size");
+   // row stamps of this launch: stamp_base + 1 ... stamp_base + #batches, never reused by a later launch
+   const uint64_t n_batches = (uint64_t)a.batches * (uint64_t)n_epochs;
+   if (n_batches >= (1ull << 31)) return fail(c, KB2E_ERR_LIMIT, "more than 2^31 batches in one launch");
+   if ((uint64_t)c->stamp_base + n_batches + 2 >= (1ull << 32)) {
+      KB2E_CUDA(c, cudaMemsetAsync(c->flag, 0, ((size_t)c->nE + c->nR) * sizeof(uint32_t), c->stream));
+      c->stamp_base = 0;
+   }
+   a.stamp_base = c->stamp_base;
    // batches that need at most half of the resident groups: one barrier per batch, every row folded where its last
    // sample finishes (train_fused.cu)
-   const bool fused = !transr && train_fused_wanted(c, a.batchsize, lps, threads);
+   const bool fused = !transr && !phase1_only && train_fused_wanted(c, a.batchsize, lps, threads);
    if (!transr) {
       int per_sm = 0;
-      KB2E_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0));
+      KB2E_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, list_bytes));
       if (per_sm < 1) return fail(c, KB2E_ERR_CUDA, "training kernel does not fit on an SM");
    }
    KB2E_CUDA(c, cudaMemsetAsync(c->barrier, 0, 64, c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->loss_dev, 0, (size_t)n_epochs * sizeof(double), c->stream));
+   KB2E_CUDA(c, cudaMemsetAsync(c->counters + 6, 0, sizeof(unsigned long long), c->stream));
    const char* trace_path = getenv("KB2E_TRAIN_TRACE");
    unsigned long long* trace_dev = nullptr;
    if (trace_path) {
@@ -841,17 +982,19 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    } else {
       int rc = fused ? train_fused_launch(c, a, lps, nv, threads) : KB2E_ERR_LIMIT;
       if (rc == KB2E_ERR_LIMIT) {   // not a small batch, or no fused instantiation for this shape: the two-barrier kernel
-         KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(threads), params, 0, c->stream));
+         KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(threads), params, list_bytes, c->stream));
       } else if (rc) {
          return rc;
       }
    }
    KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
    std::vector<double> loss(n_epochs);
-   unsigned long long cnt[3];
+   unsigned long long cnt[7];
    KB2E_CUDA(c, cudaMemcpyAsync(loss.data(), c->loss_dev, (size_t)n_epochs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaMemcpyAsync(cnt, c->counters, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   c->stamp_base += (uint32_t)n_batches;
+   if (cnt[6]) return fail(c, KB2E_ERR_LIMIT, "internal: a touched-row list overflowed (tables may be inconsistent)");
    if (trace_dev) {
       std::vector<unsigned long long> tr((size_t)c->num_sms * kTraceSlots);
       cudaMemcpy(tr.data(), trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -872,7 +1015,46 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    c->tstats.touched_ent = cnt[1];
    c->tstats.touched_rel = cnt[2];
    if (loss_out) memcpy(loss_out, loss.data(), (size_t)n_epochs * sizeof(double));
-   for (int t = 0; t < 3; t++) c->v64[t] = false;
+   if (!phase1_only) for (int t = 0; t < 3; t++) c->v64[t] = false;
+   return KB2E_OK;
+}
+
+// Test hook behind kb2e_train_batch_deltas: the accumulated (pre-normalisation) updates of the last phase1_only
+// launch, widened to fp64, then the delta tables, the stamps and the relation ranges go back to their idle state.
+__global__ void widen_delta_kernel(float* src, double* dst, long long rows, int D, int P) {
+   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= rows * P) return;
+   const int col = (int)(i % P);
+   if (col < D) dst[(i / P) * D + col] = (double)src[i];
+   src[i] = 0.f;
+}
+
+int train_take_deltas(kb2e_ctx* c, double* d_ent, double* d_rel, double* d_w) {
+   const long long we = c->cfg.model == KB2E_MODEL_TRANSE ? 0 : (c->cfg.model == KB2E_MODEL_TRANSH ? (long long)c->nR : (long long)c->nR * c->D);
+   const long long rows[3] = {c->nE, c->nR, we};
+   float* src[3] = {c->dtab, c->dtab + (size_t)c->nE * c->P, c->dw};
+   double* dst[3] = {d_ent, d_rel, d_w};
+   long long most = std::max(rows[0], std::max(rows[1], rows[2]));
+   double* dev = nullptr;
+   KB2E_CUDA(c, pool_alloc(c, &dev, (size_t)most * c->D * sizeof(double)));
+   int rc = KB2E_OK;
+   for (int t = 0; t < 3 && rc == KB2E_OK; t++) {
+      if (rows[t] == 0) continue;
+      widen_delta_kernel<<<blocks_for(rows[t] * c->P, 256), 256, 0, c->stream>>>(src[t], dev, rows[t], c->D, c->P);
+      cudaError_t e = cudaGetLastError();
+      if (e == cudaSuccess && dst[t]) e = cudaMemcpyAsync(dst[t], dev, (size_t)rows[t] * c->D * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) rc = cuda_fail(c, e, "kb2e_train_batch_deltas copy");
+   }
+   pool_free(c, dev);
+   if (rc) return rc;
+   KB2E_CUDA(c, cudaMemsetAsync(c->flag, 0, ((size_t)c->nE + c->nR) * sizeof(uint32_t), c->stream));
+   if (c->rmin) {
+      fill_int_kernel<<<blocks_for(c->nE, 256), 256, 0, c->stream>>>(c->rmin, c->nE, 0x7fffffff);
+      fill_int_kernel<<<blocks_for(c->nE, 256), 256, 0, c->stream>>>(c->rmax, c->nE, -1);
+   }
+   KB2E_CUDA(c, cudaGetLastError());
+   KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
    return KB2E_OK;
 }
 

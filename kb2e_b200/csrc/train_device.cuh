@@ -16,7 +16,7 @@ struct TrainArgs {
    float* dtab;
    float* w;
    float* dw;
-   uint8_t* flag;    // [nE + nR] batch stamp (1..255) of the last batch that touched the row; 0 = never
+   uint32_t* flag;   // [nE + nR] stamp (global batch + 1) of the last batch that touched the row; 0 = never
    int* rmin;
    int* rmax;
    const int4* triples;
@@ -34,6 +34,9 @@ struct TrainArgs {
    int batches, first_epoch, n_epochs, distance;
    float lr, margin;
    uint32_t seed_lo, seed_hi, flags;
+   uint32_t stamp_base;           // batches this context has run before this launch: batch k of the launch stamps rows with stamp_base + k + 1
+   int phase1_only;               // test hook (kb2e_train_batch_deltas): stop after the accumulation phase
+   int cap_ent, cap_rel;          // LIST kernels: capacities of the per-CTA touched-row lists (train.cu)
    unsigned long long* trace;     // tuning aid (KB2E_TRAIN_TRACE): per-CTA clock stamps of the first batches
 };
 
@@ -193,6 +196,16 @@ struct Pair {
    bool corruptTail;  // true: (h, r, c) is the negative; false: (c, r, t)
 };
 
+// KB2E_FLAG_SAMPLER_RANDMAX: common/utils.cpp:113-120 with two uniform 31-bit draws in place of the two std::rand()
+// calls -- (rand() * rand()) % x in wrapping 32-bit int arithmetic, then "while (res < 0) res += x" -- i.e. the
+// reference's (non-uniform) index distribution, driven by the counter RNG (the CPU twin in the test checker bears the same name).
+__device__ __forceinline__ int randmax_from(uint32_t x0, uint32_t x1, int x) {
+   int res = (int)((x0 >> 1) * (x1 >> 1));
+   res = res % x;
+   if (res < 0) res += x;
+   return res;
+}
+
 __device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32_t gb) {
    Pair s;
    if (a.pairs != nullptr) {
@@ -205,17 +218,24 @@ __device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32
    }
    uint32_t x[4];
    philox4x32(k, gb, 0u, 0u, a.seed_lo, a.seed_hi, x);
+   const bool randmax = (a.flags & KB2E_FLAG_SAMPLER_RANDMAX) != 0u;
    uint64_t i = mulhi64(((uint64_t)x[0] << 32) | x[1], (uint64_t)a.n_train);
+   int j = (int)mulhi32(x[3], (uint32_t)a.nE);
+   if (randmax) {
+      uint32_t y[4];
+      philox4x32(k, gb, 0u, 1u, a.seed_lo, a.seed_hi, y);
+      i = (uint64_t)randmax_from(x[0], x[1], (int)a.n_train);
+      j = randmax_from(y[0], y[1], a.nE);
+   }
    int4 tr = __ldg(a.triples + i);
    s.h = tr.x; s.t = tr.y; s.r = tr.z;
    int coin = (int)(x[2] % 1000u);
-   int j = (int)mulhi32(x[3], (uint32_t)a.nE);
    s.corruptTail = (double)coin < __ldg(a.pr + tr.z);
    for (uint32_t att = 1; att < 64; att++) {
       uint64_t key = s.corruptTail ? pack_triple(s.h, s.r, j) : pack_triple(j, s.r, s.t);
       if (!hash_contains(a.hash, a.hash_mask, key)) break;
       philox4x32(k, gb, att, 0u, a.seed_lo, a.seed_hi, x);
-      j = (int)mulhi32(x[0], (uint32_t)a.nE);
+      j = randmax ? randmax_from(x[0], x[1], a.nE) : (int)mulhi32(x[0], (uint32_t)a.nE);
    }
    s.c = j;
    return s;

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_fused_kernel(const __grid_co
       double loss_acc = 0.0;
       for (int batch = 0; batch < a.batches; batch++, rel_batch++) {
          const uint32_t gb = gb_first + rel_batch;
-         const uint8_t stamp = (uint8_t)(gb % 255u + 1u);
+         const uint32_t stamp = a.stamp_base + rel_batch + 1u;   // counts the batches this context has run (train.cu)
          uint32_t* pend = fa.pend + (size_t)(gb % 3u) * R;
          KB2E_FTRACE();
          if (has) {

@@ -118,7 +118,7 @@ __device__ __forceinline__ void get_slot(const float* slot, int D, int lane, flo
 
 // ---- phase 1 ---------------------------------------------------------------------------------------------
 template <int NE>
-__device__ __forceinline__ void transr_pair(const RArgs& ra, const Pair s, float* sM, float* sV, int lane, uint8_t stamp,
+__device__ __forceinline__ void transr_pair(const RArgs& ra, const Pair s, float* sM, float* sV, int lane, uint32_t stamp,
                                             double& loss_acc, uint32_t& active_acc) {
    const TrainArgs& a = ra.base;
    const int P = a.P, D = a.D, P4 = P >> 2;
@@ -325,7 +325,7 @@ __device__ __forceinline__ void transr_finish_relation(const RArgs& ra, int r, i
 // numbers per chunk, computed once per call when the constraint is violated at all).  Same recurrence, a
 // quarter of the dependent reductions.
 template <int NE>
-__device__ __forceinline__ void transr_constraint(const RArgs& ra, int r, float* sM, float* sV, int lane, uint8_t next_stamp,
+__device__ __forceinline__ void transr_constraint(const RArgs& ra, int r, float* sM, float* sV, int lane, uint32_t next_stamp,
                                                   float (&x)[NE]) {
    const TrainArgs& a = ra.base;
    const int P = a.P, D = a.D, P4 = P >> 2, pitch = ra.pitch;
@@ -409,8 +409,8 @@ __device__ __forceinline__ void transr_constraint(const RArgs& ra, int r, float*
 // ---- phase 2b: entity row -- unit length (transr/trainer.cpp:175-176), then transRNorm against the lowest /
 // highest relation that touched it, and -- the reference's quirk at :187 -- against M_e when relation e was touched.
 template <int NE>
-__device__ __forceinline__ void transr_finish_entity(const RArgs& ra, int e, float* sM, float* sV, int lane, uint8_t stamp,
-                                                     uint8_t next_stamp, bool own) {
+__device__ __forceinline__ void transr_finish_entity(const RArgs& ra, int e, float* sM, float* sV, int lane, uint32_t stamp,
+                                                     uint32_t next_stamp, bool own) {
    const TrainArgs& a = ra.base;
    const int P = a.P, D = a.D;
    const bool on = lane < (P >> 2);
@@ -522,8 +522,9 @@ __global__ void __launch_bounds__(kRMaxThreads, 1) train_transr_kernel(const __g
       double loss_acc = 0.0;
       for (int batch = 0; batch < a.batches; batch++) {
          const uint32_t gb = gb_first + (uint32_t)ep * (uint32_t)a.batches + (uint32_t)batch;
-         const uint8_t stamp = (uint8_t)(gb % 255u + 1u);
-         const uint8_t next_stamp = (uint8_t)((gb + 1u) % 255u + 1u);
+         // stamps count the batches this context has run (train.cu), so a stamp never recurs
+         const uint32_t stamp = a.stamp_base + (uint32_t)ep * (uint32_t)a.batches + (uint32_t)batch + 1u;
+         const uint32_t next_stamp = stamp + 1u;
          KB2E_RTRACE();
          if (has_first) transr_pair<NE>(ra, pre, sM, sV, lane, stamp, loss_acc, active_acc);
          for (long long k = g0 + G; k < a.batchsize; k += G) {
@@ -533,6 +534,7 @@ __global__ void __launch_bounds__(kRMaxThreads, 1) train_transr_kernel(const __g
          KB2E_RTRACE();
          grid_barrier(a.barrier, bar_target);
          KB2E_RTRACE();
+         if (a.phase1_only) continue;   // kb2e_train_batch_deltas: the caller reads the raw delta tables (one batch per launch)
          // ---- phase 2a: every CTA builds the same list of touched relations; entry t is cut into S row segments
          // and (entry, segment) pairs are dealt round-robin over all warps of the grid
          for (long long w0 = 0; w0 < a.nR; w0 += kListCap) {

@@ -151,8 +151,10 @@ void orc_transr_norm(double* a, double* M, int D, double lr) {
 
 /* ============================== gradient updates ============================================== */
 
+/* `raw` != 0 stops before the normalisation tail of each gradientUpdate: the accumulation code is shared with the
+ * bitwise-pinned normalising form, so (raw result, then the same tail) == the reference by construction. */
 static void grad_transe(int distance, int D, double lr, const double* ent, const double* rel,
-                        double* entN, double* relN, int h, int t, int r, int corrupted) {
+                        double* entN, double* relN, int h, int t, int r, int corrupted, int raw) {
    /* transe/trainer.cpp:25-46 */
    double modifier = corrupted ? 1.0 : -1.0;
    const double* eh = ent + (size_t)h * D;
@@ -168,13 +170,14 @@ static void grad_transe(int distance, int D, double lr, const double* ent, const
       nh[i] -= modifier * lr * x;
       nt[i] += modifier * lr * x;
    }
+   if (raw) return;
    orc_norm(nr, D, 1);
    orc_norm(nh, D, 1);
    orc_norm(nt, D, 1);
 }
 
 static void grad_transh(int D, double lr, const double* ent, const double* rel, const double* w,
-                        double* entN, double* relN, double* wN, int h, int t, int r, int corrupted) {
+                        double* entN, double* relN, double* wN, int h, int t, int r, int corrupted, int raw) {
    /* transh/trainer.cpp:11-59 */
    double beta = corrupted ? 1 : -1;
    const double* eh = ent + (size_t)h * D;
@@ -204,6 +207,7 @@ static void grad_transh(int D, double lr, const double* ent, const double* rel, 
       nw[i] += beta * lr * sum_x * eh[i];
       nw[i] -= beta * lr * sum_x * et[i];
    }
+   if (raw) return;
    orc_norm(nr, D, 1);
    orc_norm(nh, D, 1);
    orc_norm(nt, D, 1);
@@ -214,7 +218,7 @@ static void grad_transh(int D, double lr, const double* ent, const double* rel, 
 }
 
 static void grad_transr(int distance, int D, double lr, const double* ent, const double* rel, const double* w,
-                        double* entN, double* relN, double* wN, int h, int t, int r, int corrupted) {
+                        double* entN, double* relN, double* wN, int h, int t, int r, int corrupted, int raw) {
    /* transr/trainer.cpp:144-188 */
    double beta = corrupted ? 1.0 : -1.0;
    const double* eh = ent + (size_t)h * D;
@@ -240,6 +244,7 @@ static void grad_transr(int distance, int D, double lr, const double* ent, const
       }
       nr[i] -= beta * lr * x;
    }
+   if (raw) return;
    orc_norm(nr, D, 0);
    orc_norm(nh, D, 0);
    orc_norm(nt, D, 0);
@@ -253,9 +258,40 @@ static void grad_transr(int distance, int D, double lr, const double* ent, const
 void orc_grad(int model, int distance, int D, double lr,
               const double* ent, const double* rel, const double* w,
               double* entN, double* relN, double* wN, int h, int t, int r, int corrupted) {
-   if (model == 0) grad_transe(distance, D, lr, ent, rel, entN, relN, h, t, r, corrupted);
-   else if (model == 1) grad_transh(D, lr, ent, rel, w, entN, relN, wN, h, t, r, corrupted);
-   else grad_transr(distance, D, lr, ent, rel, w, entN, relN, wN, h, t, r, corrupted);
+   if (model == 0) grad_transe(distance, D, lr, ent, rel, entN, relN, h, t, r, corrupted, 0);
+   else if (model == 1) grad_transh(D, lr, ent, rel, w, entN, relN, wN, h, t, r, corrupted, 0);
+   else grad_transr(distance, D, lr, ent, rel, w, entN, relN, wN, h, t, r, corrupted, 0);
+}
+
+/* The same accumulation WITHOUT the normalisation tail (transe/trainer.cpp:43-45, transh/trainer.cpp:48-58,
+ * transr/trainer.cpp:174-187): entN/relN/wN - their inputs = the pre-normalisation update of one gradientUpdate. */
+void orc_grad_raw(int model, int distance, int D, double lr,
+                  const double* ent, const double* rel, const double* w,
+                  double* entN, double* relN, double* wN, int h, int t, int r, int corrupted) {
+   if (model == 0) grad_transe(distance, D, lr, ent, rel, entN, relN, h, t, r, corrupted, 1);
+   else if (model == 1) grad_transh(D, lr, ent, rel, w, entN, relN, wN, h, t, r, corrupted, 1);
+   else grad_transr(distance, D, lr, ent, rel, w, entN, relN, wN, h, t, r, corrupted, 1);
+}
+
+/* The normalisation tail alone, on rows that already hold the accumulated update. */
+void orc_grad_tail(int model, int D, double lr, double* entN, double* relN, double* wN, int h, int t, int r) {
+   double* nh = entN + (size_t)h * D;
+   double* nt = entN + (size_t)t * D;
+   double* nr = relN + (size_t)r * D;
+   if (model == 0) {
+      orc_norm(nr, D, 1); orc_norm(nh, D, 1); orc_norm(nt, D, 1);
+   } else if (model == 1) {
+      double* nw = wN + (size_t)r * D;
+      orc_norm(nr, D, 1); orc_norm(nh, D, 1); orc_norm(nt, D, 1); orc_norm(nw, D, 0);
+      orc_norm2(nr, nw, D, lr); orc_norm2(nh, nw, D, lr); orc_norm2(nt, nw, D, lr);
+   } else {
+      double* nM = wN + (size_t)r * D * D;
+      orc_norm(nr, D, 0); orc_norm(nh, D, 0); orc_norm(nt, D, 0);
+      for (int j = 0; j < D; j++) orc_norm(nM + (size_t)j * D, D, 0);
+      orc_transr_norm(nh, nM, D, lr);
+      orc_transr_norm(nt, nM, D, lr);
+      orc_transr_norm(entN + (size_t)r * D, nM, D, lr);
+   }
 }
 
 static size_t w_elems(int model, int D, int nR) {
@@ -412,6 +448,7 @@ struct orc_sampler {
    int *h, *t, *r;
    trip* set;
    double* pr;
+   int mode; /* 0: uniform indices (mulhi); 1: the index DISTRIBUTION of the reference's randMax */
 };
 
 orc_sampler* orc_sampler_create(long n, const int* h, const int* t, const int* r, int nE, int nR, int method) {
@@ -444,9 +481,30 @@ void orc_sampler_destroy(orc_sampler* s) {
 }
 
 const double* orc_sampler_pr(const orc_sampler* s) { return s->pr; }
+void orc_sampler_set_mode(orc_sampler* s, int mode) { s->mode = mode; }
+
+/* common/utils.cpp:113-120 with two uniform 31-bit draws in place of the two std::rand() calls:
+ * `(rand() * rand()) % x` in 32-bit int arithmetic (the product wraps), then `while (res < 0) res += x`.
+ * Same index distribution as the reference (e.g. 75 % even values), from the counter RNG. */
+static int randmax_from(uint32_t a, uint32_t b, int x) {
+   int32_t res = (int32_t)((a >> 1) * (b >> 1));
+   res = res % x; /* C remainder: sign of the dividend */
+   if (res < 0) res += x;
+   return (int)res;
+}
 
 static uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+
+/* n draws of the randMax emulation from the counter RNG (test hook: compared with the reference's own randMax). */
+void orc_randmax_draws(uint64_t seed, int x, long n, int* out) {
+   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+   for (long i = 0; i < n; i++) {
+      uint32_t y[4];
+      orc_philox((uint32_t)i, (uint32_t)(i >> 32), 0, 7, k0, k1, y);
+      out[i] = randmax_from(y[0], y[1], x);
+   }
+}
 
 void orc_sample_batch(const orc_sampler* s, uint64_t seed, uint32_t gb, long count, int* out) {
    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -456,6 +514,12 @@ void orc_sample_batch(const orc_sampler* s, uint64_t seed, uint32_t gb, long cou
       long i = (long)mulhi64(((uint64_t)x[0] << 32) | x[1], (uint64_t)s->n);
       int coin = (int)(x[2] % 1000u);
       int j = (int)mulhi32(x[3], (uint32_t)s->nE);
+      if (s->mode == 1) {
+         uint32_t y[4];
+         orc_philox((uint32_t)k, gb, 0, 1, k0, k1, y);
+         i = randmax_from(x[0], x[1], (int)s->n);
+         j = randmax_from(y[0], y[1], s->nE);
+      }
       int h = s->h[i], t = s->t[i], r = s->r[i];
       int* p = out + 6 * k;
       p[0] = h; p[1] = t; p[2] = r; p[5] = r;
@@ -465,7 +529,7 @@ void orc_sample_batch(const orc_sampler* s, uint64_t seed, uint32_t gb, long cou
          int hit = corruptTail ? trip_in(s->set, s->n, h, r, j) : trip_in(s->set, s->n, j, r, t);
          if (!hit) break;
          orc_philox((uint32_t)k, gb, a, 0, k0, k1, x);
-         j = (int)mulhi32(x[0], (uint32_t)s->nE);
+         j = s->mode == 1 ? randmax_from(x[0], x[1], s->nE) : (int)mulhi32(x[0], (uint32_t)s->nE);
       }
       if (corruptTail) { p[3] = h; p[4] = j; } else { p[3] = j; p[4] = t; }
    }
@@ -703,13 +767,18 @@ double orc_train_batch_dfr(int model, int distance, int D, int nE, int nR, doubl
    return total;
 }
 
+/* Study switch (tools/stat_parity_cpu.py): drop the perturbation of w_r / M_r that the entity-side constraint steps
+ * hand to the next batch, to measure what that carry is worth. */
+static int g_dfr_no_carry = 0;
+void orc_set_dfr_no_carry(int on) { g_dfr_no_carry = on; }
+
 void orc_train_epochs_dfr(const orc_sampler* s, int model, int distance, int D, int nE, int nR,
                           double lr, double margin, int batches, int first_epoch, int epochs, uint64_t seed,
                           double* ent, double* rel, double* w, double* loss_out) {
    long batchsize = s->n / batches; /* common/trainer.cpp:70 */
    int* pairs = (int*)malloc(sizeof(int) * 6 * (size_t)(batchsize > 0 ? batchsize : 1));
    size_t we = w_elems(model, D, nR);
-   double* carry = (double*)calloc(we ? we : 1, sizeof(double));
+   double* carry = g_dfr_no_carry ? NULL : (double*)calloc(we ? we : 1, sizeof(double));
    for (int e = 0; e < epochs; e++) {
       double loss = 0;
       for (int b = 0; b < batches; b++) {

@@ -48,6 +48,14 @@ void orc_grad(int model, int distance, int D, double lr,
               const double* ent, const double* rel, const double* w,
               double* ent_next, double* rel_next, double* w_next,
               int head, int tail, int relation, int corrupted);
+/* The accumulation part of orc_grad only (no normalisation tail), and the tail alone: raw + tail == orc_grad,
+ * so next - cur after orc_grad_raw is the pre-normalisation update the CUDA kernels RED into their delta tables. */
+void orc_grad_raw(int model, int distance, int D, double lr,
+                  const double* ent, const double* rel, const double* w,
+                  double* ent_next, double* rel_next, double* w_next,
+                  int head, int tail, int relation, int corrupted);
+void orc_grad_tail(int model, int D, double lr, double* ent_next, double* rel_next, double* w_next,
+                   int head, int tail, int relation);
 
 /* One reference batch: next = cur; for each pair in order: train_kb (common/trainer.cpp:130-149).
  * pairs = n x {h,t,r,h',t',r'}.  Returns the summed loss; losses[k] per pair if not NULL. */
@@ -82,6 +90,10 @@ typedef struct orc_sampler orc_sampler;
 orc_sampler* orc_sampler_create(long n, const int* h, const int* t, const int* r, int nE, int nR, int method);
 void orc_sampler_destroy(orc_sampler*);
 const double* orc_sampler_pr(const orc_sampler*);
+/* mode 0 (default): uniform indices; mode 1: the index distribution of the reference's randMax
+ * (common/utils.cpp:113-120: the wrapped 32-bit product of two rand() values, modulo x), driven by the counter RNG. */
+void orc_sampler_set_mode(orc_sampler*, int mode);
+void orc_randmax_draws(uint64_t seed, int x, long n, int* out);   /* the mode-1 index generator alone */
 /* Restates common/trainer.cpp:78-98 with the counter RNG: sample k of global batch gb draws
  * block = philox(k, gb, attempt, 0; seed): i = mulhi64(x0:x1, n), coin = x2 % 1000, j = mulhi32(x3, nE);
  * resample j = mulhi32(philox(k, gb, a, 0).x0, nE) for a = 1.. while the corrupted triple is in train
@@ -102,6 +114,7 @@ double orc_train_batch_dfr(int model, int distance, int D, int nE, int nR, doubl
 
 /* epochs x batches of orc_sample_batch + orc_train_batch_dfr (the CPU port of the product path;
  * bench.py's cpu_baseline "port" leg).  loss_out[epochs]. */
+void orc_set_dfr_no_carry(int on);   /* study switch: see kb2e_oracle.c */
 void orc_train_epochs_dfr(const orc_sampler*, int model, int distance, int D, int nE, int nR,
                           double lr, double margin, int batches, int first_epoch, int epochs, uint64_t seed,
                           double* ent, double* rel, double* w, double* loss_out);

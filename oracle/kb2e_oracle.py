@@ -89,6 +89,18 @@ class Oracle:
                           _d(en), _d(rn), _d(wn), int(h), int(t), int(r), int(corrupted))
         return en, rn, wn
 
+    def grad_raw(self, model, distance, lr, ent, rel, w, h, t, r, corrupted, tail=False):
+        """next tables after the accumulation part of one gradientUpdate (no normalisation); with
+        tail=True the normalisation tail is applied afterwards (== grad, bitwise)."""
+        ent, rel, w = f64(ent), f64(rel), f64(w)
+        en, rn = ent.copy(), rel.copy()
+        wn = None if w is None else w.copy()
+        self.lib.orc_grad_raw(model, distance, ent.shape[1], C.c_double(lr), _d(ent), _d(rel), _d(w),
+                              _d(en), _d(rn), _d(wn), int(h), int(t), int(r), int(corrupted))
+        if tail:
+            self.lib.orc_grad_tail(model, ent.shape[1], C.c_double(lr), _d(en), _d(rn), _d(wn), int(h), int(t), int(r))
+        return en, rn, wn
+
     def train_batch_ref(self, model, distance, lr, margin, ent, rel, w, pairs):
         ent, rel, w = f64(ent), f64(rel), f64(w)
         pairs = i32(pairs).reshape(-1, 6)
@@ -128,6 +140,11 @@ class Oracle:
     def sampler(self, train, nE, nR, method):
         return Sampler(self, train, nE, nR, method)
 
+    def randmax_draws(self, seed, x, n):
+        out = np.empty(n, dtype=np.int32)
+        self.lib.orc_randmax_draws(C.c_uint64(seed), int(x), C.c_long(n), _i(out))
+        return out
+
     def train_batch_dfr(self, model, distance, lr, margin, ent, rel, w, carry, pairs):
         """In place on ent/rel/w/carry (float64, contiguous).  Returns (loss, n_active)."""
         pairs = i32(pairs).reshape(-1, 6)
@@ -152,6 +169,11 @@ class Sampler:
             self.o.lib.orc_sampler_destroy(self.ptr)
         except Exception:
             pass
+
+    def set_mode(self, mode):
+        """0: uniform indices (default); 1: the index distribution of the reference's randMax."""
+        self.o.lib.orc_sampler_set_mode(self.ptr, int(mode))
+        return self
 
     def pr(self):
         p = self.o.lib.orc_sampler_pr(self.ptr)
@@ -225,6 +247,12 @@ class Reference:
                                       int(zero_work), _d(en), _d(rn), _d(wn), _d(losses))
         assert rc == 0
         return en, rn, wn, losses
+
+    def randmax(self, seed, x, n):
+        """n draws of the reference's own randMax(x) after srand(seed)."""
+        out = np.empty(n, dtype=np.int32)
+        self.lib.ref_randmax(C.c_uint(seed), int(x), C.c_long(n), _i(out))
+        return out
 
     def norm(self, a, ignore_short=True):
         a = f64(a).copy()

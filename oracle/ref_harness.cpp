@@ -12,6 +12,7 @@
 //   ref_grad        -> <model>::Trainer::prebatch + gradientUpdate (transe/trainer.cpp:25, transh/trainer.cpp:11, transr/trainer.cpp:144)
 //   ref_train_batch -> prebatch + N x common::Trainer::train_kb   (common/trainer.cpp:130) -- the reference's sequential batch semantics
 //   ref_norm/ref_norm2 -> common::norm overloads                  (common/utils.cpp:70, :79)
+//   ref_randmax     -> common::randMax                              (common/utils.cpp:113)
 //   ref_rank        -> common::EmbeddingEvaluation::evalCorruption (common/evaluation.cpp:124) per query
 //   ref_train_files -> loadFiles + prepTrain + bfgs (+write)       (common/trainer.cpp:151,34,69,109) timed around bfgs
 //   ref_bern        -> the per-relation statistics loadFiles computes (common/trainer.cpp:171-194)
@@ -347,6 +348,13 @@ void ref_norm2(double* a, double* b, int n, double rate) {
    common::norm(va, vb, rate);
    std::memcpy(a, va.data(), sizeof(double) * n);
    std::memcpy(b, vb.data(), sizeof(double) * n);
+}
+
+// n draws of the reference's own randMax(x) (common/utils.cpp:113-120) after srand(seed): pins the DISTRIBUTION that
+// the counter-RNG emulation (orc_sampler_set_mode(1), KB2E_FLAG_SAMPLER_RANDMAX) reproduces.
+void ref_randmax(unsigned seed, int x, long n, int* out) {
+   srand(seed);
+   for (long i = 0; i < n; i++) out[i] = common::randMax(x);
 }
 
 double ref_vec_len(const double* a, int n) {
