@@ -56,6 +56,7 @@ extern "C" {
 #define KB2E_ERR_CUDA 2   /* CUDA runtime failure (message in kb2e_last_error) */
 #define KB2E_ERR_NO_GPU 3 /* no usable CUDA device: there is NO CPU fallback */
 #define KB2E_ERR_LIMIT 4  /* size outside what the kernels support */
+#define KB2E_ERR_PEER 5   /* partitioned training: a peer GPU never arrived; every rank abandons the launch and reports this */
 
 /* flags */
 #define KB2E_FLAG_RANK_EXACT_ONLY 1u /* rank with the exact fp64 kernel only (no fp32 / tensor-core pre-filter) */
@@ -149,6 +150,10 @@ int kb2e_get_rank_stats(kb2e_ctx* ctx, kb2e_rank_stats* out);
  * arguments: the kernels exchange row requests, rows and updates with posted peer stores / vector
  * REDs over NVLink and synchronise on peer-mapped counters; no host step in between.
  * loss_per_epoch receives this rank's share of the loss (add across ranks).
+ * Failure is a property of the JOB, not of a rank: a rank whose buffers overflowed raises an error word on every
+ * peer, so all ranks return KB2E_ERR_LIMIT together; a rank that never launches (its call failed before the
+ * launch) is noticed by the others at their next cross-GPU barrier, which waits at most KB2E_DIST_TIMEOUT_MS
+ * (environment, default 30000) -- they abandon the launch and return KB2E_ERR_PEER instead of hanging the GPUs.
  * Tables: KB2E_TABLE_ENTITY = this rank's rows [ceil((N_E - rank) / world)][dim] (global ids rank,
  * rank + world, ...); KB2E_TABLE_RELATION = the replica [N_R][dim]. */
 #define KB2E_DIST_HANDLE_BYTES 64

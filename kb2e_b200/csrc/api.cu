@@ -66,6 +66,9 @@ int kb2e_create(const kb2e_config* cfg, kb2e_ctx** out) {
    c->num_sms = prop.multiProcessorCount;
    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+      if (c->ev1) cudaEventDestroy(c->ev1);
+      if (c->ev0) cudaEventDestroy(c->ev0);
+      if (c->stream) cudaStreamDestroy(c->stream);
       delete c;
       return fail(nullptr, KB2E_ERR_CUDA, std::string("kb2e_create: ") + cudaGetErrorString(e));
    }
@@ -121,6 +124,7 @@ int kb2e_set_bern(kb2e_ctx* c, const double* head_mean, const double* tail_mean)
    KB2E_CUDA(c, cudaMemcpyAsync(c->pr, pr.data(), pr.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
    c->have_pr = true;
+   c->thr_valid = false;
    return KB2E_OK;
 }
 
@@ -212,7 +216,10 @@ int kb2e_score(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t* r
    int rc = stage_triples(c, h, t, r, n, &dev);
    if (rc) { pool_free(c, dev); return rc; }
    double* dout = nullptr;
-   KB2E_CUDA(c, pool_alloc(c, &dout, (size_t)n * sizeof(double)));
+   if (cudaError_t e = pool_alloc(c, &dout, (size_t)n * sizeof(double)); e != cudaSuccess) {
+      pool_free(c, dev);
+      return cuda_fail(c, e, "kb2e_score: device buffer");
+   }
    rc = precision == 0 ? train_score32(c, dev, dev + n, dev + 2 * n, n, dout) : rank_score64(c, dev, dev + n, dev + 2 * n, n, dout);
    if (rc == KB2E_OK) {
       cudaError_t e = cudaMemcpyAsync(out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);

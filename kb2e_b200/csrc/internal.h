@@ -33,6 +33,8 @@ struct kb2e_ctx {
    float* dw = nullptr;
    size_t w_row = 0;           // elements per relation in w
    uint32_t* flag = nullptr;   // [nE + nR] stamp (global batch + 1) of the last batch that touched the row
+   uint32_t* cflag = nullptr;  // [nR] TransH: batch a relation row was marked for by an entity-side constraint step (list kernels)
+   bool thr_valid = false;     // triples[i].w holds the corruption threshold of the current pr table
    int* rmin = nullptr;        // [nE] lowest / highest relation id that touched the entity row (TransH/R)
    int* rmax = nullptr;
    bool v32[3] = {false, false, false};  // per table (entity, relation, weights): fp32 copy is current

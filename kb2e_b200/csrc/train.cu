@@ -21,10 +21,13 @@
 //
 // Touched rows, two ways (template parameter LIST):
 //   scan  every group walks its share of the stamp array in phase 2 (batches that touch most of the table);
-//   list  the FIRST toucher of a row in a batch (atomic exchange of the row's stamp) appends the row to a list in
-//         its CTA's shared memory; phase 2 of a CTA then publishes exactly its own list, one row per group, with no
-//         stamp scan and no dependence on where in the row space the touched rows fall.  At FB15k shape a batch
-//         touches ~4,000 of 16,296 rows: ~27 rows per CTA against 48 groups, so the publish is a single, balanced pass.
+//   list  every active sample appends its four rows to a list in its CTA's shared memory (no global traffic); in
+//         phase 2 a CTA walks its own list, one row per group: the group claims the row with an atomic exchange of the
+//         row's stamp -- issued together with the loads of the row and its delta, so the claim costs no extra round
+//         trip -- and publishes it unless another CTA's copy of the same row claimed it first.  No stamp scan, no
+//         dependence on where in the row space the touched rows fall, and the lists are balanced by construction
+//         (every CTA holds the same number of samples).  At FB15k shape: ~10 active samples = ~40 list entries per CTA
+//         against 48 groups, so the publish is a single pass.
 //
 // Work distribution: a "group" of LPS lanes owns one sample (LPS*NV float4 >= row pitch), so a
 // D=50 row uses 16 lanes and a D=100 row 16 lanes x 2 vectors or 32 x 1, whichever lets one batch
@@ -119,13 +122,6 @@ __device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists&
       loss_acc += (double)(a.margin + ep - en);
       active_acc++;
    }
-   // LIST: claim the four rows now (test-and-set of their stamps) so that the round trips overlap the REDs below
-   int my_row = 0;
-   bool first = false;
-   if (LIST && gl < 4) {
-      my_row = gl == 0 ? s.h : (gl == 1 ? s.t : (gl == 2 ? s.c : a.nE + s.r));
-      first = atomicExch(a.flag + my_row, stamp) != stamp;
-   }
    const float lr = a.lr;
    float4 gp[NV], gn[NV];  // lr * x for the positive / negative triple
 #pragma unroll
@@ -199,9 +195,19 @@ __device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists&
    } else if (gl == 3) {
       if (!LIST) a.flag[(size_t)a.nE + s.r] = stamp;
    }
-   if (LIST && first) {
-      if (MODEL == KB2E_MODEL_TRANSE || gl < 3) list_push(L.count + 0, L.ent, L.cap_ent, my_row, a.counters);
-      else list_push(L.count + 1 + (stamp & 1u), L.rel[stamp & 1u], L.cap_rel, my_row, a.counters);
+   if (LIST) {
+      // the sample's rows go on this CTA's lists (duplicates are resolved when the rows are claimed in phase 2)
+      const int n_ent = MODEL == KB2E_MODEL_TRANSE ? 4 : 3;
+      int slot = 0;
+      if (gl == 0) slot = atomicAdd(L.count + 0, n_ent);
+      slot = __shfl_sync(gmask, slot, (threadIdx.x & 31) - gl);
+      if (gl < n_ent) {
+         const int row = gl == 0 ? s.h : (gl == 1 ? s.t : (gl == 2 ? s.c : a.nE + s.r));
+         if (slot + gl < L.cap_ent) L.ent[slot + gl] = row;
+         else a.counters[6] = 1ull;   // cannot happen with the host's capacities; reported as an error if it ever does
+      } else if (gl == 3) {
+         list_push(L.count + 1 + (stamp & 1u), L.rel[stamp & 1u], L.cap_rel, a.nE + s.r, a.counters);
+      }
    }
 }
 
@@ -265,9 +271,13 @@ __device__ __forceinline__ void finish_entity(const TrainArgs& a, const RowLists
             for (int q = 0; q < NV; q++) b[q] = b[q] - b0[q];
             red_row<LPS, NV>(a.dw + (size_t)r * P, P, gl, b);
             if (gl == 0) {
-               if (!LIST) a.flag[(size_t)a.nE + r] = next_stamp;
-               else if (atomicExch(a.flag + a.nE + r, next_stamp) != next_stamp)
+               if (!LIST) {
+                  a.flag[(size_t)a.nE + r] = next_stamp;
+               } else {
+                  // next batch's relation list of this CTA; cflag keeps the mark across the end of a launch
+                  a.cflag[r] = next_stamp;
                   list_push(L.count + 1 + (next_stamp & 1u), L.rel[next_stamp & 1u], L.cap_rel, a.nE + r, a.counters);
+               }
             }
          }
       }
@@ -337,12 +347,14 @@ __device__ __forceinline__ void publish_rows(const TrainArgs& a, long long row_b
    });
 }
 
-// LIST kernels: the CTA's own list, n rows, one row per group and pass (two rows of a group in flight when the list is
-// longer than the CTA has groups).
+// LIST kernels: the CTA's own list, n entries, one per group and pass (two of a group in flight when the list is longer
+// than the CTA has groups).  The claim (atomic exchange of the row's stamp) travels with the loads of the row; a row that
+// another copy of the entry -- in this or in another CTA -- claimed first is dropped.
 template <int MODEL, int LPS, int NV>
 __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists& L, const int* list, int n, int group, int groups,
-                                             uint32_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel) {
+                                             uint32_t stamp, uint32_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel) {
    const int P = a.P;
+   const int leader = (threadIdx.x & 31) - gl;
    auto finish = [&](int r, float4 (&x)[NV], float4 (&d)[NV]) {
       if (r >= a.nE) { finish_relation<MODEL, LPS, NV>(a, r - a.nE, gl, gmask, x, d); trel += (gl == 0); }
       else { finish_entity<MODEL, LPS, NV, true>(a, L, r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
@@ -350,6 +362,11 @@ __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists&
    for (int i = group; i < n; i += 2 * groups) {
       const int r0 = list[i];
       const int r1 = i + groups < n ? list[i + groups] : -1;
+      int mine0 = 0, mine1 = 0;
+      if (gl == 0) {
+         mine0 = atomicExch(a.flag + r0, stamp) != stamp;
+         if (r1 >= 0) mine1 = atomicExch(a.flag + r1, stamp) != stamp;
+      }
       float4 x0[NV], d0[NV], x1[NV], d1[NV];
       load_row<LPS, NV>(a.tab + (size_t)r0 * P, P, gl, x0);
       load_row<LPS, NV>(a.dtab + (size_t)r0 * P, P, gl, d0);
@@ -357,8 +374,10 @@ __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists&
          load_row<LPS, NV>(a.tab + (size_t)r1 * P, P, gl, x1);
          load_row<LPS, NV>(a.dtab + (size_t)r1 * P, P, gl, d1);
       }
-      finish(r0, x0, d0);
-      if (r1 >= 0) finish(r1, x1, d1);
+      mine0 = __shfl_sync(gmask, mine0, leader);
+      mine1 = __shfl_sync(gmask, mine1, leader);
+      if (mine0) finish(r0, x0, d0);
+      if (mine1) finish(r1, x1, d1);
    }
 }
 
@@ -396,18 +415,23 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
    // The sampler does not depend on the embeddings, so each group draws its first sample of the
    // NEXT batch (triple fetch + rejection probes) before waiting at the end-of-batch barrier.
    Pair pre;
+   DrawStage ds;
    const bool has_first = g0 < a.batchsize;
-   if (has_first) pre = draw_pair(a, (uint32_t)g0, gb_first);
+   const uint32_t n_batches = (uint32_t)a.n_epochs * (uint32_t)a.batches;
+   if (has_first) {
+      pre = draw_pair(a, (uint32_t)g0, gb_first);
+      if (n_batches > 1u) draw_begin(a, (uint32_t)g0, gb_first + 1u, ds);   // pipelined from here on (train_device.cuh)
+   }
    const int group = threadIdx.x / LPS;
    if (LIST) {
       if (threadIdx.x < 4) L.count[threadIdx.x] = 0;
       __syncthreads();
       if (MODEL != KB2E_MODEL_TRANSE) {
          // relation rows the LAST launch's final entity phase marked for this launch's first batch (the perturbation of
-         // w_r carried into the next batch's delta): their stamps are already set, so nobody would list them again
+         // w_r carried into the next batch's delta): the list they were put on died with that launch
          const uint32_t s0 = a.stamp_base + 1u;
          for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.nR; r += gridDim.x * blockDim.x)
-            if (__ldcg(a.flag + a.nE + r) == s0) list_push(L.count + 1 + (s0 & 1u), L.rel[s0 & 1u], L.cap_rel, a.nE + r, a.counters);
+            if (__ldcg(a.cflag + r) == s0) list_push(L.count + 1 + (s0 & 1u), L.rel[s0 & 1u], L.cap_rel, a.nE + r, a.counters);
          __syncthreads();
       }
    }
@@ -431,20 +455,23 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
          grid_barrier(a.barrier, bar_target);
          KB2E_TRACE();
          if (a.phase1_only) continue;   // kb2e_train_batch_deltas: the caller reads the raw delta tables (one batch per launch)
+         const bool more = rel_batch + 1u < n_batches;
+         // next batch's sample, stage 2: its probe loads travel with the row loads of the publish below
+         if (has_first && more) draw_probe(a, ds);
          // ---- phase 2 ----
          if (LIST) {
             if (MODEL == KB2E_MODEL_TRANSE) {
-               publish_list<MODEL, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, next_stamp, gl, gmask,
+               publish_list<MODEL, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, next_stamp, gl, gmask,
                                             tent_acc, trel_acc);
                KB2E_TRACE();
             } else {
                int* nrel = L.count + 1 + (stamp & 1u);
-               publish_list<MODEL, LPS, NV>(a, L, L.rel[stamp & 1u], min(*nrel, L.cap_rel), group, groups_per_block, next_stamp, gl, gmask,
+               publish_list<MODEL, LPS, NV>(a, L, L.rel[stamp & 1u], min(*nrel, L.cap_rel), group, groups_per_block, stamp, next_stamp, gl, gmask,
                                             tent_acc, trel_acc);
                grid_barrier(a.barrier, bar_target);   // (its leading bar.sync also ends every read of *nrel)
                if (threadIdx.x == 0) *nrel = 0;
                KB2E_TRACE();
-               publish_list<MODEL, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, next_stamp, gl, gmask,
+               publish_list<MODEL, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, next_stamp, gl, gmask,
                                             tent_acc, trel_acc);
             }
             __syncthreads();
@@ -461,8 +488,12 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
          }
          KB2E_TRACE();
          grid_arrive(a.barrier, bar_target);
-         // the next batch's first sample is drawn while the other CTAs arrive
-         if (has_first && !(ep == a.n_epochs - 1 && batch == a.batches - 1)) pre = draw_pair(a, (uint32_t)g0, gb + 1u);
+         // next batch's sample, stage 3 (registers only unless the candidate has to be redrawn), and stage 1 of the batch
+         // after it: the triple fetch is in flight until the probe stage needs it, one phase from now
+         if (has_first && more) {
+            pre = draw_finish(a, (uint32_t)g0, gb + 1u, ds);
+            if (rel_batch + 2u < n_batches) draw_begin(a, (uint32_t)g0, gb + 2u, ds);
+         }
          grid_wait(a.barrier, bar_target);
       }
       // epoch loss: group leaders -> warp -> block -> one atomic per CTA
@@ -644,6 +675,16 @@ __global__ void identity_kernel(float* w, long long nR, int D, int P) {
    w[i] = (col == row) ? 1.f : 0.f;
 }
 
+// triples[i].w = the corruption threshold of the triple's relation: coin < pr  <=>  coin < ceil(pr) for an integer coin
+// (pr = NaN for a relation without triples compares false: threshold 0), so the staged sampler of train_device.cuh
+// decides the corruption side from the triple record alone.
+__global__ void fill_threshold_kernel(int4* triples, long long n, const double* __restrict__ pr) {
+   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   const double p = pr[triples[i].z];
+   triples[i].w = (p == p) ? (int)fmin(fmax(ceil(p), 0.0), 1001.0) : 0;
+}
+
 __global__ void fill_int_kernel(int* p, long long n, int v) {
    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
    if (i < n) p[i] = v;
@@ -672,6 +713,8 @@ int train_alloc(kb2e_ctx* c) {
       fill_int_kernel<<<blocks_for(c->nE, 256), 256, 0, c->stream>>>(c->rmin, c->nE, 0x7fffffff);
       fill_int_kernel<<<blocks_for(c->nE, 256), 256, 0, c->stream>>>(c->rmax, c->nE, -1);
    }
+   KB2E_CUDA(c, pool_alloc(c, &c->cflag, (size_t)c->nR * sizeof(uint32_t)));
+   KB2E_CUDA(c, cudaMemsetAsync(c->cflag, 0, (size_t)c->nR * sizeof(uint32_t), c->stream));
    KB2E_CUDA(c, pool_alloc(c, &c->barrier, 64));
    KB2E_CUDA(c, pool_alloc(c, &c->counters, 8 * sizeof(unsigned long long)));
    KB2E_CUDA(c, cudaMemsetAsync(c->counters, 0, 8 * sizeof(unsigned long long), c->stream));
@@ -686,6 +729,7 @@ void train_free(kb2e_ctx* c) {
    pool_free(c, c->barrier); pool_free(c, c->loss_dev); pool_free(c, c->counters); pool_free(c, c->pairs_dev);
    pool_free(c, c->ent64); pool_free(c, c->rel64); pool_free(c, c->w64);
    pool_free(c, c->pend);
+   pool_free(c, c->cflag);
 }
 
 int train_set_triples(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t* r, int64_t n) {
@@ -724,6 +768,7 @@ int train_set_triples(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
    if (bad != ~0ull) return fail(c, KB2E_ERR_ARG, "train triple " + std::to_string(bad) + " has an id out of range");
    c->n_train = n;
+   c->thr_valid = false;
    return KB2E_OK;
 }
 
@@ -813,6 +858,7 @@ static void fill_args(kb2e_ctx* c, TrainArgs& a) {
    memset(&a, 0, sizeof(a));
    a.tab = c->tab; a.dtab = c->dtab; a.w = c->w; a.dw = c->dw;
    a.flag = c->flag;
+   a.cflag = c->cflag;
    a.rmin = c->rmin; a.rmax = c->rmax;
    a.triples = c->triples; a.hash = c->hash; a.hash_mask = c->hash_mask; a.pr = c->pr;
    a.barrier = c->barrier; a.loss = c->loss_dev; a.counters = c->counters;
@@ -841,13 +887,14 @@ static int threads_for(int model, int nv) {
 }
 
 template <int MODEL, bool LIST>
-static TrainKernel pick_kernel(int lps, int nv) {
+static TrainKernel pick_kernel(int lps, int nv, int threads) {
 #define KB2E_PICK(L, N, T) if (lps == L && nv == N) return train_kernel<MODEL, L, N, T, LIST>;
    if (MODEL == KB2E_MODEL_TRANSH) {
       KB2E_PICK(8, 1, 512) KB2E_PICK(16, 1, 512) KB2E_PICK(32, 1, 512)
       KB2E_PICK(8, 2, 512) KB2E_PICK(16, 2, 512) KB2E_PICK(32, 2, 512)
    } else {
       KB2E_PICK(8, 1, 1024) KB2E_PICK(16, 1, 1024) KB2E_PICK(32, 1, 1024)
+      if (threads == 640) { KB2E_PICK(8, 2, 640) KB2E_PICK(16, 2, 640) KB2E_PICK(32, 2, 640) }
       KB2E_PICK(8, 2, 768) KB2E_PICK(16, 2, 768) KB2E_PICK(32, 2, 768)
       KB2E_PICK(8, 4, 512) KB2E_PICK(16, 4, 512) KB2E_PICK(32, 4, 512)
    }
@@ -866,7 +913,7 @@ static size_t list_shape(const kb2e_ctx* c, long long batchsize, int groups, int
    const long long S = (long long)groups * ((batchsize + G - 1) / G);
    const bool transe = c->cfg.model == KB2E_MODEL_TRANSE;
    const long long ce = (transe ? 4 : 3) * S;
-   const long long cr = transe ? 0 : std::min<long long>(c->nR, 7 * S);
+   const long long cr = transe ? 0 : 7 * S;   // S phase-1 entries + up to two marks per published entity row (3 S), duplicates included
    const size_t bytes = (size_t)(4 + ce + 2 * cr) * sizeof(int);
    if (bytes > 40 * 1024) return 0;
    if (4 * batchsize > (long long)c->nE + c->nR && !(env && atoi(env) == 1)) return 0;
@@ -932,8 +979,18 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
       a.batchsize = c->n_train / c->cfg.batches;  // common/trainer.cpp:70
    }
    if ((int64_t)a.batchsize >= (1ll << 32)) return fail(c, KB2E_ERR_LIMIT, "batch larger than 2^32 samples");
+   if (!pairs_dev && !c->thr_valid) {
+      fill_threshold_kernel<<<blocks_for(c->n_train, 256), 256, 0, c->stream>>>(c->triples, c->n_train, c->pr);
+      KB2E_CUDA(c, cudaGetLastError());
+      c->thr_valid = true;
+   }
    int lps, nv, threads;
    choose_shape(c, a.batchsize, lps, nv, threads);
+   // two vectors per lane: 640 threads (102 registers, nothing spills) when that many still take the batch in one pass
+   // and the one-barrier kernel (which has no 640-thread form) is not the better choice
+   if (c->cfg.model == KB2E_MODEL_TRANSE && nv == 2 && (long long)c->num_sms * 640 / lps >= a.batchsize &&
+       !(!phase1_only && train_fused_wanted(c, a.batchsize, lps, threads)) && !getenv("KB2E_TRAIN_NO640"))
+      threads = 640;
    if (nv > 4) return fail(c, KB2E_ERR_LIMIT, "embedding size above 512 is not supported by the training kernel");
    TrainKernel k = nullptr;
    const bool transr = c->cfg.model == KB2E_MODEL_TRANSR;   // own kernel: train_transr.cu
@@ -943,9 +1000,9 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    } else {
       list_bytes = list_shape(c, a.batchsize, threads / lps, a.cap_ent, a.cap_rel);
       if (c->cfg.model == KB2E_MODEL_TRANSE)
-         k = list_bytes ? pick_kernel<KB2E_MODEL_TRANSE, true>(lps, nv) : pick_kernel<KB2E_MODEL_TRANSE, false>(lps, nv);
+         k = list_bytes ? pick_kernel<KB2E_MODEL_TRANSE, true>(lps, nv, threads) : pick_kernel<KB2E_MODEL_TRANSE, false>(lps, nv, threads);
       else
-         k = list_bytes ? pick_kernel<KB2E_MODEL_TRANSH, true>(lps, nv) : pick_kernel<KB2E_MODEL_TRANSH, false>(lps, nv);
+         k = list_bytes ? pick_kernel<KB2E_MODEL_TRANSH, true>(lps, nv, threads) : pick_kernel<KB2E_MODEL_TRANSH, false>(lps, nv, threads);
    }
    if (!k && !transr) return fail(c, KB2E_ERR_LIMIT, "no training kernel for this embedding size");
    // row stamps of this launch: stamp_base + 1 ... stamp_base + #batches, never reused by a later launch

@@ -17,6 +17,7 @@ struct TrainArgs {
    float* w;
    float* dw;
    uint32_t* flag;   // [nE + nR] stamp (global batch + 1) of the last batch that touched the row; 0 = never
+   uint32_t* cflag;  // [nR] LIST kernels, TransH: stamp of the batch the relation row was last marked for by an entity-side constraint step
    int* rmin;
    int* rmax;
    const int4* triples;
@@ -241,6 +242,83 @@ __device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32
    return s;
 }
 
+
+// ---- the same sampler in three stages, for software pipelining across the phases of a batch -------------------------
+// draw_pair is a chain of dependent loads (triple -> corruption side -> hash probe): 2-3 L2 round trips.  Run in one piece
+// between "arrive" and "wait" of the end-of-batch barrier it ends up on the critical path of whichever CTA arrives last.
+// Split in three, every load is issued one phase before its value is needed:
+//   draw_begin    counter RNG -> triple index, candidate entity; ISSUES the triple fetch.  triples[i].w holds the
+//                 relation's corruption threshold ceil(pr[r]) (coin < pr  <=>  coin < ceil(pr) for an integer coin), so
+//                 the corruption side needs no second dependent load
+//   draw_probe    corruption side -> key of the candidate negative; ISSUES the first two slots of its probe sequence
+//   draw_finish   decides from the two slots (empty / match); only an unresolved sequence or a hit (candidate is a known
+//                 triple: resample, common/trainer.cpp:89-96) falls back to the loop of draw_pair.  Same samples, bit for bit.
+struct DrawStage {
+   int4 tr;
+   uint64_t v0, v1;
+   int j;   // candidate entity | coin << 24
+};
+
+__device__ __forceinline__ void draw_begin(const TrainArgs& a, uint32_t k, uint32_t gb, DrawStage& d) {
+   if (a.pairs != nullptr) return;
+   uint32_t x[4];
+   philox4x32(k, gb, 0u, 0u, a.seed_lo, a.seed_hi, x);
+   uint64_t i = mulhi64(((uint64_t)x[0] << 32) | x[1], (uint64_t)a.n_train);
+   int j = (int)mulhi32(x[3], (uint32_t)a.nE);
+   if (a.flags & KB2E_FLAG_SAMPLER_RANDMAX) {
+      uint32_t y[4];
+      philox4x32(k, gb, 0u, 1u, a.seed_lo, a.seed_hi, y);
+      i = (uint64_t)randmax_from(x[0], x[1], (int)a.n_train);
+      j = randmax_from(y[0], y[1], a.nE);
+   }
+   d.j = j | (int)((x[2] % 1000u) << kEntityBits);
+   d.tr = __ldg(a.triples + i);
+}
+
+__device__ __forceinline__ uint64_t draw_key(const DrawStage& d, bool& corruptTail) {
+   const int j = d.j & ((1 << kEntityBits) - 1), coin = (int)((uint32_t)d.j >> kEntityBits);
+   corruptTail = coin < d.tr.w;
+   return corruptTail ? pack_triple(d.tr.x, d.tr.z, j) : pack_triple(j, d.tr.z, d.tr.y);
+}
+
+__device__ __forceinline__ void draw_probe(const TrainArgs& a, DrawStage& d) {
+   if (a.pairs != nullptr) return;
+   bool ct;
+   const uint64_t slot = mix64(draw_key(d, ct)) & a.hash_mask;
+   d.v0 = __ldg(a.hash + slot);
+   d.v1 = __ldg(a.hash + ((slot + 1) & a.hash_mask));
+}
+
+__device__ __forceinline__ Pair draw_finish(const TrainArgs& a, uint32_t k, uint32_t gb, const DrawStage& d) {
+   if (a.pairs != nullptr) return draw_pair(a, k, gb);
+   Pair s;
+   s.h = d.tr.x; s.t = d.tr.y; s.r = d.tr.z;
+   const uint64_t key = draw_key(d, s.corruptTail);
+   int j = d.j & ((1 << kEntityBits) - 1);
+   bool hit;
+   if (d.v0 == key || (d.v0 != kEmptyKey && d.v1 == key)) hit = true;
+   else if (d.v0 == kEmptyKey || d.v1 == kEmptyKey) hit = false;
+   else {   // two occupied slots of other keys: walk on
+      uint64_t slot = (mix64(key) + 2) & a.hash_mask;
+      while (true) {
+         const uint64_t v = __ldg(a.hash + slot);
+         if (v == key) { hit = true; break; }
+         if (v == kEmptyKey) { hit = false; break; }
+         slot = (slot + 1) & a.hash_mask;
+      }
+   }
+   if (hit) {
+      for (uint32_t att = 1; att < 64; att++) {
+         uint32_t x[4];
+         philox4x32(k, gb, att, 0u, a.seed_lo, a.seed_hi, x);
+         j = (a.flags & KB2E_FLAG_SAMPLER_RANDMAX) ? randmax_from(x[0], x[1], a.nE) : (int)mulhi32(x[0], (uint32_t)a.nE);
+         const uint64_t key2 = s.corruptTail ? pack_triple(s.h, s.r, j) : pack_triple(j, s.r, s.t);
+         if (!hash_contains(a.hash, a.hash_mask, key2)) break;
+      }
+   }
+   s.c = j;
+   return s;
+}
 
 // ---- phase-2 row walk ------------------------------------------------------------------------------
 // Every group owns a contiguous range of rows.  The stamps of LPS rows are fetched with one coalesced

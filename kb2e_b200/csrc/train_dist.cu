@@ -74,7 +74,12 @@ struct DistArgs {
    int rank, world, wshift;
    int rows_local;
    uint32_t xbase;                     // value of every rank's cross-GPU counter when this launch starts
+   unsigned long long timeout_ns;      // longest wait for the peers at one cross-GPU barrier before the launch is abandoned
 };
+
+// words of the 64-byte cross-GPU block at off_xbar: [0] arrival counter, [4] abort word (a peer gave up: stop polling),
+// [8] error word (a peer dropped samples / updates in this launch: every rank must report it)
+constexpr int kXbarAbort = 4, kXbarError = 8;
 
 // value of entity row e as this rank sees it in phase 1b: its own table, or the cache slot the owner filled
 __device__ __forceinline__ const float* ent_row(const DistArgs& a, int e, long long slot) {
@@ -103,7 +108,11 @@ __device__ __forceinline__ float* rel_delta(const DistArgs& a, int r, uint8_t*& 
 
 // all CTAs of this GPU, then all GPUs, then all CTAs again (release / acquire at system scope).  publish: after this
 // GPU's CTAs have all arrived, its per-owner inbox counts are written to the owners before the cross-GPU signal.
-__device__ __forceinline__ void cross_barrier(const DistArgs& a, uint32_t& ltarget, uint32_t& xtarget, bool publish = false) {
+// The wait for the peers is BOUNDED: a peer that never launched (its host call failed) or died would otherwise hang every
+// GPU of the box until an operator resets it.  The poller gives up when a peer has raised the abort word of this arena
+// or when timeout_ns have passed; it then raises the abort word on every peer, records the failure in share[3] and the
+// whole grid returns (false): the host reports KB2E_ERR_PEER and the context refuses further partitioned calls.
+__device__ __forceinline__ bool cross_barrier(const DistArgs& a, uint32_t& ltarget, uint32_t& xtarget, bool publish = false) {
    __threadfence_system();   // this thread's peer stores / REDs are performed before it arrives
    grid_barrier(a.local_bar, ltarget);
    if (blockIdx.x == 0) {
@@ -123,14 +132,33 @@ __device__ __forceinline__ void cross_barrier(const DistArgs& a, uint32_t& ltarg
             asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p), "r"(1u) : "memory");
          }
          const uint32_t* mine = reinterpret_cast<const uint32_t*>(a.arena[a.rank] + a.off_xbar);
-         uint32_t v;
-         do {
+         uint32_t v, polls = 0;
+         unsigned long long t_start = 0;
+         bool dead = false;
+         while (true) {
             asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-         } while ((int32_t)(v - xtarget) < 0);
+            if ((int32_t)(v - xtarget) >= 0) break;
+            if ((++polls & 255u) == 0u) {
+               uint32_t ab;
+               asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(ab) : "l"(mine + kXbarAbort) : "memory");
+               unsigned long long now;
+               asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+               if (t_start == 0) t_start = now;
+               if (ab != 0u || now - t_start > a.timeout_ns) { dead = true; break; }
+            }
+         }
+         if (dead) {
+            for (int g = 0; g < a.world; g++) {
+               uint32_t* p = reinterpret_cast<uint32_t*>(a.arena[g] + a.off_xbar) + kXbarAbort;
+               asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(1u) : "memory");
+            }
+            __stcg(a.share + 3, 1u);
+         }
          asm volatile("fence.acq_rel.sys;" ::: "memory");
       }
    }
    grid_barrier(a.local_bar, ltarget);
+   return __ldcg(a.share + 3) == 0u;
 }
 
 template <int LPS, int NV>
@@ -225,7 +253,7 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
    const long long T = (long long)gridDim.x * blockDim.x;
    const long long t0 = (long long)threadIdx.x * gridDim.x + blockIdx.x;
    // peers may still be zeroing / publishing from the previous launch
-   cross_barrier(a, ltarget, xtarget);
+   if (!cross_barrier(a, ltarget, xtarget)) return;
 
    for (int ep = 0; ep < b.n_epochs; ep++) {
       double loss_acc = 0.0;
@@ -275,7 +303,7 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
             }
          }
          KB2E_DTRACE();
-         cross_barrier(a, ltarget, xtarget);
+         if (!cross_barrier(a, ltarget, xtarget)) return;
          KB2E_DTRACE();
          // ---- phase 1s: serve the peers' requests: own row -> the requester's cache slot ----
          if (a.world > 1) {
@@ -301,7 +329,7 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
             });
          }
          KB2E_DTRACE();
-         cross_barrier(a, ltarget, xtarget);
+         if (!cross_barrier(a, ltarget, xtarget)) return;
          KB2E_DTRACE();
          // ---- phase 1b: score + accumulate, everything local ----
          const long long my_count = min((long long)__ldcg(my_cnt), a.max_share);
@@ -317,7 +345,7 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
             dist_process_pair<LPS, NV>(a, s, j, gl, gmask, stamp, loss_acc, active_acc);
          }
          KB2E_DTRACE();
-         cross_barrier(a, ltarget, xtarget);
+         if (!cross_barrier(a, ltarget, xtarget)) return;
          KB2E_DTRACE();
          // ---- phase 2a: append the staged rows to their owners' inboxes (sequential posted stores) ----
          {
@@ -338,6 +366,7 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
                   a.share[2] = 1u;   // more staged rows for one owner than the inbox holds: reported by the host
                }
                store_row<LPS, NV>(a.stage + (size_t)r * P, P, gl, z);
+               if (gl == 0) a.sflag[r] = 0;   // 8-bit stamps recur every 255 batches: a pushed row must not look staged again
             };
             for (int o = 0; o < a.world; o++) {
                if (o == a.rank) continue;   // own rows never pass through the staging table
@@ -369,7 +398,7 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
             }
          }
          KB2E_DTRACE();
-         cross_barrier(a, ltarget, xtarget, true);
+         if (!cross_barrier(a, ltarget, xtarget, true)) return;
          KB2E_DTRACE();
          // ---- phase 2a': add the inbox entries into the own delta tables (local REDs), stamp the rows ----
          if (a.world > 1) {
@@ -424,6 +453,7 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
                   store_row<LPS, NV>(dtab + (size_t)r * P, P, gl, d);
                   norm_row<LPS, NV>(x, true, gmask);   // transe/trainer.cpp:44-45
                   store_row<LPS, NV>(tab + (size_t)r * P, P, gl, x);
+                  if (gl == 0) me[a.off_flag + r] = 0;   // stamp cleared: only rows with a real delta are published (and counted)
                   tent_acc += (gl == 0);
                };
                publish(r0, x0, d0);
@@ -440,13 +470,14 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
 #pragma unroll
             for (int q = 0; q < NV; q++) { x[q] = x[q] + d[q]; d[q] = f4(0.f); }
             store_row<LPS, NV>(drel + (size_t)r * P, P, gl, d);
+            if (gl == 0) me[a.off_rflag + r] = 0;
             norm_row<LPS, NV>(x, true, gmask);   // transe/trainer.cpp:43
             for (int g = 0; g < a.world; g++)
                store_row<LPS, NV>(reinterpret_cast<float*>(a.arena[g] + a.off_rel) + (size_t)r * P, P, gl, x);
             trel_acc += (gl == 0);
          }
          KB2E_DTRACE();
-         cross_barrier(a, ltarget, xtarget);
+         if (!cross_barrier(a, ltarget, xtarget)) return;
       }
       double v = (gl == 0) ? loss_acc : 0.0;
 #pragma unroll
@@ -459,6 +490,20 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
          if (t != 0.0) atomicAdd(b.loss + ep, t);
       }
       __syncthreads();
+   }
+   // one status for the whole job: a rank that dropped samples or updates (overflow flag share[2], set only where the
+   // overflow happened) raises the error word of every peer before the last cross-GPU barrier; afterwards every rank
+   // folds its own error word into share[2], so that all ranks return the same error (the owner whose updates were
+   // dropped by a sender would otherwise report success with silently wrong tables)
+   if (blockIdx.x == 0 && (int)threadIdx.x < a.world && __ldcg(a.share + 2) != 0u) {
+      uint32_t* p = reinterpret_cast<uint32_t*>(a.arena[threadIdx.x] + a.off_xbar) + kXbarError;
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(1u) : "memory");
+   }
+   if (!cross_barrier(a, ltarget, xtarget)) return;
+   if (blockIdx.x == 0 && threadIdx.x == 0) {
+      uint32_t e;
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(e) : "l"(reinterpret_cast<const uint32_t*>(me + a.off_xbar) + kXbarError) : "memory");
+      if (e != 0u) a.share[2] = 1u;
    }
    uint32_t c0 = (gl == 0) ? active_acc : 0u, c1 = tent_acc, c2 = trel_acc;
 #pragma unroll
@@ -475,11 +520,12 @@ __global__ void __launch_bounds__(kDistThreads, 1) train_dist_kernel(const __gri
 }
 
 // init: N(0, (1/D)^2) keyed by the GLOBAL row id, so every world size starts from the same tables
-__global__ void dist_init_kernel(float* tab, long long rows_local, int rank, int world, int D, int P, uint32_t k0, uint32_t k1) {
+__global__ void dist_init_kernel(float* tab, long long rows_local, int rank, int world, long long first_row, int D, int P, uint32_t k0,
+                                 uint32_t k1) {
    long long lrow = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
    int lane = threadIdx.x & 31;
    if (lrow >= rows_local) return;
-   long long row = lrow * world + rank;
+   long long row = first_row + lrow * world + rank;   // row id in the unified row space of the single-GPU tables
    float* p = tab + lrow * P;
    float s2 = 0.f;
    const float sigma = 1.0f / (float)D;
@@ -548,6 +594,7 @@ struct DistState {
    unsigned char* peers[kMaxPeers] = {};
    bool connected = false;
    uint32_t xcount = 0;   // cross-GPU barrier arrivals so far (identical on every rank: the counters are never reset)
+   bool broken = false;   // a launch was abandoned (a peer never arrived): the barrier counters of the ranks no longer agree
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -565,7 +612,9 @@ int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) 
       return fail(c, KB2E_ERR_ARG, "kb2e_dist_setup: call kb2e_set_train_triples first (the batch size sizes the exchange buffers)");
    int rc = train_alloc(c);   // barrier counter, counters, pr
    if (rc) return rc;
+   kb2e_dist_teardown(c);     // a second setup replaces the first one: release its arena, staging buffers and IPC mappings
    DistState* d = new DistState();
+   c->dist = d;               // owned by the context from here on: an error below is cleaned up by kb2e_dist_teardown / kb2e_destroy
    d->rank = rank; d->world = world;
    while ((1 << d->wshift) < world) d->wshift++;
    d->rows_local = ((long long)c->nE - rank + world - 1) / world;
@@ -615,8 +664,6 @@ int kb2e_dist_setup(kb2e_ctx* c, int32_t rank, int32_t world, void* handle_out) 
    KB2E_CUDA(c, cudaIpcGetMemHandle(&h, d->arena));
    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
    memcpy(handle_out, &h, sizeof(h));
-   delete c->dist;
-   c->dist = d;
    return KB2E_OK;
 }
 
@@ -642,10 +689,12 @@ int kb2e_dist_init_embeddings(kb2e_ctx* c) {
    DistState* d = c->dist;
    uint32_t k0 = (uint32_t)c->cfg.seed, k1 = (uint32_t)(c->cfg.seed >> 32);
    dist_init_kernel<<<dblocks(d->rows_local * 32, 256), 256, 0, c->stream>>>(
-      reinterpret_cast<float*>(d->arena + d->off_tab), d->rows_local, d->rank, d->world, c->D, c->P, k0, k1);
-   // relation replica: rows nE .. nE+nR-1 of the global row space, identical on every rank
+      reinterpret_cast<float*>(d->arena + d->off_tab), d->rows_local, d->rank, d->world, 0, c->D, c->P, k0, k1);
+   // relation replica: rows nE .. nE+nR-1 of the unified row space with the SAME key, identical on every rank and
+   // identical to kb2e_init_embeddings (train.cu:init_rows_kernel), so partitioned and single-GPU runs of one seed
+   // start from the same tables
    dist_init_kernel<<<dblocks((long long)c->nR * 32, 256), 256, 0, c->stream>>>(
-      reinterpret_cast<float*>(d->arena + d->off_rel) - (size_t)0, c->nR, 0, 1, c->D, c->P, k0 ^ 0x9e3779b9u, k1);
+      reinterpret_cast<float*>(d->arena + d->off_rel), c->nR, 0, 1, (long long)c->nE, c->D, c->P, k0, k1);
    KB2E_CUDA(c, cudaGetLastError());
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
    return KB2E_OK;
@@ -688,10 +737,15 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    KB2E_CUDA(c, cudaSetDevice(c->device));
    DistState* d = c->dist;
    if (!d->connected) return fail(c, KB2E_ERR_ARG, "kb2e_dist_train_epochs: call kb2e_dist_connect first");
+   if (d->broken)
+      return fail(c, KB2E_ERR_PEER, "kb2e_dist_train_epochs: an earlier launch was abandoned because a peer never arrived; the ranks are out of "
+                                    "step -- call kb2e_dist_teardown on every rank and set the job up again");
    if (!c->triples || c->n_train == 0 || !c->have_pr) return fail(c, KB2E_ERR_ARG, "kb2e_dist_train_epochs: set the train triples and bern statistics first");
    if (n_epochs <= 0) return KB2E_OK;
    if (n_epochs > c->loss_cap) {
       cudaFree(c->loss_dev);
+      c->loss_dev = nullptr;
+      c->loss_cap = 0;
       KB2E_CUDA(c, cudaMalloc(&c->loss_dev, (size_t)n_epochs * sizeof(double)));
       c->loss_cap = n_epochs;
    }
@@ -738,11 +792,19 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    else if (lps == 32 && nv == 2) k = train_dist_kernel<32, 2>;
    if (!k) return fail(c, KB2E_ERR_LIMIT, "partitioned training supports embedding sizes up to 256");
    // the peer-mapped cross-GPU counters are monotonic across launches (a reset could wipe a fast peer's
-   // arrival); every rank runs the same barrier sequence, so the start value is known on the host
+   // arrival); every rank runs the same barrier sequence, so the start value is known on the host.  Everything that can
+   // fail on the host happens BEFORE the counter is advanced; from the launch on, a rank that does not make it is
+   // noticed by its peers through the bounded wait of cross_barrier.
    a.xbase = d->xcount;
-   d->xcount += (uint32_t)d->world * (1u + 5u * (uint32_t)c->cfg.batches * (uint32_t)n_epochs);
+   {
+      const char* env = getenv("KB2E_DIST_TIMEOUT_MS");   // per cross-GPU barrier; default 30 s
+      const double ms = env ? atof(env) : 30000.0;
+      a.timeout_ns = (unsigned long long)(std::max(1.0, ms) * 1e6);
+   }
    KB2E_CUDA(c, cudaMemsetAsync(c->barrier, 0, 64, c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->loss_dev, 0, (size_t)n_epochs * sizeof(double), c->stream));
+   // this rank's error word: the peers write it only before the last barrier of a launch they share with this rank
+   KB2E_CUDA(c, cudaMemsetAsync(d->arena + d->off_xbar + kXbarError * sizeof(uint32_t), 0, sizeof(uint32_t), c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
    const char* trace_path = getenv("KB2E_TRAIN_TRACE");
    unsigned long long* trace_dev = nullptr;
@@ -753,7 +815,13 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    }
    void* params[] = {&a};
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-   KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(kDistThreads), params, 0, c->stream));
+   if (cudaError_t e = cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(kDistThreads), params, 0, c->stream); e != cudaSuccess) {
+      d->broken = true;   // the peers will time out waiting for this rank
+      if (trace_dev) cudaFree(trace_dev);
+      return cuda_fail(c, e, "kb2e_dist_train_epochs: launch");
+   }
+   // barrier sequence of one launch: 1 opening + 5 per batch + 1 closing (status exchange)
+   d->xcount += (uint32_t)d->world * (2u + 5u * (uint32_t)c->cfg.batches * (uint32_t)n_epochs);
    KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
    std::vector<double> loss(n_epochs);
    unsigned long long cnt[5];
@@ -779,9 +847,14 @@ int kb2e_dist_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, d
    c->tstats.launches += 1;
    c->tstats.samples += cnt[4] - d->samples_seen;   // samples whose head this rank owns (counted by the kernel)
    d->samples_seen = cnt[4];
+   if (share_host[3]) {
+      d->broken = true;
+      return fail(c, KB2E_ERR_PEER, "kb2e_dist_train_epochs: a peer GPU did not arrive at a cross-GPU barrier within the time limit (its call failed or it "
+                                    "never launched); the launch was abandoned on every rank -- results of this call are invalid");
+   }
    if (share_host[2])
       return fail(c, KB2E_ERR_LIMIT, "kb2e_dist_train_epochs: the heads (or the remote rows) of a batch are too unevenly spread over the ranks for the "
-                                     "exchange buffers; samples or updates were dropped -- results of this call are invalid");
+                                     "exchange buffers; samples or updates were dropped on at least one rank -- results of this call are invalid on every rank");
    c->tstats.active = cnt[0];
    c->tstats.touched_ent = cnt[1];
    c->tstats.touched_rel = cnt[2];

@@ -232,7 +232,7 @@ bool train_fused_wanted(const kb2e_ctx* c, long long batchsize, int lps, int thr
    const char* env = getenv("KB2E_TRAIN_FUSED");   // 0: never, 1: whenever a batch fits in one pass (tuning aid)
    if (env && atoi(env) == 0) return false;
    if (c->cfg.model != KB2E_MODEL_TRANSE) return false;
-   if (threads != 1024 && threads != 768 && threads != 512) return false;   // KB2E_TRAIN_THREADS override without an instantiation
+   if (threads != 1024 && threads != 768 && threads != 512) return false;   // (640: the list kernel of train.cu)   // KB2E_TRAIN_THREADS override without an instantiation
    const long long groups = (long long)c->num_sms * (threads / lps);
    if (env && atoi(env) == 1) return batchsize <= groups;
    return 2 * batchsize <= groups;

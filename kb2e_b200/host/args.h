@@ -30,6 +30,9 @@ struct EmbeddingArguments {
    unsigned int seed;
    // GPU-only (not in the reference; never printed in the Options banner)
    int device = 0;
+   // sampler indices: 0 = uniform (default), 1 = the index distribution of the reference's randMax
+   // (common/utils.cpp:113-120), for trained-model parity with the shipped reference
+   int samplerRandMax = 0;
 
    EmbeddingArguments();
    std::string to_string() const;  // the "Options: [...]" banner, byte-compatible with the reference

@@ -140,10 +140,12 @@ bool writeTable(const std::string& path, size_t rows, size_t cols, const double*
          line.push_back('\t');
       }
       line.push_back('\n');
-      fwrite(line.data(), 1, line.size(), f);
+      if (fwrite(line.data(), 1, line.size(), f) != line.size()) {   // disk full, quota, ...
+         fclose(f);
+         return false;
+      }
    }
-   fclose(f);
-   return true;
+   return fclose(f) == 0;
 }
 
 bool fileExists(const std::string& path) {

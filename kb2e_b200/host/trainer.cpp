@@ -97,7 +97,7 @@ void Trainer::prepTrain() {
    cfg.rate = args_.learningRate;
    cfg.margin = args_.margin;
    cfg.seed = args_.seed;
-   cfg.flags = 0;
+   cfg.flags = args_.samplerRandMax ? KB2E_FLAG_SAMPLER_RANDMAX : 0u;
    cfg.reserved = 0;
    if (kb2e_create(&cfg, &ctx_) != KB2E_OK) {
       printf("kb2e_create failed: %s\n", kb2e_last_error(NULL));
@@ -154,21 +154,25 @@ void Trainer::train() {
 void Trainer::write() {
    const std::string suffix = std::string(".") + methodName(args_.method);
    const int64_t D = args_.embeddingSize;
+   // every table is checked: a failed or short write (disk full, permissions) must not exit 0 with a partial checkpoint
+   auto save = [](const std::string& path, size_t rows, size_t cols, const double* data) {
+      if (!writeTable(path, rows, cols, data)) {
+         printf("Could not write to: %s\n", path.c_str());
+         exit(2);
+      }
+   };
    std::vector<double> table((size_t)numRelations_ * D);
    if (kb2e_download(ctx_, KB2E_TABLE_RELATION, table.data(), numRelations_, D)) die("kb2e_download");
-   if (!writeTable(args_.outputDir + "/relation2vec" + suffix, (size_t)numRelations_, (size_t)D, table.data())) {
-      printf("Could not write to: %s\n", args_.outputDir.c_str());
-      exit(2);
-   }
+   save(args_.outputDir + "/relation2vec" + suffix, (size_t)numRelations_, (size_t)D, table.data());
    table.resize((size_t)numEntities_ * D);
    if (kb2e_download(ctx_, KB2E_TABLE_ENTITY, table.data(), numEntities_, D)) die("kb2e_download");
-   writeTable(args_.outputDir + "/entity2vec" + suffix, (size_t)numEntities_, (size_t)D, table.data());
+   save(args_.outputDir + "/entity2vec" + suffix, (size_t)numEntities_, (size_t)D, table.data());
    if (model_ != KB2E_MODEL_TRANSE) {
       // transh/trainer.cpp:94-105: one row per relation; transr/trainer.cpp:128-142: D rows per relation
       const int64_t rows = model_ == KB2E_MODEL_TRANSH ? numRelations_ : (int64_t)numRelations_ * D;
       table.resize((size_t)rows * D);
       if (kb2e_download(ctx_, KB2E_TABLE_WEIGHTS, table.data(), rows, D)) die("kb2e_download");
-      writeTable(args_.outputDir + "/weights" + suffix, (size_t)rows, (size_t)D, table.data());
+      save(args_.outputDir + "/weights" + suffix, (size_t)rows, (size_t)D, table.data());
    }
 }
 

@@ -50,13 +50,22 @@ class PartitionedTrainer:
 
     def train_epochs(self, first_epoch, n_epochs):
         """Collective.  Returns the global per-epoch loss."""
-        loss = self.ctx.dist_train_epochs(first_epoch, n_epochs)
+        err = None
+        try:
+            loss = self.ctx.dist_train_epochs(first_epoch, n_epochs)
+        except Exception as e:   # raised on every rank below, after the ranks have agreed that the call failed
+            err, loss = e, np.zeros(n_epochs)
         if self.world > 1:
             import torch
             import torch.distributed as dist
-            t = torch.from_numpy(loss.copy()).cuda()
-            dist.all_reduce(t)
-            loss = t.cpu().numpy()
+            t = torch.from_numpy(np.concatenate([loss, [1.0 if err is not None else 0.0]])).cuda()
+            dist.all_reduce(t)   # one collective for the loss and the status: no rank is left waiting in it
+            t = t.cpu().numpy()
+            loss, failed = t[:-1], t[-1] > 0
+            if failed and err is None:
+                err = RuntimeError("partitioned training failed on another rank")
+        if err is not None:
+            raise err
         return loss
 
     def gather_global(self):

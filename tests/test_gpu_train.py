@@ -141,7 +141,10 @@ def test_pair_gradient_matches_reference_before_normalisation(gpu_lib, golden, o
     nE, nR = ent.shape[0], rel.shape[0]
     with make_ctx(model, D, nE, nR, distance=dist, rate=LR, margin=100.0) as ctx:
         upload_tables(ctx, ent, rel, w)
-        for pi in range(6):
+        # pairs whose negative really differs from the positive (with 48 entities the fixture's random corrupting entity
+        # sometimes IS the replaced one: the two updates then cancel exactly)
+        usable = [k for k in range(len(g["pairs"])) if tuple(g["pairs"][k][:3]) != tuple(g["pairs"][k][3:])][:6]
+        for pi in usable:
             pair = g["pairs"][pi:pi + 1]
             de, dr, dw, loss, active = ctx.train_batch_deltas(pair)
             assert active == 1
@@ -154,13 +157,13 @@ def test_pair_gradient_matches_reference_before_normalisation(gpu_lib, golden, o
                 if w is not None:
                     ww += wn - w
             for got, want in ((de, we), (dr, wr)) + (((dw.reshape(ww.shape), ww),) if w is not None else ()):
-                scale = np.abs(want).max()
-                assert scale > 1e-4                                   # something moved by about lr
-                assert np.abs(got - want).max() <= 1e-5 * scale + 1e-9, (ci, pi, np.abs(got - want).max(), scale)
+                scale = max(np.abs(want).max(), LR)   # (the two L1 updates of a relation row may cancel exactly)
+                assert np.abs(got - want).max() <= 1e-5 * scale, (ci, pi, np.abs(got - want).max(), scale)
+            assert np.abs(we).max() > 1e-4   # something moved by about lr
         # the hook leaves the tables as they were, and its delta tables clean for the next call
         ge, gr, gw = download_tables(ctx)
         assert np.array_equal(ge, ent) and np.array_equal(gr, rel)
-        de2, dr2, dw2, _, _ = ctx.train_batch_deltas(g["pairs"][5:6])
+        de2, dr2, dw2, _, _ = ctx.train_batch_deltas(g["pairs"][usable[-1]:usable[-1] + 1])
         assert np.array_equal(de2, de) and np.array_equal(dr2, dr)
 
 
@@ -359,3 +362,23 @@ def test_partitioned_kernel_world1_matches_single_gpu_kernel(gpu_lib):
     assert np.allclose(loss1, loss2, rtol=1e-4)
     assert np.abs(e1 - e2).max() < 5e-3 and np.abs(e1 - e2).mean() < 2e-5
     assert np.abs(r1 - r2).max() < 5e-3
+
+
+def test_partitioned_init_equals_single_gpu_init(gpu_lib):
+    """kb2e_dist_init_embeddings seeds entity AND relation rows by their row id in the unified row space with the
+    context's key, exactly as kb2e_init_embeddings does: a partitioned run and a single-GPU run of one seed start from
+    the same tables."""
+    from kb2e_b200 import kg, TABLE_ENTITY, TABLE_RELATION
+    from kb2e_b200.partitioned import PartitionedTrainer
+    g = kg.make_kg("tiny", seed=3)
+    nE, nR, D = g["nE"], g["nR"], 24
+    cfg = dict(method=0, distance=1, batches=10, rate=LR, margin=1.0, seed=0x5EED1234)
+    with make_ctx("transe", D, nE, nR, **cfg) as ctx:
+        ctx.init_embeddings()
+        e1, r1 = ctx.download(TABLE_ENTITY), ctx.download(TABLE_RELATION)
+    pt = PartitionedTrainer(D, nE, nR, 0, 1, 0, **cfg)
+    pt.set_training_set(g["train"], None, None)
+    pt.init_embeddings()
+    e2, r2 = pt.gather_global()
+    pt.close()
+    assert np.array_equal(e1, e2) and np.array_equal(r1, r2)
