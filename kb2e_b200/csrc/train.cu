@@ -352,9 +352,19 @@ __device__ __forceinline__ void publish_rows(const TrainArgs& a, long long row_b
 // another copy of the entry -- in this or in another CTA -- claimed first is dropped.
 template <int MODEL, int LPS, int NV>
 __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists& L, const int* list, int n, int group, int groups,
-                                             uint32_t stamp, uint32_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel) {
+                                             uint32_t stamp, uint32_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel,
+                                             unsigned long long* fine = nullptr) {
    const int P = a.P;
    const int leader = (threadIdx.x & 31) - gl;
+   // tuning aid (KB2E_TRAIN_TRACE_FINE): thread 0 stamps its own group's claim / first row / second row
+   auto mark = [&](int k, unsigned long long extra) {
+      if (fine != nullptr && threadIdx.x == 0) {
+         unsigned long long t_;
+         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+         fine[k] = t_;
+         fine[k + 3] = extra;
+      }
+   };
    auto finish = [&](int r, float4 (&x)[NV], float4 (&d)[NV]) {
       if (r >= a.nE) { finish_relation<MODEL, LPS, NV>(a, r - a.nE, gl, gmask, x, d); trel += (gl == 0); }
       else { finish_entity<MODEL, LPS, NV, true>(a, L, r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
@@ -376,8 +386,11 @@ __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists&
       }
       mine0 = __shfl_sync(gmask, mine0, leader);
       mine1 = __shfl_sync(gmask, mine1, leader);
+      mark(0, (unsigned long long)n);
       if (mine0) finish(r0, x0, d0);
+      mark(1, (unsigned long long)(mine0 + 2 * mine1));
       if (mine1) finish(r1, x1, d1);
+      mark(2, (unsigned long long)(r1 >= 0));
    }
 }
 
@@ -461,8 +474,13 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
          // ---- phase 2 ----
          if (LIST) {
             if (MODEL == KB2E_MODEL_TRANSE) {
+               unsigned long long* fine = nullptr;
+               if ((a.flags & 0x80000000u) && a.trace != nullptr && trace_slot + 8 < kTraceSlots) {
+                  fine = a.trace + (size_t)blockIdx.x * kTraceSlots + trace_slot;
+                  trace_slot += 6;
+               }
                publish_list<MODEL, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, next_stamp, gl, gmask,
-                                            tent_acc, trel_acc);
+                                            tent_acc, trel_acc, fine);
                KB2E_TRACE();
             } else {
                int* nrel = L.count + 1 + (stamp & 1u);
@@ -525,10 +543,17 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
 }
 
 // ---- test hooks ---------------------------------------------------------------------------------
+// The sample through BOTH forms of the sampler -- draw_pair (one piece: the TransR, one-barrier and partitioned kernels)
+// and the three pipelined stages of train_kernel; a disagreement poisons the row so that the parity test fails loudly.
 __global__ void sample_kernel(const TrainArgs a, uint32_t gb, long long count, int32_t* out) {
    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
    if (k >= count) return;
    Pair s = draw_pair(a, (uint32_t)k, gb);
+   DrawStage ds;
+   draw_begin(a, (uint32_t)k, gb, ds);
+   draw_probe(a, ds);
+   const Pair s2 = draw_finish(a, (uint32_t)k, gb, ds);
+   if (s2.h != s.h || s2.t != s.t || s2.r != s.r || s2.c != s.c || s2.corruptTail != s.corruptTail) s.h = s.t = s.r = s.c = -1;
    int32_t* p = out + 6 * k;
    p[0] = s.h; p[1] = s.t; p[2] = s.r; p[5] = s.r;
    if (s.corruptTail) { p[3] = s.h; p[4] = s.c; } else { p[3] = s.c; p[4] = s.t; }
@@ -1027,6 +1052,7 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    const char* trace_path = getenv("KB2E_TRAIN_TRACE");
    unsigned long long* trace_dev = nullptr;
    if (trace_path) {
+      if (getenv("KB2E_TRAIN_TRACE_FINE")) a.flags |= 0x80000000u;   // + per-group stamps inside the list publish (11 slots per batch)
       KB2E_CUDA(c, pool_alloc(c, &trace_dev, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long)));
       KB2E_CUDA(c, cudaMemsetAsync(trace_dev, 0, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long), c->stream));
       a.trace = trace_dev;
@@ -1117,6 +1143,11 @@ int train_take_deltas(kb2e_ctx* c, double* d_ent, double* d_rel, double* d_w) {
 
 int train_sample(kb2e_ctx* c, int epoch, int batch, int64_t count, int32_t* out_dev) {
    if (!c->triples || !c->have_pr) return fail(c, KB2E_ERR_ARG, "sampler needs kb2e_set_train_triples and kb2e_set_bern");
+   if (!c->thr_valid) {
+      fill_threshold_kernel<<<blocks_for(c->n_train, 256), 256, 0, c->stream>>>(c->triples, c->n_train, c->pr);
+      KB2E_CUDA(c, cudaGetLastError());
+      c->thr_valid = true;
+   }
    TrainArgs a;
    fill_args(c, a);
    uint32_t gb = (uint32_t)epoch * (uint32_t)c->cfg.batches + (uint32_t)batch;

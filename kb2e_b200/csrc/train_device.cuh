@@ -256,7 +256,8 @@ __device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32
 struct DrawStage {
    int4 tr;
    uint64_t v0, v1;
-   int j;   // candidate entity | coin << 24
+   int j;      // candidate entity
+   int coin;   // 0..999, compared with the relation's corruption threshold
 };
 
 __device__ __forceinline__ void draw_begin(const TrainArgs& a, uint32_t k, uint32_t gb, DrawStage& d) {
@@ -271,14 +272,14 @@ __device__ __forceinline__ void draw_begin(const TrainArgs& a, uint32_t k, uint3
       i = (uint64_t)randmax_from(x[0], x[1], (int)a.n_train);
       j = randmax_from(y[0], y[1], a.nE);
    }
-   d.j = j | (int)((x[2] % 1000u) << kEntityBits);
+   d.j = j;
+   d.coin = (int)(x[2] % 1000u);
    d.tr = __ldg(a.triples + i);
 }
 
 __device__ __forceinline__ uint64_t draw_key(const DrawStage& d, bool& corruptTail) {
-   const int j = d.j & ((1 << kEntityBits) - 1), coin = (int)((uint32_t)d.j >> kEntityBits);
-   corruptTail = coin < d.tr.w;
-   return corruptTail ? pack_triple(d.tr.x, d.tr.z, j) : pack_triple(j, d.tr.z, d.tr.y);
+   corruptTail = d.coin < d.tr.w;
+   return corruptTail ? pack_triple(d.tr.x, d.tr.z, d.j) : pack_triple(d.j, d.tr.z, d.tr.y);
 }
 
 __device__ __forceinline__ void draw_probe(const TrainArgs& a, DrawStage& d) {
@@ -294,7 +295,7 @@ __device__ __forceinline__ Pair draw_finish(const TrainArgs& a, uint32_t k, uint
    Pair s;
    s.h = d.tr.x; s.t = d.tr.y; s.r = d.tr.z;
    const uint64_t key = draw_key(d, s.corruptTail);
-   int j = d.j & ((1 << kEntityBits) - 1);
+   int j = d.j;
    bool hit;
    if (d.v0 == key || (d.v0 != kEmptyKey && d.v1 == key)) hit = true;
    else if (d.v0 == kEmptyKey || d.v1 == kEmptyKey) hit = false;
