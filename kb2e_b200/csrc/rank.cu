@@ -51,8 +51,8 @@ struct RankState {
    uint32_t* seg_end = nullptr;   // hash slot -> one past the segment's last entry
    uint64_t seg_mask = 0;
    uint32_t n_ent = 0;
-   int4* chunks = nullptr;        // (query, first entry, #entries <= 32, segment start) work items of the filter pass
-   unsigned int chunk_cap = 0;    // chunks needed by the whole test set (both sides): bound for any window
+   int2* chunks = nullptr;        // (query, known-true neighbour) work items of the filter pass; neighbour -1 = nothing to score
+   unsigned int chunk_cap = 0;    // entries needed by the whole test set (both sides): bound for any window
    unsigned int* chunk_count = nullptr;
    // candidate matrices
    double* ct0 = nullptr;         // entity table transposed [D][ld]
@@ -80,6 +80,10 @@ struct RankState {
    kb2e::TcState tc;
    kb2e::F32State f32;
    kb2e::TrpState trp;
+   // the filter pass depends only on the queries' exact energies, not on the all-candidates kernel: in a single-pass call
+   // it runs beside that kernel on a second stream (fork after E_true, join before finalize)
+   cudaStream_t side = nullptr;
+   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace kb2e {
@@ -373,12 +377,15 @@ __global__ void segment_end_kernel(const uint64_t* ent_key, uint32_t n, const ui
 }
 
 // ---- filter adjustment ---------------------------------------------------------------------------------
-// The known-true neighbours of a query are one segment of the sorted entry list.  Segment lengths are
-// heavy-tailed (FB15k-shape planted KG: median 2, 99th percentile 222, maximum 775 entries), and one exact
-// energy is a chain of D dependent fp64 additions, so "one group of lanes per query" is bound by the longest
-// segment.  Instead the segments are cut into chunks of up to 32 entries (filter_plan_kernel: hash lookup,
-// warp scan, one atomic per warp to reserve chunk slots) and a persistent grid takes the chunks one per warp,
-// one (query, neighbour) pair per lane (filter_pairs_kernel).  No host step: the chunk count stays on the device.
+// The known-true neighbours of a query are one segment of the sorted entry list.  Segment lengths are heavy-tailed
+// (FB15k-shape planted KG: 833,075 neighbours for 118,142 queries -- median 1, 99th percentile 126, maximum 775), and one
+// exact energy is a chain of D dependent fp64 additions.  Work is therefore flattened to ONE (query, neighbour) PAIR per
+// thread: filter_plan_kernel looks the segments up (hash), reserves room with a warp scan and one atomic per warp and
+// writes the pairs -- the warp walks its 32 queries together, so a 775-neighbour segment costs 25 coalesced passes, not
+// 775 iterations of one lane -- dropping the truth itself and triples listed twice; filter_pairs_kernel (persistent
+// grid) scores one pair per thread with every lane busy.  (The previous scheme, one <= 32-neighbour chunk per warp, left
+// a warp with one or two active lanes for the median segment: 0.31 ms at FB15k shape.)  No host step: the pair count stays
+// on the device.
 struct SegRef { uint32_t off, len; };
 
 __device__ __forceinline__ SegRef find_segment(const uint64_t* __restrict__ seg_key, const uint32_t* __restrict__ seg_val,
@@ -392,9 +399,7 @@ __device__ __forceinline__ SegRef find_segment(const uint64_t* __restrict__ seg_
    }
 }
 
-constexpr int kChunk = 32;
-
-// upper bound of the chunks any kb2e_rank window can need: all test triples, both sides (runs once per filter build)
+// upper bound of the pairs any kb2e_rank window can need: all test triples, both sides (runs once per filter build)
 __global__ void count_chunks_kernel(const int32_t* __restrict__ th, const int32_t* __restrict__ tt, const int32_t* __restrict__ tr,
                                     long long n_test, const uint64_t* seg_key, const uint32_t* seg_val, const uint32_t* seg_end,
                                     uint64_t mask, unsigned long long* total) {
@@ -403,85 +408,80 @@ __global__ void count_chunks_kernel(const int32_t* __restrict__ th, const int32_
    if (q < 2 * n_test) {
       const long long i = q >> 1;
       const int side = (int)(q & 1);
-      const SegRef sr = find_segment(seg_key, seg_val, seg_end, mask, seg_key_of(side, tr[i], side == 0 ? tt[i] : th[i]));
-      n = (sr.len + kChunk - 1) / kChunk;
+      n = find_segment(seg_key, seg_val, seg_end, mask, seg_key_of(side, tr[i], side == 0 ? tt[i] : th[i])).len;
    }
 #pragma unroll
    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
    if ((threadIdx.x & 31) == 0 && n) atomicAdd(total, (unsigned long long)n);
 }
 
-__global__ void filter_plan_kernel(const RankArgs a, const uint32_t* __restrict__ seg_end, int4* chunks, unsigned int* chunk_count,
-                                   unsigned int chunk_cap) {
+__global__ void filter_plan_kernel(const RankArgs a, const uint32_t* __restrict__ seg_end, int2* pairs, unsigned int* pair_count,
+                                   unsigned int pair_cap) {
    const long long q = a.q_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
    const int lane = threadIdx.x & 31;
    SegRef sr{0u, 0u};
-   if (q < a.q_end) sr = find_segment(a.seg_key, a.seg_val, seg_end, a.seg_mask, seg_key_of(a.q_side[q], a.q_rel[q], a.q_fixed[q]));
-   const unsigned int n = (sr.len + kChunk - 1) / kChunk;
-   unsigned int x = n;   // inclusive warp scan
+   int truth = -1;
+   if (q < a.q_end) {
+      sr = find_segment(a.seg_key, a.seg_val, seg_end, a.seg_mask, seg_key_of(a.q_side[q], a.q_rel[q], a.q_fixed[q]));
+      truth = a.q_truth[q];
+   }
+   unsigned int x = sr.len;   // inclusive warp scan
 #pragma unroll
    for (int o = 1; o < 32; o <<= 1) {
       const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
       if (lane >= o) x += y;
    }
    const unsigned int total = __shfl_sync(0xffffffffu, x, 31);
+   if (total == 0) return;
    unsigned int base = 0;
-   if (lane == 0 && total) base = atomicAdd(chunk_count, total);
-   base = __shfl_sync(0xffffffffu, base, 0) + (x - n);
-   for (unsigned int k = 0; k < n; k++) {
-      if (base + k < chunk_cap)
-         chunks[base + k] = make_int4((int)q, (int)(sr.off + k * kChunk), (int)min((unsigned int)kChunk, sr.len - k * kChunk), (int)sr.off);
+   if (lane == 0) base = atomicAdd(pair_count, total);
+   base = __shfl_sync(0xffffffffu, base, 0) + (x - sr.len);
+   for (int src = 0; src < 32; src++) {
+      const unsigned int len = __shfl_sync(0xffffffffu, sr.len, src);
+      if (len == 0) continue;
+      const unsigned int off = __shfl_sync(0xffffffffu, sr.off, src), out = __shfl_sync(0xffffffffu, base, src);
+      const int tq = __shfl_sync(0xffffffffu, truth, src);
+      const int qq = (int)(q - lane + src);
+      for (unsigned int k = lane; k < len; k += 32) {
+         int c = __ldg(a.nbr + off + k);
+         // the truth itself is not a competitor; the same triple listed twice (e.g. in train and valid) counts once
+         if (c == tq || (k > 0 && __ldg(a.nbr + off + k - 1) == c)) c = -1;
+         if (out + k < pair_cap) pairs[out + k] = make_int2(qq, c);
+      }
    }
 }
 
 // ROWS = true (TransE): the candidate matrix IS the entity table, so the energies are taken from the row-major
 // fp64 table (contiguous 8*D-byte rows) instead of the transposed copy; arithmetic and order are exact_energy's.
 template <int L2, bool ROWS>
-__global__ void filter_pairs_kernel(const RankArgs a, const double* __restrict__ ent64, const int4* __restrict__ chunks,
-                                    const unsigned int* __restrict__ chunk_count, unsigned int chunk_cap) {
-   const unsigned int n = min(*chunk_count, chunk_cap);
-   const int lane = threadIdx.x & 31;
-   const unsigned int warps = (gridDim.x * blockDim.x) >> 5;
-   for (unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps) {
-      const int4 ch = __ldg(chunks + w);
-      const long long q = ch.x;
-      const int side = a.q_side[q], rel = a.q_rel[q], fixed = a.q_fixed[q], truth = a.q_truth[q];
-      const double et = a.q_etrue[q];
-      const double dsign = side ? -1.0 : 1.0;
-      const double* d = a.rel64 + (size_t)rel * a.D;
-      int less = 0, eq = 0;
-      if (lane < ch.z) {
-         const uint32_t k = (uint32_t)ch.y + lane;
-         const int c = __ldg(a.nbr + k);
-         const bool dup = k > (uint32_t)ch.w && __ldg(a.nbr + k - 1) == c;  // the same triple listed twice (e.g. in train and valid)
-         if (c != truth && !dup) {
-            double e;
-            if (ROWS) {
-               const double* v = ent64 + (size_t)fixed * a.D;
-               const double* x = ent64 + (size_t)c * a.D;
-               e = 0.0;
+__global__ void filter_pairs_kernel(const RankArgs a, const double* __restrict__ ent64, const int2* __restrict__ pairs,
+                                    const unsigned int* __restrict__ pair_count, unsigned int pair_cap) {
+   const unsigned int n = min(*pair_count, pair_cap);
+   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+      const int2 pr = __ldg(pairs + k);
+      const int c = pr.y;
+      if (c < 0) continue;
+      const long long q = pr.x;
+      const int fixed = a.q_fixed[q];
+      const double dsign = a.q_side[q] ? -1.0 : 1.0;
+      const double* d = a.rel64 + (size_t)a.q_rel[q] * a.D;
+      double e;
+      if (ROWS) {
+         const double* v = ent64 + (size_t)fixed * a.D;
+         const double* x = ent64 + (size_t)c * a.D;
+         e = 0.0;
 #pragma unroll 8
-               for (int i = 0; i < a.D; i++) {
-                  const double t = __dsub_rn(__dsub_rn(__ldg(v + i), __ldg(x + i)), dsign * __ldg(d + i));
-                  e = L2 ? __dadd_rn(e, __dmul_rn(t, t)) : __dadd_rn(e, fabs(t));
-               }
-            } else {
-               const double* ct = a.ct + (size_t)a.q_slot[q] * a.D * a.ld;
-               e = exact_energy<L2>(ct, a.ld, a.D, fixed, c, d, dsign);
-            }
-            less = e < et;
-            eq = e == et;
+         for (int i = 0; i < a.D; i++) {
+            const double t = __dsub_rn(__dsub_rn(__ldg(v + i), __ldg(x + i)), dsign * __ldg(d + i));
+            e = L2 ? __dadd_rn(e, __dmul_rn(t, t)) : __dadd_rn(e, fabs(t));
          }
+      } else {
+         const double* ct = a.ct + (size_t)a.q_slot[q] * a.D * a.ld;
+         e = exact_energy<L2>(ct, a.ld, a.D, fixed, c, d, dsign);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-         less += __shfl_xor_sync(0xffffffffu, less, o);
-         eq += __shfl_xor_sync(0xffffffffu, eq, o);
-      }
-      if (lane == 0) {
-         if (less) atomicAdd(a.q_cnt + 2 * a.nq + q, less);
-         if (eq) atomicAdd(a.q_cnt + 3 * a.nq + q, eq);
-      }
+      const double et = a.q_etrue[q];
+      if (e < et) atomicAdd(a.q_cnt + 2 * a.nq + q, 1);
+      else if (e == et) atomicAdd(a.q_cnt + 3 * a.nq + q, 1);
    }
 }
 
@@ -583,7 +583,7 @@ static int build_filter(kb2e_ctx* c) {
    KB2E_CUDA(c, cudaMemcpyAsync(s->nbr, val_tmp, 2 * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
    segment_hash_kernel<<<nblk((long long)(2 * n), 256), 256, 0, c->stream>>>(s->ent_key, s->n_ent, s->seg_key, s->seg_val, s->seg_mask);
    segment_end_kernel<<<nblk((long long)(2 * n), 256), 256, 0, c->stream>>>(s->ent_key, s->n_ent, s->seg_key, s->seg_end, s->seg_mask);
-   // work items the filter pass of the whole test set needs (kb2e_rank windows need at most as many)
+   // (query, neighbour) pairs the filter pass of the whole test set needs (kb2e_rank windows need at most as many)
    unsigned long long* total_dev = reinterpret_cast<unsigned long long*>(s->chunk_count) + 1;
    unsigned long long total = 0;
    KB2E_CUDA(c, cudaMemsetAsync(total_dev, 0, sizeof(unsigned long long), c->stream));
@@ -592,7 +592,7 @@ static int build_filter(kb2e_ctx* c) {
    KB2E_CUDA(c, cudaGetLastError());
    KB2E_CUDA(c, cudaMemcpyAsync(&total, total_dev, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
-   if (total >= (1ull << 31)) return fail(c, KB2E_ERR_LIMIT, "filter pass needs more than 2^31 work items");
+   if (total >= (1ull << 31)) return fail(c, KB2E_ERR_LIMIT, "filter pass needs more than 2^31 (query, neighbour) pairs");
    s->chunk_cap = (unsigned int)std::max<unsigned long long>(1, total);
    if ((rc = grow(c, &s->chunks, &s->cap_chunks, (size_t)s->chunk_cap))) return rc;
    c->filter_dirty = false;
@@ -812,6 +812,39 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    }
    lap("tensor-core operand prep");
    bool f32_started = false;
+   const bool overlap = passes.size() == 1 && s->n_ent != 0 && getenv("KB2E_RANK_NO_OVERLAP") == nullptr;
+   if (overlap && !s->side) {
+      KB2E_CUDA(c, cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+      KB2E_CUDA(c, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+      KB2E_CUDA(c, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+   }
+   // filter pass of the current pass window (a.q_begin / a.q_end / a.ct as set below), enqueued on `st`
+   auto run_filter = [&](cudaStream_t st) -> int {
+      KB2E_CUDA(c, cudaMemsetAsync(s->chunk_count, 0, sizeof(unsigned int), st));
+      filter_plan_kernel<<<nblk(a.q_end - a.q_begin, 256), 256, 0, st>>>(a, s->seg_end, s->chunks, s->chunk_count, s->chunk_cap);
+      const unsigned fb = 8 * c->num_sms;   // persistent: 8 x 256 threads per SM striding over the pair list
+      if (use_trp) {
+         int rc2 = trp_filter(c, &s->trp, l2, s->q_int, nq, s->q_etrue, s->chunks, s->chunk_count, s->chunk_cap, s->q_cnt, st);
+         if (rc2) return rc2;
+      } else if (per_rel) {
+         if (l2) filter_pairs_kernel<1, false><<<fb, 256, 0, st>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
+         else filter_pairs_kernel<0, false><<<fb, 256, 0, st>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
+      } else {
+         if (l2) filter_pairs_kernel<1, true><<<fb, 256, 0, st>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
+         else filter_pairs_kernel<0, true><<<fb, 256, 0, st>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
+      }
+      KB2E_CUDA(c, cudaGetLastError());
+      return KB2E_OK;
+   };
+   // fork: everything enqueued on the main stream so far (E_true of the pass) happens before the filter pass starts
+   auto fork_filter = [&]() -> int {
+      KB2E_CUDA(c, cudaEventRecord(s->ev_fork, c->stream));
+      KB2E_CUDA(c, cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+      int rc2 = run_filter(s->side);
+      if (rc2) return rc2;
+      KB2E_CUDA(c, cudaEventRecord(s->ev_join, s->side));
+      return KB2E_OK;
+   };
    // Everything below is enqueued without a host wait; the one synchronisation is at the end of the call.
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
    for (size_t p = 0; p < passes.size(); p++) {
@@ -839,6 +872,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
          KB2E_CUDA(c, cudaEventRecord(s->pass_ev[2 * passes.size() + 2 * p + 1], c->stream));
          rc = trp_queries(c, &s->trp, l2, s->q_int, nq, ps.q_begin, ps.q_end, s->q_etrue);         // exact V[q], E_true[q]
          if (rc) return rc;
+         if (overlap && (rc = fork_filter())) return rc;
          rc = trp_thresholds(c, &s->trp, &s->f32, l2, s->q_int, nq, ps.q_begin, ps.q_end, s->q_etrue);
          if (rc) return rc;
          rc = f32_main(c, &s->f32, l2, s->ld, a.tiles, ntiles, s->q_cnt, s->pass_ev[2 * p], s->pass_ev[2 * p + 1]);
@@ -846,8 +880,11 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
          rc = trp_recheck(c, &s->trp, &s->f32, l2, s->q_int, nq, s->q_etrue, s->q_cnt);
          if (rc) return rc;
          c->rstats.launches += 6;
-      } else if (l2) etrue_kernel<1><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
-      else etrue_kernel<0><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
+      } else {
+         if (l2) etrue_kernel<1><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
+         else etrue_kernel<0><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
+         if (overlap && (rc = fork_filter())) return rc;
+      }
       if (use_trp) {
          // scored above
       } else if (use_tc) {
@@ -883,24 +920,14 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
          else rank_exact_kernel<0><<<dim3(ntiles, (unsigned)splits), kRankThreads, smem, c->stream>>>(a);
          KB2E_CUDA(c, cudaEventRecord(s->pass_ev[2 * p + 1], c->stream));
       }
-      if (s->n_ent) {
-         KB2E_CUDA(c, cudaMemsetAsync(s->chunk_count, 0, sizeof(unsigned int), c->stream));
-         filter_plan_kernel<<<nblk(pq, 256), 256, 0, c->stream>>>(a, s->seg_end, s->chunks, s->chunk_count, s->chunk_cap);
-         const unsigned fb = 8 * c->num_sms;   // persistent: 8 x 256 threads per SM, one chunk per warp at a time
-         if (use_trp) {
-            rc = trp_filter(c, &s->trp, l2, s->q_int, nq, s->q_etrue, s->nbr, s->chunks, s->chunk_count, s->chunk_cap, s->q_cnt);
-            if (rc) return rc;
-         } else if (per_rel) {
-            if (l2) filter_pairs_kernel<1, false><<<fb, 256, 0, c->stream>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
-            else filter_pairs_kernel<0, false><<<fb, 256, 0, c->stream>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
-         } else {
-            if (l2) filter_pairs_kernel<1, true><<<fb, 256, 0, c->stream>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
-            else filter_pairs_kernel<0, true><<<fb, 256, 0, c->stream>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
-         }
+      if (s->n_ent && !overlap) {
+         rc = run_filter(c->stream);
+         if (rc) return rc;
       }
       KB2E_CUDA(c, cudaGetLastError());
       c->rstats.launches += per_rel ? 5 : 4;
    }
+   if (overlap) KB2E_CUDA(c, cudaStreamWaitEvent(c->stream, s->ev_join, 0));   // join: the filter counts are complete
    finalize_kernel<<<nblk(nq, 256), 256, 0, c->stream>>>(s->q_cnt, s->q_int + 5 * nq, nq, s->out, s->sums);
    KB2E_CUDA(c, cudaGetLastError());
    KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
@@ -1004,6 +1031,7 @@ void rank_free(kb2e_ctx* c) {
    pool_free(c, s->q_int); pool_free(c, s->q_etrue); pool_free(c, s->q_cnt); pool_free(c, s->tiles); pool_free(c, s->slot_rel);
    pool_free(c, s->sums); pool_free(c, s->out);
    for (cudaEvent_t e : s->pass_ev) cudaEventDestroy(e);
+   if (s->side) { cudaStreamDestroy(s->side); cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); }
    pool_free(c, s->ids);
    tc_free(c, &s->tc);
    f32_free(c, &s->f32);

@@ -437,43 +437,33 @@ __global__ void __launch_bounds__(32 * EX_WARPS) recheck_kernel(const QueryRefs 
    }
 }
 
-// filter pass: one chunk (<= 32 known-true neighbours of one query) per warp, neighbours projected on demand
+// filter pass: (query, known-true neighbour) pairs (rank.cu: filter_plan_kernel), neighbours projected on demand, one
+// warp per pair over contiguous shares of the pair list (neighbouring pairs share the query, hence M_r stays in L1)
 template <int L2>
-__global__ void __launch_bounds__(32 * EX_WARPS) filter_kernel(const QueryRefs r, const int32_t* __restrict__ nbr, const int4* __restrict__ chunks,
-                                                               const unsigned int* __restrict__ chunk_count, unsigned int chunk_cap,
+__global__ void __launch_bounds__(32 * EX_WARPS) filter_kernel(const QueryRefs r, const int2* __restrict__ pairs,
+                                                               const unsigned int* __restrict__ pair_count, unsigned int pair_cap,
                                                                const double* __restrict__ V, const double* __restrict__ q_etrue, int32_t* q_cnt,
                                                                long long nq) {
    __shared__ double s_terms[EX_WARPS][MAXD];
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-   const unsigned int n = min(*chunk_count, chunk_cap);
+   const unsigned int n = min(*pair_count, pair_cap);
    const unsigned int warps = gridDim.x * EX_WARPS;
-   const unsigned int per = (n + warps - 1) / warps;   // contiguous shares: neighbouring chunks share the relation
+   const unsigned int per = (n + warps - 1) / warps;
    const unsigned int w = blockIdx.x * EX_WARPS + warp;
    const unsigned int k_end = min(n, (w + 1) * per);
    const int D = r.D;
    for (unsigned int k = w * per; k < k_end; k++) {
-      const int4 ch = __ldg(chunks + k);
-      const long long q = ch.x;
-      const int rel = r.q_rel[q], truth = r.q_truth[q];
-      const double* M = r.w64 + (size_t)rel * D * D;
-      const double* d = r.rel64 + (size_t)rel * D;
-      const double dsign = r.q_side[q] ? -1.0 : 1.0;
-      const double et = q_etrue[q];
-      int less = 0, eq = 0;
-      for (int t = 0; t < ch.z; t++) {
-         const uint32_t pos = (uint32_t)ch.y + t;
-         const int c = __ldg(nbr + pos);
-         const bool dup = pos > (uint32_t)ch.w && __ldg(nbr + pos - 1) == c;   // the same triple listed twice (e.g. train and valid)
-         if (c == truth || dup) continue;
-         double p[4];
-         project_exact(M, r.ent64 + (size_t)c * D, D, lane, p);
-         const double e = energy_exact<L2>(p, V + (size_t)q * D, d, dsign, D, lane, s_terms[warp]);
-         less += e < et;
-         eq += e == et;
-      }
+      const int2 pr = __ldg(pairs + k);
+      if (pr.y < 0) continue;
+      const long long q = pr.x;
+      const int rel = r.q_rel[q];
+      double p[4];
+      project_exact(r.w64 + (size_t)rel * D * D, r.ent64 + (size_t)pr.y * D, D, lane, p);
+      const double e = energy_exact<L2>(p, V + (size_t)q * D, r.rel64 + (size_t)rel * D, r.q_side[q] ? -1.0 : 1.0, D, lane, s_terms[warp]);
       if (lane == 0) {
-         if (less) atomicAdd(q_cnt + 2 * nq + q, less);
-         if (eq) atomicAdd(q_cnt + 3 * nq + q, eq);
+         const double et = q_etrue[q];
+         if (e < et) atomicAdd(q_cnt + 2 * nq + q, 1);
+         else if (e == et) atomicAdd(q_cnt + 3 * nq + q, 1);
       }
    }
 }
@@ -635,12 +625,12 @@ int trp_recheck(kb2e_ctx* c, TrpState* s, F32State* f, bool l2, const int32_t* q
    return KB2E_OK;
 }
 
-int trp_filter(kb2e_ctx* c, TrpState* s, bool l2, const int32_t* q_int, long long nq_total, const double* q_etrue, const int32_t* nbr,
-               const int4* chunks, const unsigned int* chunk_count, unsigned int chunk_cap, int32_t* q_cnt) {
+int trp_filter(kb2e_ctx* c, TrpState* s, bool l2, const int32_t* q_int, long long nq_total, const double* q_etrue, const int2* pairs,
+               const unsigned int* pair_count, unsigned int pair_cap, int32_t* q_cnt, cudaStream_t stream) {
    const trp::QueryRefs r = make_refs(c, q_int, nq_total);
    const unsigned blocks = 8 * c->num_sms;
-   if (l2) trp::filter_kernel<1><<<blocks, 32 * trp::EX_WARPS, 0, c->stream>>>(r, nbr, chunks, chunk_count, chunk_cap, s->V, q_etrue, q_cnt, nq_total);
-   else trp::filter_kernel<0><<<blocks, 32 * trp::EX_WARPS, 0, c->stream>>>(r, nbr, chunks, chunk_count, chunk_cap, s->V, q_etrue, q_cnt, nq_total);
+   if (l2) trp::filter_kernel<1><<<blocks, 32 * trp::EX_WARPS, 0, stream>>>(r, pairs, pair_count, pair_cap, s->V, q_etrue, q_cnt, nq_total);
+   else trp::filter_kernel<0><<<blocks, 32 * trp::EX_WARPS, 0, stream>>>(r, pairs, pair_count, pair_cap, s->V, q_etrue, q_cnt, nq_total);
    KB2E_CUDA(c, cudaGetLastError());
    return KB2E_OK;
 }

@@ -43,9 +43,9 @@ int trp_thresholds(kb2e_ctx* c, TrpState* s, F32State* f, bool l2, const int32_t
                    const double* q_etrue);
 // Exact re-score of the undecided band of f32_main (candidates projected on demand in fp64, reference operation order).
 int trp_recheck(kb2e_ctx* c, TrpState* s, F32State* f, bool l2, const int32_t* q_int, long long nq_total, const double* q_etrue, int32_t* q_cnt);
-// Filter pass: one chunk (<= 32 known neighbours of one query) per warp, neighbours projected on demand in fp64.
-int trp_filter(kb2e_ctx* c, TrpState* s, bool l2, const int32_t* q_int, long long nq_total, const double* q_etrue, const int32_t* nbr,
-               const int4* chunks, const unsigned int* chunk_count, unsigned int chunk_cap, int32_t* q_cnt);
+// Filter pass: (query, known-true neighbour) pairs, neighbours projected on demand in fp64.
+int trp_filter(kb2e_ctx* c, TrpState* s, bool l2, const int32_t* q_int, long long nq_total, const double* q_etrue, const int2* pairs,
+               const unsigned int* pair_count, unsigned int pair_cap, int32_t* q_cnt, cudaStream_t stream);
 // Test hook (kb2e_debug_transr_projection): the tensor-core projection of every entity under one relation, [num_entities][dim],
 // and the relative error bound eps_p it is guaranteed to meet: |P~[c][i] - P[c][i]| <= eps_p * sum_j |e_cj| |M_ji|.
 int trp_debug_project(kb2e_ctx* c, TrpState* s, int relation, float* out, double* eps_rel);

@@ -74,6 +74,7 @@ EmbeddingArguments parseArgs(int argc, char** argv) {
       {"seedmethod", [&](const char* v) { a.seedMethod = atoi(v); }},
       {"seed", [&](const char* v) { a.seed = (unsigned int)atoi(v); }},
       {"device", [&](const char* v) { a.device = atoi(v); }},
+      {"gpus", [&](const char* v) { a.gpus = atoi(v); }},
       {"sampler", [&](const char* v) { a.samplerRandMax = (std::strcmp(v, "reference") == 0 || std::strcmp(v, "randmax") == 0 || atoi(v) == 1); }},
    };
    for (const Option& o : options) {
@@ -101,6 +102,7 @@ void printUsage(const char* invokedFile) {
    printf("   --%s [%d (%s)] (TransR only)\n", "seedmethod", kMethodUnif, methodName(kMethodUnif));
    printf("   --%s [now]\n", "seed");
    printf("   --%s [0] (B200 build only: CUDA device ordinal)\n", "device");
+   printf("   --%s [1] (B200 build only, eval programs: shard the test triples over this many GPUs)\n", "gpus");
    printf("   --%s [uniform] (B200 build only: 'reference' draws indices with the distribution of the reference's randMax)\n", "sampler");
 }
 

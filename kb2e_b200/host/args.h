@@ -30,6 +30,7 @@ struct EmbeddingArguments {
    unsigned int seed;
    // GPU-only (not in the reference; never printed in the Options banner)
    int device = 0;
+   int gpus = 1;   // eval programs: shard the test triples over this many GPUs (devices device .. device + gpus - 1)
    // sampler indices: 0 = uniform (default), 1 = the index distribution of the reference's randMax
    // (common/utils.cpp:113-120), for trained-model parity with the shipped reference
    int samplerRandMax = 0;

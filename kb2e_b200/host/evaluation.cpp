@@ -1,9 +1,11 @@
 #include "evaluation.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <thread>
 
 #include "kb2e_b200.h"
 #include "loader.h"
@@ -18,7 +20,16 @@ EmbeddingEvaluation::EmbeddingEvaluation(int model, const EmbeddingArguments& ar
 }
 
 EmbeddingEvaluation::~EmbeddingEvaluation() {
-   if (ctx_) kb2e_destroy(ctx_);
+   for (kb2e_ctx* c : contexts_) kb2e_destroy(c);
+}
+
+void EmbeddingEvaluation::uploadTable(int table, const double* data, long long rows, long long cols) {
+   for (kb2e_ctx* c : contexts_) {
+      if (kb2e_upload(c, table, data, rows, cols)) {
+         ctx_ = c;
+         die("kb2e_upload");
+      }
+   }
 }
 
 void EmbeddingEvaluation::die(const char* what) {
@@ -65,7 +76,7 @@ void EmbeddingEvaluation::loadEmbeddings() {
       printf("Failed to read embedding values from file: '%s'\n", relationEmbeddingPath_.c_str());
       exit(1);
    }
-   if (kb2e_upload(ctx_, KB2E_TABLE_RELATION, table.data(), numRelations_, (int64_t)D)) die("kb2e_upload");
+   uploadTable(KB2E_TABLE_RELATION, table.data(), numRelations_, (long long)D);
    if (!loadTable(entityEmbeddingPath_, (size_t)numEntities_, D, table)) {
       printf("Failed to read embedding values from file: '%s'\n", entityEmbeddingPath_.c_str());
       exit(1);
@@ -77,14 +88,14 @@ void EmbeddingEvaluation::loadEmbeddings() {
       len = std::sqrt(len);
       if (len - 1 > 1e-3) std::cout << "wrong_entity" << i << ' ' << len << std::endl;
    }
-   if (kb2e_upload(ctx_, KB2E_TABLE_ENTITY, table.data(), numEntities_, (int64_t)D)) die("kb2e_upload");
+   uploadTable(KB2E_TABLE_ENTITY, table.data(), numEntities_, (long long)D);
    if (model_ != KB2E_MODEL_TRANSE) {
       const size_t rows = model_ == KB2E_MODEL_TRANSH ? (size_t)numRelations_ : (size_t)numRelations_ * D;
       if (!loadTable(weightEmbeddingPath_, rows, D, table)) {
          printf("Failed to read embedding weight values from seed file: '%s'\n", weightEmbeddingPath_.c_str());
          exit(1);
       }
-      if (kb2e_upload(ctx_, KB2E_TABLE_WEIGHTS, table.data(), (int64_t)rows, (int64_t)D)) die("kb2e_upload");
+      uploadTable(KB2E_TABLE_WEIGHTS, table.data(), (long long)rows, (long long)D);
    }
 }
 
@@ -112,20 +123,51 @@ void EmbeddingEvaluation::prepare() {
    cfg.seed = args_.seed;
    cfg.flags = 0;
    cfg.reserved = 0;
-   if (kb2e_create(&cfg, &ctx_) != KB2E_OK) {
-      printf("kb2e_create failed: %s\n", kb2e_last_error(NULL));
-      exit(3);
+   const int gpus = std::max(1, args_.gpus);
+   for (int g = 0; g < gpus; g++) {
+      cfg.device = args_.device + g;
+      kb2e_ctx* c = nullptr;
+      if (kb2e_create(&cfg, &c) != KB2E_OK) {
+         printf("kb2e_create failed: %s\n", kb2e_last_error(NULL));
+         exit(3);
+      }
+      contexts_.push_back(c);
    }
+   ctx_ = contexts_[0];
    loadEmbeddings();
-   if (kb2e_set_test_triples(ctx_, heads_.data(), tails_.data(), relations_.data(), (int64_t)heads_.size())) die("kb2e_set_test_triples");
-   if (!filterHeads_.empty() &&
-       kb2e_add_filter_triples(ctx_, filterHeads_.data(), filterTails_.data(), filterRelations_.data(), (int64_t)filterHeads_.size()))
-      die("kb2e_add_filter_triples");
+   for (kb2e_ctx* c : contexts_) {
+      ctx_ = c;
+      if (kb2e_set_test_triples(c, heads_.data(), tails_.data(), relations_.data(), (int64_t)heads_.size())) die("kb2e_set_test_triples");
+      if (!filterHeads_.empty() &&
+          kb2e_add_filter_triples(c, filterHeads_.data(), filterTails_.data(), filterRelations_.data(), (int64_t)filterHeads_.size()))
+         die("kb2e_add_filter_triples");
+   }
+   ctx_ = contexts_[0];
 }
 
 void EmbeddingEvaluation::run() {
+   // every GPU ranks a contiguous window of the test triples on its own host thread; the four sums add up
+   // (common/evaluation.cpp:169-178 accumulates them in exactly this way)
+   const size_t G = contexts_.size();
+   const int64_t n = (int64_t)heads_.size();
+   std::vector<int64_t> part(4 * G, 0);
+   std::vector<int> status(G, 0);
+   std::vector<std::thread> workers;
+   for (size_t g = 0; g < G; g++) {
+      const int64_t lo = n * (int64_t)g / (int64_t)G, hi = n * (int64_t)(g + 1) / (int64_t)G;
+      workers.emplace_back([this, g, lo, hi, &part, &status]() {
+         status[g] = kb2e_rank(contexts_[g], lo, hi - lo, NULL, NULL, NULL, NULL, part.data() + 4 * g);
+      });
+   }
+   for (std::thread& w : workers) w.join();
    int64_t sums[4] = {0, 0, 0, 0};
-   if (kb2e_rank(ctx_, 0, (int64_t)heads_.size(), NULL, NULL, NULL, NULL, sums)) die("kb2e_rank");
+   for (size_t g = 0; g < G; g++) {
+      if (status[g]) {
+         ctx_ = contexts_[g];
+         die("kb2e_rank");
+      }
+      for (int k = 0; k < 4; k++) sums[k] += part[4 * g + k];
+   }
    // the reference prints a progress line per relation (common/evaluation.cpp:243); all relations
    // are ranked in one pass here, so only the final state of that line is shown
    printf("\rProcessed %05.2f%% ...", 100.0);

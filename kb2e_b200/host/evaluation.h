@@ -35,11 +35,16 @@ class EmbeddingEvaluation {
       std::string relationEmbeddingPath_, entityEmbeddingPath_, weightEmbeddingPath_;
       std::vector<int> heads_, tails_, relations_;              // working set = test.txt, in file order
       std::vector<int> filterHeads_, filterTails_, filterRelations_;  // train.txt + valid.txt
+      // one context per GPU (--gpus N: devices device .. device + N - 1); the test triples are sharded over them in
+      // contiguous windows, tables and filter set are replicated (common/evaluation.cpp:221-241 shares nothing between
+      // test triples); ctx_ is contexts_[0]
+      std::vector<kb2e_ctx*> contexts_;
       kb2e_ctx* ctx_ = nullptr;
       EvaluationResult result_;
 
       void loadTriples();     // common/evaluation.cpp:41-62
       void loadEmbeddings();  // common/evaluation.cpp:74-105, transh/evaluation.cpp:20-40, transr/evaluation.cpp:34-60
+      void uploadTable(int table, const double* data, long long rows, long long cols);
       void die(const char* what);
 };
 

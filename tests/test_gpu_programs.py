@@ -155,3 +155,25 @@ def test_reference_side_binding_through_the_virtual_seam(data, tmp_path, model, 
         assert a == b, f
     e = np.loadtxt(os.path.join(out_a, files[0]))
     assert e.shape == (500, 16) and np.isfinite(e).all() and np.abs(e).max() > 0.01
+
+
+def test_eval_program_shards_the_test_set_over_gpus(data, tmp_path):
+    """evalTrans* --gpus N: one process, one context and one host thread per GPU, the test triples in contiguous windows,
+    the four sums added (common/evaluation.cpp:213-241 is the loop that shards).  Same numbers as on one GPU; with a
+    single GPU in the box the flag is checked with N = 1 and an impossible N (error exit, no fallback)."""
+    import torch
+    datadir, g = data
+    out = str(tmp_path)
+    common = ["--datadir", datadir, "--outdir", out, "--size", 16, "--rate", 0.01, "--method", 1, "--batches", 10, "--seed", 5]
+    rc, o = run(os.path.join(OURS, "trainTransE"), *common, "--epochs", 30)
+    assert rc == 0, o
+    rc, o1 = run(os.path.join(OURS, "evalTransE"), *common)
+    assert rc == 0, o1
+    one = parse_eval(o1)
+    n = torch.cuda.device_count()
+    for gpus in sorted({1, min(2, n), n}):
+        rc, o = run(os.path.join(OURS, "evalTransE"), *common, "--gpus", gpus)
+        assert rc == 0, o
+        assert parse_eval(o) == one, (gpus, o)
+    rc, o = run(os.path.join(OURS, "evalTransE"), *common, "--gpus", n + 1)
+    assert rc == 3 and "kb2e_create failed" in o
