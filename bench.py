@@ -47,6 +47,16 @@ WORKLOAD = "TransE bern L2 size=100 rate=0.01 margin=1 batches=100, synthetic FB
 HBM_FALLBACK_GBS = 6650.0
 
 
+def bench_config(world):
+    """The `config` object of the JSON line -- the SAME dict in the product arm and in the reference arm."""
+    return {"workload": WORKLOAD,
+            "step": "one epoch = 100 batches x 4831 sampled (positive, negative) pairs",
+            "parallelism": "replicas only (training), test triples sharded (ranking)" if world > 1 else "single GPU",
+            "l2": "flushed before every timed step (256 MiB write); the 13 MB of tables are L2-resident within a step by nature of the workload",
+            "timing": "CUDA events on the launching stream around each persistent launch, max over ranks (product arm); "
+                      "wall clock of the reference's own bfgs() on one host core (reference arm)"}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -275,7 +285,18 @@ def run_product(args):
                 dt = (time.perf_counter() - t0) * 1e3
                 if it >= 1:
                     ev_e2e.append(max_over_ranks(dt))
+            # resident: tables, test triples and the filter CSR stay on the device between calls (an evaluation loop
+            # over checkpoints of one KG re-uploads only what changed); per step: kb2e_rank + ranks copied back
+            ev_res = []
+            for it in range(1 + KE):
+                barrier()
+                t0 = time.perf_counter()
+                e2.rank(lo, hi - lo, out=p_out)
+                dt = (time.perf_counter() - t0) * 1e3
+                if it >= 1:
+                    ev_res.append(max_over_ranks(dt))
         ev_e2e_value = nq * KE / (sum(ev_e2e) * 1e-3)
+        ev_res_value = nq * KE / (sum(ev_res) * 1e-3)
         ev_h2d = int(ent_eval.nbytes + rel_eval.nbytes + 3 * p_test[0].nbytes + 3 * p_filt[0].nbytes)
         ev_d2h = int(4 * 4 * 2 * (hi - lo) + 32)
         ev_launches = int(r1["launches"] - r0["launches"])
@@ -308,10 +329,7 @@ def run_product(args):
         "metric": "train_triples_per_s", "value": value, "unit": "triples/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "kb2e_b200",
-        "config": {"workload": WORKLOAD, "step": "one epoch = 100 batches x 4831 sampled (positive, negative) pairs",
-                   "parallelism": "replicas only (training), test triples sharded (ranking)" if world > 1 else "single GPU",
-                   "l2": "flushed before every timed step (256 MiB write); the 13 MB of tables are L2-resident within a step by nature of the workload",
-                   "timing": "CUDA events on the launching stream around each persistent launch, max over ranks"},
+        "config": bench_config(world),
         "wall_ms_per_step": sum(wall_ms) / K,
         "gpu_launches": launches + ev_launches,
         "clocks": clk,
@@ -319,7 +337,7 @@ def run_product(args):
                 "ms_per_step": sum(e2e_ms) / K,
                 "what": "kb2e_set_train_triples + kb2e_set_bern + kb2e_upload x2 + kb2e_train_epochs(1) + kb2e_download x2, pinned host buffers"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "kb2e::train_kernel<TransE,16,2,768>",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "kb2e::train_kernel<TransE, 16 lanes x 2 float4 per pair, 640 threads, touched-row lists>",
                      "alpha": alpha, "touched_rows_per_batch": touched / (K * CFG["batches"]),
                      "algorithmic_bytes_per_launch": abytes / max(launches, 1),
                      "note": "algorithmic bytes (SURVEY 8d) / CUDA-event time of the persistent launch; tables are L2-resident, so DRAM traffic is far below the algorithmic bytes"},
@@ -332,8 +350,10 @@ def run_product(args):
             "raw_hits10": float(sums[2]) / nq, "filtered_hits10": float(sums[3]) / nq,
             "e2e": {"value": ev_e2e_value, "unit": "queries/s", "h2d_bytes_per_step": ev_h2d, "d2h_bytes_per_step": ev_d2h,
                     "ms_per_step": sum(ev_e2e) / KE,
-                    "what": "per step, on one long-lived context: kb2e_upload x2 (fp64 tables) + kb2e_set_test_triples + kb2e_add_filter_triples "
-                            "(train + valid; filter CSR rebuilt on the device) + kb2e_rank with per-query ranks copied back; pinned host buffers"},
+                    "what": "COLD: per step, on one long-lived context: kb2e_upload x2 (fp64 tables) + kb2e_set_test_triples + kb2e_add_filter_triples "
+                            "(train + valid; filter CSR rebuilt on the device) + kb2e_rank with per-query ranks copied back; pinned host buffers",
+                    "resident": {"value": ev_res_value, "unit": "queries/s", "ms_per_step": sum(ev_res) / KE, "d2h_bytes_per_step": ev_d2h,
+                                 "what": "tables, test triples and filter CSR already on the device: kb2e_rank + per-query ranks copied back"}},
             "roofline": {"bound": "tensor", "achieved": ranking_flops / (main_ms * 1e-3) / 1e12, "peak": tensor_peak,
                          "unit": "TFLOP/s", "frac": ranking_flops / (main_ms * 1e-3) / 1e12 / tensor_peak, "traffic": profile_traffic("rank"),
                          "peak_source": peak_src + ", bf16 burst", "main_kernel_ms": main_ms,
@@ -377,6 +397,8 @@ def run_scaled_single(local, hbm_peak, peak_src):
     achieved = abytes / (ms * 1e-3) / 1e9
     return {"metric": "train_triples_per_s", "value": n / (ms * 1e-3), "unit": "triples/s", "n_gpus": 1, "scaling": "strong",
             "ms_per_epoch": ms, "alpha": alpha,
+            "series_note": "N = 1 point of the partitioned series: the single-GPU kernel (kb2e_train_epochs), same triples, seed and "
+                           "initial tables as the N > 1 points (kb2e_dist_init_embeddings seeds rows exactly like kb2e_init_embeddings)",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": profile_traffic("scaled"), "peak_source": peak_src, "kernel": "kb2e::train_kernel<TransE,32,2,768>",
                          "note": "traffic = dram bytes of one 100-batch launch from the committed ncu capture (profiles/r01_ncu_full_summary.txt)"},
@@ -410,8 +432,20 @@ def run_partitioned(rank, world, local, max_over_ranks, sum_over_ranks):
                               s1["touched_ent"] - s0["touched_ent"] + s1["touched_rel"] - s0["touched_rel"]])
         n, active, touched = (float(x) for x in cnt)
         abytes, alpha = algorithmic_bytes(n, active, touched, dim)
+        hbm_peak, _, peak_src = peaks()
+        per_gpu = abytes / world / (ms * 1e-3) / 1e9
+        # bytes that must cross NVLink per GPU and epoch: a kept sample has its head local; tail and corrupting rows are remote
+        # with probability (world - 1) / world each: one row served in, and (if the hinge is active) one update pushed out
+        P4 = (dim + 3) // 4 * 4 * 4
+        nvlink_bytes = n / world * 2.0 * (world - 1) / world * (P4 + 8 + alpha * (P4 + 16))
         return {"metric": "train_triples_per_s", "value": n / (ms * 1e-3), "unit": "triples/s", "n_gpus": world, "scaling": "strong",
                 "ms_per_epoch": ms, "alpha": alpha, "algorithmic_GBps_total": abytes / (ms * 1e-3) / 1e9,
+                "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu / hbm_peak, "traffic": None,
+                             "peak_source": peak_src, "kernel": "kb2e::train_dist_kernel",
+                             "nvlink_GBps_per_gpu_each_way": nvlink_bytes / (ms * 1e-3) / 1e9, "nvlink_peak_GBps": 640.0,
+                             "nvlink_frac": nvlink_bytes / (ms * 1e-3) / 1e9 / 640.0,
+                             "note": "per-GPU algorithmic bytes (SURVEY 8d) / epoch time against the measured HBM peak; NVLink: rows served in + "
+                                     "updates pushed out per GPU against the 640 GB/s posted-write rate of profiles/r01_p2p_bench.txt"},
                 "config": {"workload": "TransE L2 size=200, 4,000,000 entities x 1,345 relations, 100,000,000 random triples, batches=100 "
                                        "(1,000,000 pairs per batch), entity rows partitioned by id mod N, relation rows replicated",
                            "exchange": "row requests, rows and updates as posted peer stores / vector REDs over NVLink (CUDA IPC peer memory); no NCCL on the data path",
@@ -497,7 +531,7 @@ def run_reference(args):
         "metric": "train_triples_per_s", "value": tb["value"], "unit": "triples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tb["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": WORKLOAD, "step": "one epoch of the reference's bfgs() = 100 batches x 4831 pairs, on the host CPU"},
+        "config": bench_config(world),
         "cpu_baseline": {k: tb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": tb["value"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -65,6 +65,11 @@ extern "C" {
  * product of two rand() values modulo x -- e.g. 75 % even indices) instead of uniform ones; still the counter RNG.
  * For trained-model parity with the shipped reference; needs n_train < 2^31. */
 #define KB2E_FLAG_SAMPLER_RANDMAX 4u
+/* Reproducible training (TransE, TransH): updates are accumulated as 32-bit fixed-point integers (2^-24 units) instead of
+ * floating-point REDs, and the epoch loss as a 64-bit fixed-point sum, so tables, losses and output files are
+ * bit-identical from run to run for a given seed -- what the single-threaded reference gives its users.  Costs four
+ * scalar REDs per float4; needs |accumulated update| < 128 per row and batch. */
+#define KB2E_FLAG_DETERMINISTIC 8u
 
 typedef struct kb2e_ctx kb2e_ctx;
 

@@ -6,4 +6,4 @@ that ABI used by the tests, the bench and the multi-GPU launcher.  There is no C
 importing works anywhere, creating a ``Context`` needs a B200.
 """
 from .api import (Context, Kb2eError, load_library, MODELS, TABLE_ENTITY, TABLE_RELATION, TABLE_WEIGHTS,  # noqa: F401
-                  FLAG_RANK_EXACT_ONLY, FLAG_TRANSR_NO_QUIRK, FLAG_SAMPLER_RANDMAX)
+                  FLAG_RANK_EXACT_ONLY, FLAG_TRANSR_NO_QUIRK, FLAG_SAMPLER_RANDMAX, FLAG_DETERMINISTIC)

@@ -12,6 +12,7 @@ TABLE_ENTITY, TABLE_RELATION, TABLE_WEIGHTS = 0, 1, 2
 FLAG_RANK_EXACT_ONLY = 1
 FLAG_TRANSR_NO_QUIRK = 2
 FLAG_SAMPLER_RANDMAX = 4
+FLAG_DETERMINISTIC = 8
 
 SYMBOLS = [
     "kb2e_create", "kb2e_destroy", "kb2e_last_error", "kb2e_stream", "kb2e_set_train_triples", "kb2e_set_bern",

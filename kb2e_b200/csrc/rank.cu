@@ -812,7 +812,9 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    }
    lap("tensor-core operand prep");
    bool f32_started = false;
-   const bool overlap = passes.size() == 1 && s->n_ent != 0 && getenv("KB2E_RANK_NO_OVERLAP") == nullptr;
+   // Opt-in (KB2E_RANK_OVERLAP=1): measured on B200 at FB15k shape the filter pass beside the tensor-core kernel costs that
+   // kernel more issue slots than the overlap saves (1.83 ms with, 1.43 ms without: profiles/r02_rank_probes.txt)
+   const bool overlap = passes.size() == 1 && s->n_ent != 0 && getenv("KB2E_RANK_OVERLAP") != nullptr;
    if (overlap && !s->side) {
       KB2E_CUDA(c, cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
       KB2E_CUDA(c, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));

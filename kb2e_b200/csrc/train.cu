@@ -64,6 +64,39 @@ __device__ __forceinline__ void list_push(int* count, int* list, int cap, int ro
    else counters[6] = 1ull;   // cannot happen with the host's capacities; reported as an error if it ever does
 }
 
+// ---- accumulation into the delta tables ---------------------------------------------------------------
+// Default: one 16-byte floating-point vector RED per float4 (order of the additions = order of arrival: results agree
+// from run to run only to rounding).  KB2E_FLAG_DETERMINISTIC: the same updates as 32-bit FIXED-POINT integers (2^-24
+// units, |sum| < 128 per row and batch) added with integer REDs -- integer addition is associative, so the sums, and with
+// them every table and every printed loss, are bit-identical from run to run, as the reference's are for a given -seed.
+constexpr float kDetScale = 16777216.0f;   // 2^24
+constexpr double kDetLossScale = 1048576.0;   // 2^20: per-epoch loss as a 64-bit fixed-point sum
+
+template <int LPS, int NV>
+__device__ __forceinline__ void acc_row(const TrainArgs& a, float* base, int P, int gl, const float4 (&v)[NV]) {
+   if (!(a.flags & KB2E_FLAG_DETERMINISTIC)) {
+      red_row<LPS, NV>(base, P, gl, v);
+      return;
+   }
+#pragma unroll
+   for (int q = 0; q < NV; q++) {
+      const int off = (q * LPS + gl) * 4;
+      if (off < P) {
+         int* p = reinterpret_cast<int*>(base + off);
+         atomicAdd(p + 0, __float2int_rn(v[q].x * kDetScale));
+         atomicAdd(p + 1, __float2int_rn(v[q].y * kDetScale));
+         atomicAdd(p + 2, __float2int_rn(v[q].z * kDetScale));
+         atomicAdd(p + 3, __float2int_rn(v[q].w * kDetScale));
+      }
+   }
+}
+
+__device__ __forceinline__ float4 det_to_float(float4 bits) {
+   const float inv = 1.0f / kDetScale;
+   return make_float4((float)__float_as_int(bits.x) * inv, (float)__float_as_int(bits.y) * inv, (float)__float_as_int(bits.z) * inv,
+                      (float)__float_as_int(bits.w) * inv);
+}
+
 // ---- phase 1: one (positive, negative) pair, TransE and TransH -----------------------------------
 template <int MODEL, int LPS, int NV, bool LIST>
 __device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists& L, const Pair s, int gl, uint32_t gmask, uint32_t stamp,
@@ -143,23 +176,23 @@ __device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists&
    // relation row: -= m*lr*x  with m = -1 (positive), +1 (negative)
 #pragma unroll
    for (int q = 0; q < NV; q++) u[q] = gp[q] - gn[q];
-   red_row<LPS, NV>(dr, P, gl, u);
+   acc_row<LPS, NV>(a, dr, P, gl, u);
    if (s.corruptTail) {
       // negative = (h, r, c): head -= gn, c += gn; positive: head += gp, tail -= gp
-      red_row<LPS, NV>(dh, P, gl, u);
+      acc_row<LPS, NV>(a, dh, P, gl, u);
 #pragma unroll
       for (int q = 0; q < NV; q++) u[q] = -1.f * gp[q];
-      red_row<LPS, NV>(dt, P, gl, u);
-      red_row<LPS, NV>(dc, P, gl, gn);
+      acc_row<LPS, NV>(a, dt, P, gl, u);
+      acc_row<LPS, NV>(a, dc, P, gl, gn);
    } else {
       // negative = (c, r, t): c -= gn, tail += gn
-      red_row<LPS, NV>(dh, P, gl, gp);
+      acc_row<LPS, NV>(a, dh, P, gl, gp);
 #pragma unroll
       for (int q = 0; q < NV; q++) u[q] = gn[q] - gp[q];
-      red_row<LPS, NV>(dt, P, gl, u);
+      acc_row<LPS, NV>(a, dt, P, gl, u);
 #pragma unroll
       for (int q = 0; q < NV; q++) u[q] = -1.f * gn[q];
-      red_row<LPS, NV>(dc, P, gl, u);
+      acc_row<LPS, NV>(a, dc, P, gl, u);
    }
    if (MODEL == KB2E_MODEL_TRANSH) {
       // transh/trainer.cpp:33,39-40,44-45: w += beta*lr*(x*(hs-ts) + sum_x*(h - t)), with the RAW h, t.
@@ -182,7 +215,7 @@ __device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists&
          float4 neg = (nhs - nts) * gn[q] + sxn * (nh - nt);
          u[q] = neg - pos;
       }
-      red_row<LPS, NV>(a.dw + (size_t)s.r * P, P, gl, u);
+      acc_row<LPS, NV>(a, a.dw + (size_t)s.r * P, P, gl, u);
    }
    // flag the touched rows (+ relation range per entity for the TransH/TransR constraints)
    if (gl < 3) {
@@ -215,9 +248,10 @@ __device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists&
 // Common head of every publish: x = cur + delta, delta = 0 (rows arrive preloaded so that the loads of
 // two rows are in flight together).
 template <int LPS, int NV>
-__device__ __forceinline__ void apply_delta(float* del, int P, int gl, float4 (&x)[NV], float4 (&d)[NV]) {
+__device__ __forceinline__ void apply_delta(const TrainArgs& a, float* del, int P, int gl, float4 (&x)[NV], float4 (&d)[NV]) {
+   const bool det = (a.flags & KB2E_FLAG_DETERMINISTIC) != 0u;
 #pragma unroll
-   for (int q = 0; q < NV; q++) { x[q] = x[q] + d[q]; d[q] = f4(0.f); }
+   for (int q = 0; q < NV; q++) { x[q] = x[q] + (det ? det_to_float(d[q]) : d[q]); d[q] = f4(0.f); }
    store_row<LPS, NV>(del, P, gl, d);
 }
 
@@ -226,7 +260,7 @@ template <int MODEL, int LPS, int NV>
 __device__ __forceinline__ void finish_relation(const TrainArgs& a, int r, int gl, uint32_t gmask, float4 (&x)[NV], float4 (&d)[NV]) {
    const int P = a.P;
    float* cur = a.tab + ((size_t)a.nE + r) * P;
-   apply_delta<LPS, NV>(a.dtab + ((size_t)a.nE + r) * P, P, gl, x, d);
+   apply_delta<LPS, NV>(a, a.dtab + ((size_t)a.nE + r) * P, P, gl, x, d);
    norm_row<LPS, NV>(x, true, gmask);
    if (MODEL == KB2E_MODEL_TRANSH) {
       float* wc = a.w + (size_t)r * P;
@@ -234,7 +268,7 @@ __device__ __forceinline__ void finish_relation(const TrainArgs& a, int r, int g
       float4 b[NV], db[NV];
       load_row<LPS, NV>(wc, P, gl, b);
       load_row<LPS, NV>(wd, P, gl, db);
-      apply_delta<LPS, NV>(wd, P, gl, b, db);
+      apply_delta<LPS, NV>(a, wd, P, gl, b, db);
       norm_row<LPS, NV>(b, false, gmask);          // transh/trainer.cpp:52
       norm_row<LPS, NV>(b, false, gmask);          // common/utils.cpp:82
       soft_orth_loop<LPS, NV>(x, b, a.lr, gmask);  // common/utils.cpp:83-108
@@ -250,7 +284,7 @@ __device__ __forceinline__ void finish_entity(const TrainArgs& a, const RowLists
                                               float4 (&x)[NV], float4 (&d)[NV]) {
    const int P = a.P;
    float* cur = a.tab + (size_t)e * P;
-   apply_delta<LPS, NV>(a.dtab + (size_t)e * P, P, gl, x, d);
+   apply_delta<LPS, NV>(a, a.dtab + (size_t)e * P, P, gl, x, d);
    norm_row<LPS, NV>(x, true, gmask);
    if (MODEL == KB2E_MODEL_TRANSH) {
       int r0 = __ldcg(a.rmin + e), r1 = __ldcg(a.rmax + e);
@@ -269,7 +303,7 @@ __device__ __forceinline__ void finish_entity(const TrainArgs& a, const RowLists
             norm_row<LPS, NV>(b, false, gmask);
 #pragma unroll
             for (int q = 0; q < NV; q++) b[q] = b[q] - b0[q];
-            red_row<LPS, NV>(a.dw + (size_t)r * P, P, gl, b);
+            acc_row<LPS, NV>(a, a.dw + (size_t)r * P, P, gl, b);
             if (gl == 0) {
                if (!LIST) {
                   a.flag[(size_t)a.nE + r] = next_stamp;
@@ -523,7 +557,12 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
       if (threadIdx.x == 0) {
          double t = 0.0;
          for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += s_loss[i];
-         if (t != 0.0) atomicAdd(a.loss + ep, t);
+         if (t != 0.0) {
+            if (a.flags & KB2E_FLAG_DETERMINISTIC)   // CTA partial sums are reproducible; add them as integers
+               atomicAdd(reinterpret_cast<unsigned long long*>(a.loss + ep), (unsigned long long)__double2ll_rn(t * kDetLossScale));
+            else
+               atomicAdd(a.loss + ep, t);
+         }
       }
       __syncthreads();
    }
@@ -940,8 +979,7 @@ static size_t list_shape(const kb2e_ctx* c, long long batchsize, int groups, int
    const long long ce = (transe ? 4 : 3) * S;
    const long long cr = transe ? 0 : 7 * S;   // S phase-1 entries + up to two marks per published entity row (3 S), duplicates included
    const size_t bytes = (size_t)(4 + ce + 2 * cr) * sizeof(int);
-   if (bytes > 40 * 1024) return 0;
-   if (4 * batchsize > (long long)c->nE + c->nR && !(env && atoi(env) == 1)) return 0;
+   if (bytes > 40 * 1024) return 0;   // (large batches -- the scaled shape: 6,757 pairs per CTA -- keep the stamp scan)
    cap_ent = (int)ce;
    cap_rel = (int)cr;
    return bytes;
@@ -1022,6 +1060,7 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    size_t list_bytes = 0;
    if (transr) {
       if (c->P > 128) return fail(c, KB2E_ERR_LIMIT, "TransR training supports embedding sizes up to 128");
+      if (c->cfg.flags & KB2E_FLAG_DETERMINISTIC) return fail(c, KB2E_ERR_LIMIT, "KB2E_FLAG_DETERMINISTIC covers TransE and TransH");
    } else {
       list_bytes = list_shape(c, a.batchsize, threads / lps, a.cap_ent, a.cap_rel);
       if (c->cfg.model == KB2E_MODEL_TRANSE)
@@ -1040,7 +1079,7 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    a.stamp_base = c->stamp_base;
    // batches that need at most half of the resident groups: one barrier per batch, every row folded where its last
    // sample finishes (train_fused.cu)
-   const bool fused = !transr && !phase1_only && train_fused_wanted(c, a.batchsize, lps, threads);
+   const bool fused = !transr && !phase1_only && !(c->cfg.flags & KB2E_FLAG_DETERMINISTIC) && train_fused_wanted(c, a.batchsize, lps, threads);
    if (!transr) {
       int per_sm = 0;
       KB2E_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, list_bytes));
@@ -1097,6 +1136,13 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    c->tstats.active = cnt[0];
    c->tstats.touched_ent = cnt[1];
    c->tstats.touched_rel = cnt[2];
+   if (c->cfg.flags & KB2E_FLAG_DETERMINISTIC) {
+      for (double& l : loss) {
+         long long fixed;
+         memcpy(&fixed, &l, sizeof(fixed));
+         l = (double)fixed / kDetLossScale;
+      }
+   }
    if (loss_out) memcpy(loss_out, loss.data(), (size_t)n_epochs * sizeof(double));
    if (!phase1_only) for (int t = 0; t < 3; t++) c->v64[t] = false;
    return KB2E_OK;
@@ -1104,11 +1150,11 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
 
 // Test hook behind kb2e_train_batch_deltas: the accumulated (pre-normalisation) updates of the last phase1_only
 // launch, widened to fp64, then the delta tables, the stamps and the relation ranges go back to their idle state.
-__global__ void widen_delta_kernel(float* src, double* dst, long long rows, int D, int P) {
+__global__ void widen_delta_kernel(float* src, double* dst, long long rows, int D, int P, int det) {
    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= rows * P) return;
    const int col = (int)(i % P);
-   if (col < D) dst[(i / P) * D + col] = (double)src[i];
+   if (col < D) dst[(i / P) * D + col] = det ? (double)__float_as_int(src[i]) / (double)kDetScale : (double)src[i];
    src[i] = 0.f;
 }
 
@@ -1123,7 +1169,8 @@ int train_take_deltas(kb2e_ctx* c, double* d_ent, double* d_rel, double* d_w) {
    int rc = KB2E_OK;
    for (int t = 0; t < 3 && rc == KB2E_OK; t++) {
       if (rows[t] == 0) continue;
-      widen_delta_kernel<<<blocks_for(rows[t] * c->P, 256), 256, 0, c->stream>>>(src[t], dev, rows[t], c->D, c->P);
+      widen_delta_kernel<<<blocks_for(rows[t] * c->P, 256), 256, 0, c->stream>>>(src[t], dev, rows[t], c->D, c->P,
+                                                                                  (c->cfg.flags & KB2E_FLAG_DETERMINISTIC) ? 1 : 0);
       cudaError_t e = cudaGetLastError();
       if (e == cudaSuccess && dst[t]) e = cudaMemcpyAsync(dst[t], dev, (size_t)rows[t] * c->D * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

@@ -229,8 +229,11 @@ __global__ void __launch_bounds__(THREADS, 1) train_fused_kernel(const __grid_co
 
 // ---- host ------------------------------------------------------------------------------------------------
 bool train_fused_wanted(const kb2e_ctx* c, long long batchsize, int lps, int threads) {
-   const char* env = getenv("KB2E_TRAIN_FUSED");   // 0: never, 1: whenever a batch fits in one pass (tuning aid)
-   if (env && atoi(env) == 0) return false;
+   // Opt-in since round 2 (KB2E_TRAIN_FUSED=1: whenever a batch fits in one pass; =2: only for batches that need at most
+   // half of the resident groups, the round-1 default): with touched-row lists and the pipelined sampler the two-barrier
+   // kernel of train.cu is faster at every measured shape (WN18 shape, TransE size 100: 6.7 vs 7.4 us per batch).
+   const char* env = getenv("KB2E_TRAIN_FUSED");
+   if (!env || atoi(env) == 0) return false;
    if (c->cfg.model != KB2E_MODEL_TRANSE) return false;
    if (threads != 1024 && threads != 768 && threads != 512) return false;   // (640: the list kernel of train.cu)   // KB2E_TRAIN_THREADS override without an instantiation
    const long long groups = (long long)c->num_sms * (threads / lps);

@@ -75,6 +75,7 @@ EmbeddingArguments parseArgs(int argc, char** argv) {
       {"seed", [&](const char* v) { a.seed = (unsigned int)atoi(v); }},
       {"device", [&](const char* v) { a.device = atoi(v); }},
       {"gpus", [&](const char* v) { a.gpus = atoi(v); }},
+      {"deterministic", [&](const char* v) { a.deterministic = atoi(v); }},
       {"sampler", [&](const char* v) { a.samplerRandMax = (std::strcmp(v, "reference") == 0 || std::strcmp(v, "randmax") == 0 || atoi(v) == 1); }},
    };
    for (const Option& o : options) {
@@ -103,6 +104,7 @@ void printUsage(const char* invokedFile) {
    printf("   --%s [now]\n", "seed");
    printf("   --%s [0] (B200 build only: CUDA device ordinal)\n", "device");
    printf("   --%s [1] (B200 build only, eval programs: shard the test triples over this many GPUs)\n", "gpus");
+   printf("   --%s [0] (B200 build only, TransE / TransH training: 1 = bit-reproducible runs, fixed-point accumulation)\n", "deterministic");
    printf("   --%s [uniform] (B200 build only: 'reference' draws indices with the distribution of the reference's randMax)\n", "sampler");
 }
 

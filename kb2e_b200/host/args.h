@@ -34,6 +34,7 @@ struct EmbeddingArguments {
    // sampler indices: 0 = uniform (default), 1 = the index distribution of the reference's randMax
    // (common/utils.cpp:113-120), for trained-model parity with the shipped reference
    int samplerRandMax = 0;
+   int deterministic = 0;   // 1: bit-reproducible training (KB2E_FLAG_DETERMINISTIC; TransE, TransH)
 
    EmbeddingArguments();
    std::string to_string() const;  // the "Options: [...]" banner, byte-compatible with the reference

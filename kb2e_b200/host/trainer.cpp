@@ -97,7 +97,7 @@ void Trainer::prepTrain() {
    cfg.rate = args_.learningRate;
    cfg.margin = args_.margin;
    cfg.seed = args_.seed;
-   cfg.flags = args_.samplerRandMax ? KB2E_FLAG_SAMPLER_RANDMAX : 0u;
+   cfg.flags = (args_.samplerRandMax ? KB2E_FLAG_SAMPLER_RANDMAX : 0u) | (args_.deterministic ? KB2E_FLAG_DETERMINISTIC : 0u);
    cfg.reserved = 0;
    if (kb2e_create(&cfg, &ctx_) != KB2E_OK) {
       printf("kb2e_create failed: %s\n", kb2e_last_error(NULL));

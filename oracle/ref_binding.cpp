@@ -57,8 +57,10 @@ class Binding : public Base {
    kb2e_ctx* ctx_;
 
    void open() {
+      // bit-reproducible accumulation on request (the reference's parser has no such flag: environment); TransE / TransH
+      const unsigned flags = (getenv("KB2E_DETERMINISTIC") && model_ != KB2E_MODEL_TRANSR) ? KB2E_FLAG_DETERMINISTIC : 0u;
       kb2e_config cfg = {model_, this->embeddingSize_, this->method_, args_.distanceType, this->numBatches_, /*device*/ 0,
-                         this->numEntities_, this->numRelations_, this->learningRate_, this->margin_, args_.seed, 0, 0};
+                         this->numEntities_, this->numRelations_, this->learningRate_, this->margin_, args_.seed, flags, 0};
       if (kb2e_create(&cfg, &ctx_) != KB2E_OK) {
          printf("kb2e_create failed: %s\n", kb2e_last_error(NULL));
          exit(3);

@@ -15,8 +15,9 @@ OURS = os.path.join(ROOT, "kb2e_b200", "bin")
 REF = os.path.join(ROOT, "oracle", "_ref", "bin")
 
 
-def run(binary, *args):
-    p = subprocess.run([binary, *map(str, args)], capture_output=True, text=True, timeout=600)
+def run(binary, *args, env=None):
+    p = subprocess.run([binary, *map(str, args)], capture_output=True, text=True, timeout=600,
+                       env=None if env is None else dict(os.environ, **env))
     return p.returncode, p.stdout
 
 
@@ -124,7 +125,7 @@ def test_reference_side_binding_through_the_virtual_seam(data, tmp_path, model, 
     """INTEGRATION.md section 1 compiled for real (oracle/ref_binding.cpp -> oracle/_ref/bin/gpuTrainTrans*): subclasses of the
     REFERENCE's own trainers override the virtual bfgs() (common/trainer.h:59) and call the C ABI; argument parsing,
     loadFiles() with its bern statistics, train(), write() and main are the reference's objects.  Run through that seam, the
-    output files are byte-identical to those of kb2e_b200/bin/train* on the same data and seed -- the host layer this
+    losses and output files equal those of kb2e_b200/bin/train* on the same data and seed -- the host layer this
     repository ships and the patched reference are the same program as far as the hot path is concerned."""
     binding = os.path.join(REF, "gpuTrain" + model)
     if not os.path.exists(binding):
@@ -141,18 +142,28 @@ def test_reference_side_binding_through_the_virtual_seam(data, tmp_path, model, 
                     "--method", 0, "--batches", 10, "--epochs", 30, "--seed", 4)
         assert rc == 0, o
         common += ["--seeddatadir", seed_dir, "--seedmethod", 0]
-    rc_a, o_a = run(binding, *common, "--outdir", out_a)
-    rc_b, o_b = run(os.path.join(OURS, "train" + model), *common, "--outdir", out_b)
+    # TransE / TransH: both sides in the bit-reproducible mode (fixed-point accumulation), so the comparison is exact
+    det = model != "TransR"
+    rc_a, o_a = run(binding, *common, "--outdir", out_a, env={"KB2E_DETERMINISTIC": "1"} if det else None)
+    rc_b, o_b = run(os.path.join(OURS, "train" + model), *common, "--outdir", out_b, *(["--deterministic", 1] if det else []))
     assert rc_a == 0 and rc_b == 0, (o_a, o_b)
-    # same per-epoch losses on stdout (the reference's own printf format on one side, ours on the other)
-    la = re.findall(r"Epoch: \d+, Loss: [0-9.]+", o_a)
-    lb = re.findall(r"Epoch: \d+, Loss: [0-9.]+", o_b)
-    assert len(la) == 25 and la == lb
+    if det:
+        assert re.findall(r"Epoch: \d+, Loss: [0-9.]+", o_a) == re.findall(r"Epoch: \d+, Loss: [0-9.]+", o_b)
+        for f in ["entity2vec." + method, "relation2vec." + method] + (["weights." + method] if model != "TransE" else []):
+            assert open(os.path.join(out_a, f), "rb").read() == open(os.path.join(out_b, f), "rb").read(), f
+    # same per-epoch losses on stdout (the reference's own printf format on one side, ours on the other) and the same
+    # tables in the files -- to fp32 rounding, not bit for bit: the updates are accumulated with floating-point REDs whose
+    # order differs from run to run (two runs of ONE program differ in the same way)
+    la = [float(x) for x in re.findall(r"Epoch: \d+, Loss: ([0-9.]+)", o_a)]
+    lb = [float(x) for x in re.findall(r"Epoch: \d+, Loss: ([0-9.]+)", o_b)]
+    assert len(la) == 25 and np.allclose(la, lb, rtol=2e-3)
+    assert la[0] == lb[0] or abs(la[0] - lb[0]) < 1e-6 * la[0]   # the first epoch starts from identical tables
     assert "Number of Relations: 12" in o_a and "Number of Entities: 500" in o_a
     files = ["entity2vec." + method, "relation2vec." + method] + (["weights." + method] if model != "TransE" else [])
     for f in files:
-        a, b = open(os.path.join(out_a, f), "rb").read(), open(os.path.join(out_b, f), "rb").read()
-        assert a == b, f
+        a, b = np.loadtxt(os.path.join(out_a, f)), np.loadtxt(os.path.join(out_b, f))
+        assert a.shape == b.shape
+        assert np.abs(a - b).mean() < 2e-3 and np.median(np.abs(a - b)) < 2e-4, (f, np.abs(a - b).mean())
     e = np.loadtxt(os.path.join(out_a, files[0]))
     assert e.shape == (500, 16) and np.isfinite(e).all() and np.abs(e).max() > 0.01
 

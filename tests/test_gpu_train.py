@@ -382,3 +382,49 @@ def test_partitioned_init_equals_single_gpu_init(gpu_lib):
     e2, r2 = pt.gather_global()
     pt.close()
     assert np.array_equal(e1, e2) and np.array_equal(r1, r2)
+
+
+@pytest.mark.parametrize("model,D,dist", [("transe", 100, 1), ("transe", 50, 0), ("transh", 100, 0)])
+def test_deterministic_mode_is_bit_reproducible_and_equivalent(gpu_lib, oracle, model, D, dist):
+    """KB2E_FLAG_DETERMINISTIC: fixed-point integer accumulation makes whole training runs bit-identical from run to run
+    (the default floating-point REDs agree only to rounding), and the result stays within fp32 rounding of the default
+    mode's batch semantics (one batch against the fp64 twin, same tolerance as the default kernel's test)."""
+    import kb2e_b200
+    from kb2e_b200 import kg
+    g = kg.make_kg("tiny", seed=4)
+    nE, nR, batches, seed = g["nE"], g["nR"], 10, 123
+    hm, tm = kg.bern_stats(g["train"], nR)
+    runs = []
+    for rep in range(2):
+        with make_ctx(model, D, nE, nR, method=1, distance=dist, batches=batches, rate=LR, margin=1.0, seed=seed,
+                      flags=kb2e_b200.FLAG_DETERMINISTIC) as ctx:
+            ctx.set_train_triples(g["train"])
+            ctx.set_bern(hm, tm)
+            ctx.init_embeddings()
+            loss = np.concatenate([ctx.train_epochs(0, 7), ctx.train_epochs(7, 3)])
+            runs.append((loss,) + download_tables(ctx))
+    for x, y in zip(runs[0], runs[1]):
+        if x is not None:
+            assert np.array_equal(x, y)
+    assert runs[0][0][-1] < runs[0][0][0]
+    # one batch against the deferred-renormalisation twin, like test_batch_matches_deferred_oracle
+    m = kb2e_b200.MODELS[model]
+    rng = np.random.default_rng(5)
+    ent = f32(rng.normal(0, 1.0 / np.sqrt(D), (nE, D)) * 1.05)
+    rel = f32(rng.normal(0, 0.5 / np.sqrt(D), (nR, D)))
+    w = None
+    if m == 1:
+        w = rng.normal(0, 1, (nR, D))
+        w = f32(w / np.linalg.norm(w, axis=1, keepdims=True))
+    pairs = oracle.sampler(g["train"], nE, nR, 1).sample_batch(99, 0, 1500)
+    with make_ctx(model, D, nE, nR, distance=dist, rate=LR, margin=1.0, flags=kb2e_b200.FLAG_DETERMINISTIC) as ctx:
+        upload_tables(ctx, ent, rel, w)
+        loss, active = ctx.train_batch_pairs(pairs)
+        ge, gr, gw = download_tables(ctx)
+    oe, orl, ow = ent.copy(), rel.copy(), None if w is None else w.copy()
+    carry = None if w is None else np.zeros_like(w)
+    oloss, oactive = oracle.train_batch_dfr(m, dist, LR, 1.0, oe, orl, ow, carry, pairs)
+    assert abs(active - oactive) <= 2 and abs(loss - oloss) <= 2e-5 * abs(oloss) + 4.0 * abs(active - oactive)
+    for got, want in ((ge, oe), (gr, orl)) + (((gw, ow),) if m != 0 else ()):
+        diff = np.abs(got - want)
+        assert (diff > 3e-6).mean() < 1e-2 and diff.max() <= 8 * LR

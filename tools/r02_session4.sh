@@ -1,0 +1,30 @@
+#!/bin/bash
+O=gpurun_out
+mkdir -p $O
+timeout 2400 python -m pytest tests -m gpu -q -s > $O/r02_s4_pytest_full.txt 2>&1
+tail -8 $O/r02_s4_pytest_full.txt
+{
+  echo "# config 0: TransE unif L1 size=50, FB15k shape"; timeout 300 python tools/probe.py --model transe --dim 50 --distance 0 --method 0 --epochs 20 --test 100 2>&1 | grep -E "epochs|Error|error"
+  echo "# config 1: TransE bern L2 size=100, FB15k shape"; timeout 300 python tools/probe.py --model transe --dim 100 --distance 1 --epochs 20 --test 100 2>&1 | grep -E "epochs|Error|error"
+  echo "# config 1, stamp scan instead of lists"; KB2E_TRAIN_LIST=0 timeout 300 python tools/probe.py --model transe --dim 100 --distance 1 --epochs 20 --test 100 2>&1 | grep -E "epochs|Error|error"
+  echo "# config 1, 768 threads"; KB2E_TRAIN_NO640=1 timeout 300 python tools/probe.py --model transe --dim 100 --distance 1 --epochs 20 --test 100 2>&1 | grep -E "epochs|Error|error"
+  echo "# config 2: TransH bern size=100, WN18 shape"; timeout 300 python tools/probe.py --model transh --shape wn18 --dim 100 --distance 0 --epochs 20 --test 100 2>&1 | grep -E "epochs|Error|error"
+  echo "# TransH bern size=100, FB15k shape"; timeout 300 python tools/probe.py --model transh --dim 100 --distance 0 --epochs 20 --test 100 2>&1 | grep -E "epochs|Error|error"
+  echo "# TransE L1 size=100, WN18 shape"; timeout 300 python tools/probe.py --model transe --shape wn18 --dim 100 --distance 0 --epochs 20 --test 10 2>&1 | grep -E "epochs|Error|error"
+} > $O/r02_s4_probes.txt 2>&1
+cat $O/r02_s4_probes.txt
+KB2E_TRAIN_TRACE=$O/r02_s4_trace.txt timeout 300 python tools/probe.py --model transe --dim 100 --distance 1 --epochs 10 --test 10 > /dev/null 2>&1
+python tools/trace_report.py $O/r02_s4_trace.txt 5 > $O/r02_s4_trace_report.txt 2>/dev/null
+tail -12 $O/r02_s4_trace_report.txt
+KB2E_TRAIN_TRACE_FINE=1 KB2E_TRAIN_TRACE=$O/r02_s4_trace_fine.txt timeout 300 python tools/probe.py --model transe --dim 100 --distance 1 --epochs 10 --test 10 > /dev/null 2>&1
+{
+  echo "# config 1 ranking: TransE L2 size=100"; timeout 600 python tools/probe.py --model transe --dim 100 --distance 1 --epochs 5 --test 59071 2>&1 | grep -E "rank|Error|error"
+} > $O/r02_s4_rank_probes.txt 2>&1
+cat $O/r02_s4_rank_probes.txt
+timeout 900 python bench.py --steps 5 --warmup 3 > $O/r02_s4_bench.json 2> $O/r02_s4_bench.err || tail -5 $O/r02_s4_bench.err
+cut -c1-600 $O/r02_s4_bench.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r02_s4_bench.json'))
+print('train value %.1f M/s e2e %.1f M/s frac %.3f | eval value %.1f M q/s e2e cold %.1f resident %.1f' % (d['value']/1e6, d['e2e']['value']/1e6, d['roofline']['frac'], d['eval']['value']/1e6, d['eval']['e2e']['value']/1e6, d['eval']['e2e']['resident']['value']/1e6))
+PY
