@@ -2,6 +2,7 @@
 // argument checking.  The kernels live in train.cu / rank.cu.  There is no CPU fallback anywhere:
 // without a usable CUDA device kb2e_create fails with KB2E_ERR_NO_GPU.
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -156,6 +157,7 @@ int kb2e_upload(kb2e_ctx* c, int table, const double* host, int64_t rows, int64_
    // the exact fp64 values stay on the device for ranking; training gets the fp32 rounding of them
    KB2E_CUDA(c, cudaMemcpyAsync(dev, host, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, c->stream));
    c->v64[table] = true;
+   c->tables_epoch++;
    rc = narrow_table(c, table);
    if (rc) return rc;
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -245,22 +247,52 @@ int kb2e_set_test_triples(kb2e_ctx* c, const int32_t* h, const int32_t* t, const
    return KB2E_OK;
 }
 
+// first index in [0, n) whose ids are out of range -> *bad (atomicMin), else *bad stays ~0
+__global__ void validate_triples_kernel(const int32_t* h, const int32_t* t, const int32_t* r, long long n, int nE, int nR, unsigned long long* bad) {
+   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   if (h[i] < 0 || h[i] >= nE || t[i] < 0 || t[i] >= nE || r[i] < 0 || r[i] >= nR) atomicMin(bad, (unsigned long long)i);
+}
+
 int kb2e_add_filter_triples(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t* r, int64_t n) {
    KB2E_ENTER(c);
    if (n < 0) return fail(c, KB2E_ERR_ARG, "kb2e_add_filter_triples: negative count");
    if (n == 0) {
-      c->filt_h.clear(); c->filt_t.clear(); c->filt_r.clear();
+      c->filt_n = 0;
       c->filter_dirty = true;
       return KB2E_OK;
    }
    if (!h || !t || !r) return fail(c, KB2E_ERR_ARG, "kb2e_add_filter_triples: null buffer");
-   for (int64_t i = 0; i < n; i++) {
-      if (h[i] < 0 || h[i] >= c->nE || t[i] < 0 || t[i] >= c->nE || r[i] < 0 || r[i] >= c->nR)
-         return fail(c, KB2E_ERR_ARG, "filter triple " + std::to_string(i) + " has an id out of range");
+   int rc = train_alloc(c);   // counters
+   if (rc) return rc;
+   // The columns go straight from the caller's buffers to the device (a DMA when they are pinned) and are checked there:
+   // no host loop over the set, no host copy of it.  Capacity only grows (doubling), old entries are kept.
+   const size_t need = c->filt_n + (size_t)n;
+   if (need > c->filt_cap) {
+      const size_t cap = std::max(need, 2 * c->filt_cap);
+      int32_t* fresh = nullptr;
+      KB2E_CUDA(c, pool_alloc(c, &fresh, 3 * cap * sizeof(int32_t)));
+      for (int k = 0; k < 3 && c->filt_n; k++) {
+         cudaError_t e = cudaMemcpyAsync(fresh + k * cap, c->filt_dev + k * c->filt_cap, c->filt_n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream);
+         if (e != cudaSuccess) { pool_free(c, fresh); return cuda_fail(c, e, "kb2e_add_filter_triples: regrow"); }
+      }
+      KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+      pool_free(c, c->filt_dev);
+      c->filt_dev = fresh;
+      c->filt_cap = cap;
    }
-   c->filt_h.insert(c->filt_h.end(), h, h + n);
-   c->filt_t.insert(c->filt_t.end(), t, t + n);
-   c->filt_r.insert(c->filt_r.end(), r, r + n);
+   const int32_t* src[3] = {h, t, r};
+   for (int k = 0; k < 3; k++)
+      KB2E_CUDA(c, cudaMemcpyAsync(c->filt_dev + k * c->filt_cap + c->filt_n, src[k], (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+   KB2E_CUDA(c, cudaMemsetAsync(c->counters + 7, 0xff, sizeof(unsigned long long), c->stream));
+   validate_triples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->filt_dev + c->filt_n, c->filt_dev + c->filt_cap + c->filt_n,
+                                                                              c->filt_dev + 2 * c->filt_cap + c->filt_n, n, c->nE, c->nR, c->counters + 7);
+   KB2E_CUDA(c, cudaGetLastError());
+   unsigned long long bad = 0;
+   KB2E_CUDA(c, cudaMemcpyAsync(&bad, c->counters + 7, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
+   KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   if (bad != ~0ull) return fail(c, KB2E_ERR_ARG, "filter triple " + std::to_string(bad) + " has an id out of range");
+   c->filt_n += (size_t)n;
    c->filter_dirty = true;
    return KB2E_OK;
 }

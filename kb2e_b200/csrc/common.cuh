@@ -61,11 +61,31 @@ __device__ __forceinline__ bool hash_contains(const uint64_t* __restrict__ table
 // they are always read/written through L2 (.cg), never through the non-coherent L1 path.
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st_cg4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
+// The same load as ld_cg4, pinned in program order: the compiler sinks an ordinary load into the conditional block that
+// uses it (measured in the list publish of train.cu: the row loads ended up BEHIND the claim they were meant to travel
+// with, one extra L2 round trip per batch); a volatile asm stays where it is written.
+__device__ __forceinline__ float4 ld_cg4_pinned(const float* p) {
+   float4 v;
+   asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+   return v;
+}
 
 // Vector reduction into global memory: one 16-byte RED instead of four scalar atomics (sm_90+).
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// read-only loads pinned in program order (the staged sampler of train_device.cuh issues them one phase ahead of their use)
+__device__ __forceinline__ int4 ld_nc_int4_pinned(const int4* p) {
+   int4 v;
+   asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ uint64_t ld_nc_u64_pinned(const uint64_t* p) {
+   uint64_t v;
+   asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+   return v;
 }
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {

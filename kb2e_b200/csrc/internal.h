@@ -68,9 +68,11 @@ struct kb2e_ctx {
    bool v64[3] = {false, false, false};  // per table: fp64 copy is current
 
    // ---- evaluation set -------------------------------------------------------------------------
-   std::vector<int32_t> test_h, test_t, test_r;
-   std::vector<int32_t> filt_h, filt_t, filt_r;
+   std::vector<int32_t> test_h, test_t, test_r;   // host copy: the per-relation models order their queries on the host
+   int32_t* filt_dev = nullptr;   // known-true triples besides the test set, device-resident: h | t | r columns of filt_cap each
+   size_t filt_n = 0, filt_cap = 0;
    bool filter_dirty = true;
+   uint64_t tables_epoch = 1;     // bumped whenever a table changes (upload, init, training): keys the ranking's derived operands
    struct RankState* rank = nullptr;
    DistState* dist = nullptr;  // entity-partitioned multi-GPU training (train_dist.cu)
    uint32_t* pend = nullptr;           // [3][nE + nR] per-row reference counters of the one-barrier kernel (train_fused.cu)

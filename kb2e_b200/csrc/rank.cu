@@ -84,6 +84,7 @@ struct RankState {
    // it runs beside that kernel on a second stream (fork after E_true, join before finalize)
    cudaStream_t side = nullptr;
    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+   uint64_t ct_epoch = 0;   // tables_epoch the transposed entity table was made for
 };
 
 namespace kb2e {
@@ -547,7 +548,7 @@ static int build_filter(kb2e_ctx* c) {
    RankState* s = c->rank;
    if (!c->filter_dirty && s->seg_key) return KB2E_OK;
    // known triples = test + filter (common/evaluation.cpp:59-61)
-   const size_t nt = c->test_h.size(), nf = c->filt_h.size(), n = nt + nf;
+   const size_t nt = c->test_h.size(), nf = c->filt_n, n = nt + nf;
    if (2 * n >= (1ull << 32)) return fail(c, KB2E_ERR_LIMIT, "filter set larger than 2^31 triples");
    s->n_ent = (uint32_t)(2 * n);
    uint64_t slots = 1024;
@@ -566,10 +567,10 @@ static int build_filter(kb2e_ctx* c) {
    int32_t* ids = s->ids;      // h | t | r columns of test then filter triples
    uint64_t* key_tmp = s->key_tmp;
    int32_t* val_tmp = s->val_tmp;
-   const std::vector<int32_t>* cols[3][2] = {{&c->test_h, &c->filt_h}, {&c->test_t, &c->filt_t}, {&c->test_r, &c->filt_r}};
+   const std::vector<int32_t>* test_cols[3] = {&c->test_h, &c->test_t, &c->test_r};
    for (int k = 0; k < 3; k++) {
-      if (nt) KB2E_CUDA(c, cudaMemcpyAsync(ids + k * n, cols[k][0]->data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-      if (nf) KB2E_CUDA(c, cudaMemcpyAsync(ids + k * n + nt, cols[k][1]->data(), nf * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+      if (nt) KB2E_CUDA(c, cudaMemcpyAsync(ids + k * n, test_cols[k]->data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+      if (nf) KB2E_CUDA(c, cudaMemcpyAsync(ids + k * n + nt, c->filt_dev + k * c->filt_cap, nf * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
    }
    filter_entries_kernel<<<nblk((long long)n, 256), 256, 0, c->stream>>>(ids, ids + n, ids + 2 * n, (long long)n, key_tmp, val_tmp);
    // stable LSD radix sort: by neighbour (24 bits), then by segment key (41 bits) -> (key, neighbour) order
@@ -649,9 +650,11 @@ static int prepare_tables(kb2e_ctx* c) {
    rc = ensure64(c);
    if (rc) return rc;
    RankState* s = c->rank;
+   if (s->ct_epoch == c->tables_epoch) return KB2E_OK;   // the transposed copy is current: tables unchanged since the last call
    dim3 grid(nblk(s->ld, 32), nblk(c->D, 32));
    transpose_kernel<<<grid, dim3(32, 8), 0, c->stream>>>(c->ent64, s->ct0, c->nE, c->D, s->ld);
    KB2E_CUDA(c, cudaGetLastError());
+   s->ct_epoch = c->tables_epoch;
    return KB2E_OK;
 }
 
@@ -793,8 +796,11 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    if (use_tc) {
       rc = tc_init(c, &s->tc);
       if (rc) return rc;
-      rc = tc_prepare_candidates(c, &s->tc);
-      if (rc) return rc;
+      if (s->tc.epoch != c->tables_epoch) {   // operand tiles + max |c| are a function of the entity table alone
+         rc = tc_prepare_candidates(c, &s->tc);
+         if (rc) return rc;
+         s->tc.epoch = c->tables_epoch;
+      }
    }
    while (s->pass_ev.size() < 2 * passes.size()) {
       cudaEvent_t e;
@@ -802,8 +808,11 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       s->pass_ev.push_back(e);
    }
    if (use_trp) {
-      rc = trp_prepare_entities(c, &s->trp);
-      if (rc) return rc;
+      if (s->trp.epoch != c->tables_epoch) {
+         rc = trp_prepare_entities(c, &s->trp);
+         if (rc) return rc;
+         s->trp.epoch = c->tables_epoch;
+      }
       while (s->pass_ev.size() < 4 * passes.size()) {   // + two per pass around the tensor-core projection
          cudaEvent_t e;
          KB2E_CUDA(c, cudaEventCreate(&e));

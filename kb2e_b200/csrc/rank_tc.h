@@ -44,6 +44,7 @@ struct TcState {
    unsigned int* host_count = nullptr;   // pinned: band count of the last tc_run, valid after tc_collect
    float last_ms = 0.f;
    unsigned int last_band = 0;
+   uint64_t epoch = 0;   // kb2e_ctx::tables_epoch the candidate operand tiles were made for
 };
 
 bool tc_supported(const kb2e_ctx* c);

@@ -27,6 +27,7 @@ struct TrpState {
    long long q_cap = 0;
    size_t e_cap = 0;
    cudaEvent_t e0 = nullptr, e1 = nullptr;   // around the tensor-core projection of the last pass
+   uint64_t epoch = 0;                       // kb2e_ctx::tables_epoch the entity operand tiles were made for
 };
 
 // TransR, embedding sizes the tensor-core tiles cover, pre-filter not disabled

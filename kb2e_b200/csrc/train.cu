@@ -412,11 +412,11 @@ __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists&
          if (r1 >= 0) mine1 = atomicExch(a.flag + r1, stamp) != stamp;
       }
       float4 x0[NV], d0[NV], x1[NV], d1[NV];
-      load_row<LPS, NV>(a.tab + (size_t)r0 * P, P, gl, x0);
-      load_row<LPS, NV>(a.dtab + (size_t)r0 * P, P, gl, d0);
+      load_row_pinned<LPS, NV>(a.tab + (size_t)r0 * P, P, gl, x0);   // pinned: issued with the claim, not after it
+      load_row_pinned<LPS, NV>(a.dtab + (size_t)r0 * P, P, gl, d0);
       if (r1 >= 0) {
-         load_row<LPS, NV>(a.tab + (size_t)r1 * P, P, gl, x1);
-         load_row<LPS, NV>(a.dtab + (size_t)r1 * P, P, gl, d1);
+         load_row_pinned<LPS, NV>(a.tab + (size_t)r1 * P, P, gl, x1);
+         load_row_pinned<LPS, NV>(a.dtab + (size_t)r1 * P, P, gl, d1);
       }
       mine0 = __shfl_sync(gmask, mine0, leader);
       mine1 = __shfl_sync(gmask, mine1, leader);
@@ -794,6 +794,7 @@ void train_free(kb2e_ctx* c) {
    pool_free(c, c->ent64); pool_free(c, c->rel64); pool_free(c, c->w64);
    pool_free(c, c->pend);
    pool_free(c, c->cflag);
+   pool_free(c, c->filt_dev);
 }
 
 int train_set_triples(kb2e_ctx* c, const int32_t* h, const int32_t* t, const int32_t* r, int64_t n) {
@@ -849,6 +850,7 @@ int train_init_embeddings(kb2e_ctx* c) {
    }
    KB2E_CUDA(c, cudaGetLastError());
    for (int t = 0; t < 3; t++) { c->v32[t] = true; c->v64[t] = false; }
+   c->tables_epoch++;
    return KB2E_OK;
 }
 
@@ -1144,7 +1146,10 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
       }
    }
    if (loss_out) memcpy(loss_out, loss.data(), (size_t)n_epochs * sizeof(double));
-   if (!phase1_only) for (int t = 0; t < 3; t++) c->v64[t] = false;
+   if (!phase1_only) {
+      for (int t = 0; t < 3; t++) c->v64[t] = false;
+      c->tables_epoch++;
+   }
    return KB2E_OK;
 }
 

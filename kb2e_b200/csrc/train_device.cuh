@@ -71,6 +71,15 @@ __device__ __forceinline__ void load_row(const float* base, int P, int gl, float
 }
 
 template <int LPS, int NV>
+__device__ __forceinline__ void load_row_pinned(const float* base, int P, int gl, float4 (&v)[NV]) {
+#pragma unroll
+   for (int q = 0; q < NV; q++) {
+      int off = (q * LPS + gl) * 4;
+      v[q] = off < P ? ld_cg4_pinned(base + off) : f4(0.f);
+   }
+}
+
+template <int LPS, int NV>
 __device__ __forceinline__ void red_row(float* base, int P, int gl, const float4 (&v)[NV]) {
 #pragma unroll
    for (int q = 0; q < NV; q++) {
@@ -274,7 +283,7 @@ __device__ __forceinline__ void draw_begin(const TrainArgs& a, uint32_t k, uint3
    }
    d.j = j;
    d.coin = (int)(x[2] % 1000u);
-   d.tr = __ldg(a.triples + i);
+   d.tr = ld_nc_int4_pinned(a.triples + i);
 }
 
 __device__ __forceinline__ uint64_t draw_key(const DrawStage& d, bool& corruptTail) {
@@ -286,8 +295,8 @@ __device__ __forceinline__ void draw_probe(const TrainArgs& a, DrawStage& d) {
    if (a.pairs != nullptr) return;
    bool ct;
    const uint64_t slot = mix64(draw_key(d, ct)) & a.hash_mask;
-   d.v0 = __ldg(a.hash + slot);
-   d.v1 = __ldg(a.hash + ((slot + 1) & a.hash_mask));
+   d.v0 = ld_nc_u64_pinned(a.hash + slot);
+   d.v1 = ld_nc_u64_pinned(a.hash + ((slot + 1) & a.hash_mask));
 }
 
 __device__ __forceinline__ Pair draw_finish(const TrainArgs& a, uint32_t k, uint32_t gb, const DrawStage& d) {
