@@ -14,6 +14,8 @@
  *                                   (common/trainer.h:36-37, transh/trainer.h:17, transr/trainer.h:31),
  *                                   TransR seeding (transr/trainer.cpp:88-113), loadEmbeddings
  *                                   (common/evaluation.cpp:74-105), write (common/trainer.cpp:109-127)
+ *   kb2e_set_replicas /
+ *   kb2e_select_replica             (no counterpart: one reference process = one model)
  *   kb2e_train_epochs               Trainer::bfgs (common/trainer.cpp:69-107) incl. the sampler (:78-98),
  *                                   train_kb (:130-149), <model>::gradientUpdate / prebatch / postbatch
  *   kb2e_score                      <model>::tripleEnergy (transe/transe.cpp:10, transh/transh.cpp:10, transr/transr.cpp:13)
@@ -126,6 +128,19 @@ int kb2e_download(kb2e_ctx* ctx, int table, double* host, int64_t rows, int64_t 
  * one persistent launch.  loss_per_epoch[n_epochs] = the value the reference prints per epoch. */
 int kb2e_train_epochs(kb2e_ctx* ctx, int32_t first_epoch, int32_t n_epochs, double* loss_per_epoch);
 int kb2e_get_train_stats(kb2e_ctx* ctx, kb2e_train_stats* out);
+
+/* ---- batched training: several models in one launch (seed / rate / margin sweeps; TransE) ------------------------
+ * The reference trains one model per process and has no sweep driver; its users run it once per setting
+ * (common/args.cpp flags -rate, -margin, -seed).  At FB15k / WN18 shape one model leaves most of a B200 idle (a batch is
+ * a chain of L2 round trips and grid barriers), so n_models independent models of one size on one KG can share every
+ * launch, phase and barrier: each computes exactly what it would compute alone with its seed / rate / margin.
+ *   kb2e_set_replicas     right after kb2e_create, before any table exists.  rates / margins / seeds: n_models values
+ *                         each, or NULL for the context's own (seeds default to seed + index).
+ *   kb2e_init_embeddings  initialises every model from its own seed.
+ *   kb2e_train_epochs     trains all of them; loss_per_epoch receives n_models x n_epochs values, model-major.
+ *   kb2e_select_replica   chooses the model that kb2e_upload / kb2e_download / kb2e_score / kb2e_rank address (0 at first). */
+int kb2e_set_replicas(kb2e_ctx* ctx, int32_t n_models, const double* rates, const double* margins, const uint64_t* seeds);
+int kb2e_select_replica(kb2e_ctx* ctx, int32_t model_index);
 
 /* ---- scoring / ranking ---------------------------------------------------------------------- */
 /* Energies of n triples from the CURRENT tables: precision 0 = the fp32 scoring code the training

@@ -18,7 +18,7 @@ SYMBOLS = [
     "kb2e_create", "kb2e_destroy", "kb2e_last_error", "kb2e_stream", "kb2e_set_train_triples", "kb2e_set_bern",
     "kb2e_init_embeddings", "kb2e_upload", "kb2e_download", "kb2e_train_epochs", "kb2e_get_train_stats",
     "kb2e_score", "kb2e_set_test_triples", "kb2e_add_filter_triples", "kb2e_rank", "kb2e_get_rank_stats",
-    "kb2e_sample_batch", "kb2e_train_batch_pairs", "kb2e_train_batch_deltas", "kb2e_debug_transr_projection",
+    "kb2e_sample_batch", "kb2e_train_batch_pairs", "kb2e_train_batch_deltas", "kb2e_debug_transr_projection", "kb2e_set_replicas", "kb2e_select_replica",
     "kb2e_dist_setup", "kb2e_dist_connect", "kb2e_dist_init_embeddings", "kb2e_dist_upload", "kb2e_dist_download",
     "kb2e_dist_train_epochs", "kb2e_dist_teardown",
 ]
@@ -166,11 +166,25 @@ class Context:
                     "kb2e_download")
         return out
 
+    def set_replicas(self, n_models, rates=None, margins=None, seeds=None):
+        """Batched training: n_models stacked models (call right after construction)."""
+        r = None if rates is None else np.ascontiguousarray(rates, dtype=np.float64)
+        m = None if margins is None else np.ascontiguousarray(margins, dtype=np.float64)
+        s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        self._check(self.lib.kb2e_set_replicas(self.ptr, int(n_models), _p(r, C.c_double), _p(m, C.c_double), _p(s, C.c_uint64)),
+                    "kb2e_set_replicas")
+        self.n_models = int(n_models)
+
+    def select_replica(self, index):
+        self._check(self.lib.kb2e_select_replica(self.ptr, int(index)), "kb2e_select_replica")
+
     def train_epochs(self, first_epoch, n_epochs):
-        loss = np.zeros(max(n_epochs, 1), dtype=np.float64)
+        """Per-epoch losses; after set_replicas(K > 1) an array of shape (K, n_epochs)."""
+        k = getattr(self, "n_models", 1)
+        loss = np.zeros(max(k * n_epochs, 1), dtype=np.float64)
         self._check(self.lib.kb2e_train_epochs(self.ptr, int(first_epoch), int(n_epochs), _p(loss, C.c_double)),
                     "kb2e_train_epochs")
-        return loss[:n_epochs]
+        return loss[:n_epochs] if k == 1 else loss[:k * n_epochs].reshape(k, n_epochs)
 
     def train_stats(self):
         s = TrainStats()

@@ -186,6 +186,16 @@ int kb2e_train_epochs(kb2e_ctx* c, int32_t first_epoch, int32_t n_epochs, double
    return train_run(c, first_epoch, n_epochs, nullptr, 0, loss_per_epoch);
 }
 
+int kb2e_set_replicas(kb2e_ctx* c, int32_t n_models, const double* rates, const double* margins, const uint64_t* seeds) {
+   KB2E_ENTER(c);
+   return train_set_replicas(c, n_models, rates, margins, seeds);
+}
+
+int kb2e_select_replica(kb2e_ctx* c, int32_t model_index) {
+   KB2E_ENTER(c);
+   return train_select_replica(c, model_index);
+}
+
 int kb2e_get_train_stats(kb2e_ctx* c, kb2e_train_stats* out) {
    if (!c || !out) return KB2E_ERR_ARG;
    *out = c->tstats;

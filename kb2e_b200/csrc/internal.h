@@ -27,8 +27,15 @@ struct kb2e_ctx {
    // tab  : [nE + nR][P]  entity rows, then relation rows (one row-index space for the touched lists)
    // dtab : same shape, the batch's accumulated update ("next - cur" of the reference's *_next_ copies)
    // w    : TransH [nR][P] hyperplane normals; TransR [nR][D][P] = M[r][j=in][i=out]; dw same shape
-   float* tab = nullptr;
+   float* tab = nullptr;    // (with several stacked models, kb2e_set_replicas: the SELECTED model's rows; *_all = the allocation)
    float* dtab = nullptr;
+   float* tab_all = nullptr;
+   float* dtab_all = nullptr;
+   uint32_t* flag_all = nullptr;
+   int K = 1, sel = 0;                       // stacked models and the one upload / download / score / rank address
+   std::vector<double> rep_rate, rep_margin;
+   std::vector<uint64_t> rep_seed;
+   void* rep_dev = nullptr;                  // kb2e::RepParams[K]
    float* w = nullptr;
    float* dw = nullptr;
    size_t w_row = 0;           // elements per relation in w
@@ -110,6 +117,8 @@ int train_init_embeddings(kb2e_ctx* ctx);
 int train_run(kb2e_ctx* ctx, int first_epoch, int n_epochs, const int32_t* pairs_dev, int64_t n_pairs, double* loss_out,
               bool phase1_only = false);
 int train_take_deltas(kb2e_ctx* ctx, double* d_ent, double* d_rel, double* d_w);
+int train_set_replicas(kb2e_ctx* ctx, int K, const double* rates, const double* margins, const uint64_t* seeds);
+int train_select_replica(kb2e_ctx* ctx, int m);
 int train_sample(kb2e_ctx* ctx, int epoch, int batch, int64_t count, int32_t* pairs_dev);
 int train_score32(kb2e_ctx* ctx, const int32_t* h_dev, const int32_t* t_dev, const int32_t* r_dev, int64_t n, double* out_dev);
 int num_tables(const kb2e_ctx* ctx);

@@ -98,14 +98,16 @@ __device__ __forceinline__ float4 det_to_float(float4 bits) {
 }
 
 // ---- phase 1: one (positive, negative) pair, TransE and TransH -----------------------------------
+// row_base: first row of the model the pair belongs to in the stacked tables (0 unless several models are trained in one
+// launch, train_sweep_kernel); lr / margin: that model's learning rate and margin.
 template <int MODEL, int LPS, int NV, bool LIST>
-__device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists& L, const Pair s, int gl, uint32_t gmask, uint32_t stamp,
-                                             double& loss_acc, uint32_t& active_acc) {
+__device__ __forceinline__ void process_pair_at(const TrainArgs& a, const RowLists& L, const Pair s, size_t row_base, float lr, float margin,
+                                                int gl, uint32_t gmask, uint32_t stamp, double& loss_acc, uint32_t& active_acc) {
    const int P = a.P, D = a.D;
-   const float* eh = a.tab + (size_t)s.h * P;
-   const float* et = a.tab + (size_t)s.t * P;
-   const float* ec = a.tab + (size_t)s.c * P;
-   const float* er = a.tab + ((size_t)a.nE + s.r) * P;
+   const float* eh = a.tab + (row_base + s.h) * P;
+   const float* et = a.tab + (row_base + s.t) * P;
+   const float* ec = a.tab + (row_base + s.c) * P;
+   const float* er = a.tab + (row_base + a.nE + s.r) * P;
    float4 vh[NV], vt[NV], vc[NV], vr[NV], vw[NV];
    load_row<LPS, NV>(eh, P, gl, vh);
    load_row<LPS, NV>(et, P, gl, vt);
@@ -149,13 +151,12 @@ __device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists&
    ep = gsum<LPS>(ep, gmask);
    en = gsum<LPS>(en, gmask);
    // common/trainer.cpp:138: strict '>'
-   if (!(ep + a.margin > en)) return;
+   if (!(ep + margin > en)) return;
 
    if (gl == 0) {
-      loss_acc += (double)(a.margin + ep - en);
+      loss_acc += (double)(margin + ep - en);
       active_acc++;
    }
-   const float lr = a.lr;
    float4 gp[NV], gn[NV];  // lr * x for the positive / negative triple
 #pragma unroll
    for (int q = 0; q < NV; q++) {
@@ -168,10 +169,10 @@ __device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists&
          gn[q] = (2.f * lr) * rn[q];
       }
    }
-   float* dh = a.dtab + (size_t)s.h * P;
-   float* dt = a.dtab + (size_t)s.t * P;
-   float* dc = a.dtab + (size_t)s.c * P;
-   float* dr = a.dtab + ((size_t)a.nE + s.r) * P;
+   float* dh = a.dtab + (row_base + s.h) * P;
+   float* dt = a.dtab + (row_base + s.t) * P;
+   float* dc = a.dtab + (row_base + s.c) * P;
+   float* dr = a.dtab + (row_base + a.nE + s.r) * P;
    float4 u[NV];
    // relation row: -= m*lr*x  with m = -1 (positive), +1 (negative)
 #pragma unroll
@@ -235,13 +236,19 @@ __device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists&
       if (gl == 0) slot = atomicAdd(L.count + 0, n_ent);
       slot = __shfl_sync(gmask, slot, (threadIdx.x & 31) - gl);
       if (gl < n_ent) {
-         const int row = gl == 0 ? s.h : (gl == 1 ? s.t : (gl == 2 ? s.c : a.nE + s.r));
+         const int row = (int)row_base + (gl == 0 ? s.h : (gl == 1 ? s.t : (gl == 2 ? s.c : a.nE + s.r)));
          if (slot + gl < L.cap_ent) L.ent[slot + gl] = row;
          else a.counters[6] = 1ull;   // cannot happen with the host's capacities; reported as an error if it ever does
       } else if (gl == 3) {
          list_push(L.count + 1 + (stamp & 1u), L.rel[stamp & 1u], L.cap_rel, a.nE + s.r, a.counters);
       }
    }
+}
+
+template <int MODEL, int LPS, int NV, bool LIST>
+__device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists& L, const Pair s, int gl, uint32_t gmask, uint32_t stamp,
+                                             double& loss_acc, uint32_t& active_acc) {
+   process_pair_at<MODEL, LPS, NV, LIST>(a, L, s, 0, a.lr, a.margin, gl, gmask, stamp, loss_acc, active_acc);
 }
 
 // ---- phase 2 -------------------------------------------------------------------------------------
@@ -387,7 +394,7 @@ __device__ __forceinline__ void publish_rows(const TrainArgs& a, long long row_b
 template <int MODEL, int LPS, int NV>
 __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists& L, const int* list, int n, int group, int groups,
                                              uint32_t stamp, uint32_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel,
-                                             unsigned long long* fine = nullptr) {
+                                             unsigned long long* fine = nullptr, int rows_per_model = 0) {
    const int P = a.P;
    const int leader = (threadIdx.x & 31) - gl;
    // tuning aid (KB2E_TRAIN_TRACE_FINE): thread 0 stamps its own group's claim / first row / second row
@@ -400,7 +407,9 @@ __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists&
       }
    };
    auto finish = [&](int r, float4 (&x)[NV], float4 (&d)[NV]) {
-      if (r >= a.nE) { finish_relation<MODEL, LPS, NV>(a, r - a.nE, gl, gmask, x, d); trel += (gl == 0); }
+      // (several stacked models, TransE only: row r of the stack; relation and entity rows are finished alike)
+      const bool is_rel = rows_per_model ? (r % rows_per_model) >= a.nE : r >= a.nE;
+      if (is_rel) { finish_relation<MODEL, LPS, NV>(a, r - a.nE, gl, gmask, x, d); trel += (gl == 0); }
       else { finish_entity<MODEL, LPS, NV, true>(a, L, r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
    };
    for (int i = group; i < n; i += 2 * groups) {
@@ -567,6 +576,122 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
       __syncthreads();
    }
    // counters
+   uint32_t c0 = (gl == 0) ? active_acc : 0u, c1 = tent_acc, c2 = trel_acc;
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+   }
+   if (lane == 0) {
+      if (c0) atomicAdd(a.counters + 0, (unsigned long long)c0);
+      if (c1) atomicAdd(a.counters + 1, (unsigned long long)c1);
+      if (c2) atomicAdd(a.counters + 2, (unsigned long long)c2);
+   }
+}
+
+
+// ================================ batched training: K models in one persistent launch ==============================
+// SURVEY.md 8f row 4 (seed / hyper-parameter sweeps: "tables are tiny; many configs fit at once").  At FB15k shape one
+// model's batch is ~10 us of DEPENDENT L2 round trips and grid barriers with four fifths of the issue slots idle
+// (profiles/README.md): the machine is latency-bound, not throughput-bound.  K independent TransE models of one size on
+// one KG -- different seeds, learning rates, margins -- therefore share the launch, the phases and the barriers: the
+// K x (nE + nR) rows are stacked in tab / dtab / flag, a batch consists of K * batchsize (model, sample) TASKS dealt
+// round-robin over all groups (task tau -> model tau % K, sample tau / K; a group handles tasks_per_group of them, one
+// after the other in phase 1), and the publish walks one list of stacked rows.  Every model computes exactly what it would
+// compute alone (same counter-RNG stream, same batch semantics; bit-identical tables in the deterministic mode --
+// tests/test_gpu_train.py); the batch takes about as long as one model's, so throughput grows almost K-fold.
+// Sampling: lane t of a group owns the group's t-th task and runs the three pipelined stages of train_device.cuh for it (in
+// the single-model kernel all lanes draw the same sample redundantly); finished samples wait in shared memory.
+// The per-model epoch loss is accumulated in shared memory as a 64-bit fixed-point sum (2^-24 units).
+constexpr double kSweepLossScale = 16777216.0;
+
+template <int LPS, int NV, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) train_sweep_kernel(const __grid_constant__ TrainArgs a) {
+   extern __shared__ int s_dyn[];
+   const int K = a.replicas, T = a.tasks_per_group;
+   const int groups_per_block = THREADS / LPS;
+   RowLists L{};
+   L.count = s_dyn;
+   L.cap_ent = a.cap_ent;
+   L.cap_rel = 0;
+   L.ent = s_dyn + 4;
+   L.rel[0] = L.rel[1] = nullptr;
+   int4* s_pairs = reinterpret_cast<int4*>(s_dyn + 4 + ((a.cap_ent + 3) & ~3));           // [groups][T]: h, t, r, c | corruptTail << 31; h = -1: no task
+   unsigned long long* s_loss = reinterpret_cast<unsigned long long*>(s_pairs + (size_t)groups_per_block * T);   // [K]
+   const int lane = threadIdx.x & 31;
+   const int gl = lane % LPS;
+   const uint32_t gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << ((lane / LPS) * LPS));
+   const int group = threadIdx.x / LPS;
+   const long long G = (long long)gridDim.x * groups_per_block;
+   const long long g0 = (long long)group * gridDim.x + blockIdx.x;
+   const long long n_tasks = (long long)K * a.batchsize;
+   const int R = a.nE + a.nR;
+   uint32_t bar_target = 0;
+   uint32_t active_acc = 0, tent_acc = 0, trel_acc = 0;
+   const uint32_t gb_first = (uint32_t)a.first_epoch * (uint32_t)a.batches;
+   const uint32_t n_batches = (uint32_t)a.n_epochs * (uint32_t)a.batches;
+   // this lane's sampling task: the gl-th task of the group
+   const long long tau = g0 + (long long)gl * G;
+   const bool samples = gl < T && tau < n_tasks;
+   const int my_model = samples ? (int)(tau % K) : 0;
+   const uint32_t my_k = (uint32_t)(tau / K);
+   RepParams mine = a.rep[my_model];
+   DrawStage ds;
+   int4* my_slot = s_pairs + (size_t)group * T + gl;
+   auto park = [&](const Pair& p) { *my_slot = make_int4(p.h, p.t, p.r, p.c | (p.corruptTail ? (int)0x80000000 : 0)); };
+   if (threadIdx.x < 4) L.count[threadIdx.x] = 0;
+   for (int m = threadIdx.x; m < K; m += THREADS) s_loss[m] = 0ull;
+   if (gl < T) {
+      if (samples) {
+         park(draw_pair(a, my_k, gb_first, mine.seed_lo, mine.seed_hi));
+         if (n_batches > 1u) draw_begin(a, my_k, gb_first + 1u, ds, mine.seed_lo, mine.seed_hi);
+      } else {
+         *my_slot = make_int4(-1, 0, 0, 0);
+      }
+   }
+   __syncthreads();
+
+   uint32_t rel_batch = 0;
+   for (int ep = 0; ep < a.n_epochs; ep++) {
+      for (int batch = 0; batch < a.batches; batch++, rel_batch++) {
+         const uint32_t gb = gb_first + rel_batch;
+         const uint32_t stamp = a.stamp_base + rel_batch + 1u;
+         // ---- phase 1: the group's tasks, one after the other ----
+         for (int t = 0; t < T; t++) {
+            const int4 pk = s_pairs[(size_t)group * T + t];
+            if (pk.x < 0) break;
+            Pair s;
+            s.h = pk.x; s.t = pk.y; s.r = pk.z; s.c = pk.w & 0x7fffffff; s.corruptTail = pk.w < 0;
+            const int m = (int)((g0 + (long long)t * G) % K);
+            const RepParams rp = a.rep[m];
+            double loss = 0.0;
+            process_pair_at<KB2E_MODEL_TRANSE, LPS, NV, true>(a, L, s, (size_t)m * R, rp.lr, rp.margin, gl, gmask, stamp, loss, active_acc);
+            if (gl == 0 && loss != 0.0) atomicAdd(s_loss + m, (unsigned long long)__double2ll_rn(loss * kSweepLossScale));
+         }
+         grid_barrier(a.barrier, bar_target);
+         const bool more = rel_batch + 1u < n_batches;
+         if (samples && more) draw_probe(a, ds);
+         // ---- phase 2: the CTA's list of stacked rows ----
+         publish_list<KB2E_MODEL_TRANSE, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, stamp + 1u, gl, gmask,
+                                                  tent_acc, trel_acc, nullptr, R);
+         __syncthreads();
+         if (threadIdx.x == 0) L.count[0] = 0;
+         grid_arrive(a.barrier, bar_target);
+         if (samples && more) {
+            park(draw_finish(a, my_k, gb + 1u, ds, mine.seed_lo, mine.seed_hi));
+            if (rel_batch + 2u < n_batches) draw_begin(a, my_k, gb + 2u, ds, mine.seed_lo, mine.seed_hi);
+         }
+         grid_wait(a.barrier, bar_target);   // (its closing bar.sync publishes the parked samples to the whole group)
+      }
+      // epoch losses: one integer atomic per model and CTA (a.loss holds K x n_epochs 64-bit fixed-point sums)
+      __syncthreads();
+      for (int m = threadIdx.x; m < K; m += THREADS) {
+         if (s_loss[m]) atomicAdd(reinterpret_cast<unsigned long long*>(a.loss) + (size_t)m * a.n_epochs + ep, s_loss[m]);
+         s_loss[m] = 0ull;
+      }
+      __syncthreads();
+   }
    uint32_t c0 = (gl == 0) ? active_acc : 0u, c1 = tent_acc, c2 = trel_acc;
 #pragma unroll
    for (int o = 16; o > 0; o >>= 1) {
@@ -760,12 +885,17 @@ static inline unsigned blocks_for(long long n, int threads) { return (unsigned)(
 int train_alloc(kb2e_ctx* c) {
    if (c->tab) return KB2E_OK;
    size_t rows = (size_t)c->nE + c->nR;
-   KB2E_CUDA(c, pool_alloc(c, &c->tab, rows * c->P * sizeof(float)));
-   KB2E_CUDA(c, pool_alloc(c, &c->dtab, rows * c->P * sizeof(float)));
-   KB2E_CUDA(c, cudaMemsetAsync(c->tab, 0, rows * c->P * sizeof(float), c->stream));
-   KB2E_CUDA(c, cudaMemsetAsync(c->dtab, 0, rows * c->P * sizeof(float), c->stream));
-   KB2E_CUDA(c, pool_alloc(c, &c->flag, rows * sizeof(uint32_t)));
-   KB2E_CUDA(c, cudaMemsetAsync(c->flag, 0, rows * sizeof(uint32_t), c->stream));
+   const size_t all = (size_t)c->K * rows;   // K stacked models (kb2e_set_replicas), K = 1 otherwise
+   if (all >= (1ull << 31)) return fail(c, KB2E_ERR_LIMIT, "more than 2^31 rows in the stacked tables");
+   KB2E_CUDA(c, pool_alloc(c, &c->tab_all, all * c->P * sizeof(float)));
+   KB2E_CUDA(c, pool_alloc(c, &c->dtab_all, all * c->P * sizeof(float)));
+   KB2E_CUDA(c, cudaMemsetAsync(c->tab_all, 0, all * c->P * sizeof(float), c->stream));
+   KB2E_CUDA(c, cudaMemsetAsync(c->dtab_all, 0, all * c->P * sizeof(float), c->stream));
+   KB2E_CUDA(c, pool_alloc(c, &c->flag_all, all * sizeof(uint32_t)));
+   KB2E_CUDA(c, cudaMemsetAsync(c->flag_all, 0, all * sizeof(uint32_t), c->stream));
+   c->tab = c->tab_all + (size_t)c->sel * rows * c->P;
+   c->dtab = c->dtab_all + (size_t)c->sel * rows * c->P;
+   c->flag = c->flag_all + (size_t)c->sel * rows;
    if (c->cfg.model != KB2E_MODEL_TRANSE) {
       c->w_row = c->cfg.model == KB2E_MODEL_TRANSH ? (size_t)c->P : (size_t)c->D * c->P;
       KB2E_CUDA(c, pool_alloc(c, &c->w, (size_t)c->nR * c->w_row * sizeof(float)));
@@ -788,7 +918,8 @@ int train_alloc(kb2e_ctx* c) {
 }
 
 void train_free(kb2e_ctx* c) {
-   pool_free(c, c->tab); pool_free(c, c->dtab); pool_free(c, c->w); pool_free(c, c->dw); pool_free(c, c->flag);
+   pool_free(c, c->tab_all); pool_free(c, c->dtab_all); pool_free(c, c->w); pool_free(c, c->dw); pool_free(c, c->flag_all);
+   pool_free(c, c->rep_dev);
    pool_free(c, c->rmin); pool_free(c, c->rmax); pool_free(c, c->triples); pool_free(c, c->stage); pool_free(c, c->hash); pool_free(c, c->pr);
    pool_free(c, c->barrier); pool_free(c, c->loss_dev); pool_free(c, c->counters); pool_free(c, c->pairs_dev);
    pool_free(c, c->ent64); pool_free(c, c->rel64); pool_free(c, c->w64);
@@ -842,7 +973,14 @@ int train_init_embeddings(kb2e_ctx* c) {
    if (rc) return rc;
    uint32_t k0 = (uint32_t)c->cfg.seed, k1 = (uint32_t)(c->cfg.seed >> 32);
    long long rows = (long long)c->nE + c->nR;
-   init_rows_kernel<<<blocks_for(rows * 32, 256), 256, 0, c->stream>>>(c->tab, rows, c->D, c->P, k0, k1, 1u, 0);
+   if (c->K > 1) {
+      // every stacked model from its own seed, exactly as a single-model context with that seed would start
+      for (int m = 0; m < c->K; m++)
+         init_rows_kernel<<<blocks_for(rows * 32, 256), 256, 0, c->stream>>>(c->tab_all + (size_t)m * rows * c->P, rows, c->D, c->P,
+                                                                             (uint32_t)c->rep_seed[m], (uint32_t)(c->rep_seed[m] >> 32), 1u, 0);
+   } else {
+      init_rows_kernel<<<blocks_for(rows * 32, 256), 256, 0, c->stream>>>(c->tab, rows, c->D, c->P, k0, k1, 1u, 0);
+   }
    if (c->cfg.model == KB2E_MODEL_TRANSH) {
       init_rows_kernel<<<blocks_for((long long)c->nR * 32, 256), 256, 0, c->stream>>>(c->w, c->nR, c->D, c->P, k0, k1, 2u, 1);
    } else if (c->cfg.model == KB2E_MODEL_TRANSR) {
@@ -1018,7 +1156,139 @@ static void choose_shape(const kb2e_ctx* c, long long batchsize, int& lps, int& 
    lps = Ls[pick]; nv = Ns[pick]; threads_out = Ts[pick];
 }
 
+// ---- batched training of K stacked models (train_sweep_kernel) -----------------------------------------------
+int train_set_replicas(kb2e_ctx* c, int K, const double* rates, const double* margins, const uint64_t* seeds) {
+   if (c->tab_all) return fail(c, KB2E_ERR_ARG, "kb2e_set_replicas: call it before any table exists (right after kb2e_create)");
+   if (c->cfg.model != KB2E_MODEL_TRANSE) return fail(c, KB2E_ERR_LIMIT, "kb2e_set_replicas: batched training is built for TransE");
+   if (K < 1 || K > 64) return fail(c, KB2E_ERR_ARG, "kb2e_set_replicas: 1 <= K <= 64");
+   c->K = K;
+   c->sel = 0;
+   c->rep_rate.assign(K, c->cfg.rate);
+   c->rep_margin.assign(K, c->cfg.margin);
+   c->rep_seed.resize(K);
+   for (int m = 0; m < K; m++) {
+      if (rates) c->rep_rate[m] = rates[m];
+      if (margins) c->rep_margin[m] = margins[m];
+      c->rep_seed[m] = seeds ? seeds[m] : c->cfg.seed + (uint64_t)m;
+   }
+   return KB2E_OK;
+}
+
+int train_select_replica(kb2e_ctx* c, int m) {
+   if (m < 0 || m >= c->K) return fail(c, KB2E_ERR_ARG, "kb2e_select_replica: no such model");
+   int rc = train_alloc(c);
+   if (rc) return rc;
+   if (m == c->sel) return KB2E_OK;
+   const size_t rows = (size_t)c->nE + c->nR;
+   c->sel = m;
+   c->tab = c->tab_all + (size_t)m * rows * c->P;
+   c->dtab = c->dtab_all + (size_t)m * rows * c->P;
+   c->flag = c->flag_all + (size_t)m * rows;
+   // the fp64 copies (and everything the ranking derives from them) describe the previously selected model
+   for (int t = 0; t < 3; t++) c->v64[t] = false;
+   c->tables_epoch++;
+   return KB2E_OK;
+}
+
+typedef void (*SweepKernel)(const TrainArgs);
+static SweepKernel pick_sweep(int lps, int nv, int threads) {
+#define KB2E_SWEEP(L, N, T) if (lps == L && nv == N && threads == T) return train_sweep_kernel<L, N, T>;
+   KB2E_SWEEP(8, 1, 1024) KB2E_SWEEP(16, 1, 1024) KB2E_SWEEP(32, 1, 1024)
+   KB2E_SWEEP(8, 2, 640) KB2E_SWEEP(16, 2, 640) KB2E_SWEEP(32, 2, 640)
+   KB2E_SWEEP(8, 4, 512) KB2E_SWEEP(16, 4, 512) KB2E_SWEEP(32, 4, 512)
+#undef KB2E_SWEEP
+   return nullptr;
+}
+
+static int sweep_run(kb2e_ctx* c, int first_epoch, int n_epochs, double* loss_out) {
+   const int K = c->K;
+   if (!c->triples || c->n_train == 0) return fail(c, KB2E_ERR_ARG, "no training triples: call kb2e_set_train_triples first");
+   if (!c->have_pr) return fail(c, KB2E_ERR_ARG, "no corruption probabilities: call kb2e_set_bern first");
+   if (c->cfg.batches <= 0) return fail(c, KB2E_ERR_ARG, "batches must be positive");
+   if (!c->v32[0] || !c->v32[1]) return fail(c, KB2E_ERR_ARG, "the stacked models have no values: call kb2e_init_embeddings (or upload every model) first");
+   if ((size_t)K * n_epochs > (size_t)c->loss_cap) {
+      pool_free(c, c->loss_dev);
+      c->loss_dev = nullptr;
+      c->loss_cap = 0;
+      KB2E_CUDA(c, pool_alloc(c, &c->loss_dev, (size_t)K * n_epochs * sizeof(double)));
+      c->loss_cap = K * n_epochs;
+   }
+   TrainArgs a;
+   fill_args(c, a);
+   a.tab = c->tab_all; a.dtab = c->dtab_all; a.flag = c->flag_all;
+   a.first_epoch = first_epoch;
+   a.n_epochs = n_epochs;
+   a.batchsize = c->n_train / c->cfg.batches;
+   a.replicas = K;
+   if (!c->thr_valid) {
+      fill_threshold_kernel<<<blocks_for(c->n_train, 256), 256, 0, c->stream>>>(c->triples, c->n_train, c->pr);
+      KB2E_CUDA(c, cudaGetLastError());
+      c->thr_valid = true;
+   }
+   std::vector<RepParams> rp(K);
+   for (int m = 0; m < K; m++) rp[m] = RepParams{(float)c->rep_rate[m], (float)c->rep_margin[m], (uint32_t)c->rep_seed[m], (uint32_t)(c->rep_seed[m] >> 32)};
+   if (!c->rep_dev) KB2E_CUDA(c, pool_alloc(c, &c->rep_dev, (size_t)K * sizeof(RepParams)));
+   KB2E_CUDA(c, cudaMemcpyAsync(c->rep_dev, rp.data(), (size_t)K * sizeof(RepParams), cudaMemcpyHostToDevice, c->stream));
+   KB2E_CUDA(c, cudaStreamSynchronize(c->stream));   // rp is a local
+   a.rep = static_cast<const RepParams*>(c->rep_dev);
+   int lps, nv, threads;
+   choose_shape(c, a.batchsize, lps, nv, threads);
+   if (nv == 2) threads = 640;
+   SweepKernel k = pick_sweep(lps, nv, threads);
+   if (!k) return fail(c, KB2E_ERR_LIMIT, "no batched training kernel for this embedding size");
+   const int groups = threads / lps;
+   const long long G = (long long)c->num_sms * groups;
+   const long long T = ((long long)K * a.batchsize + G - 1) / G;
+   if (T > lps) return fail(c, KB2E_ERR_LIMIT, "too many models for one launch at this batch size: K * batch size must not exceed " +
+                                                std::to_string(G * lps) + " (model, sample) tasks");
+   a.tasks_per_group = (int)T;
+   a.cap_ent = (int)(4 * groups * T);
+   a.cap_rel = 0;
+   const size_t smem = (size_t)(4 + ((a.cap_ent + 3) & ~3)) * sizeof(int) + (size_t)groups * T * sizeof(int4) + (size_t)K * sizeof(unsigned long long);
+   if (smem > 96 * 1024) return fail(c, KB2E_ERR_LIMIT, "batched training: task lists do not fit in shared memory");
+   KB2E_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   const uint64_t n_batches = (uint64_t)a.batches * (uint64_t)n_epochs;
+   if (n_batches >= (1ull << 31)) return fail(c, KB2E_ERR_LIMIT, "more than 2^31 batches in one launch");
+   if ((uint64_t)c->stamp_base + n_batches + 2 >= (1ull << 32)) {
+      KB2E_CUDA(c, cudaMemsetAsync(c->flag_all, 0, (size_t)K * ((size_t)c->nE + c->nR) * sizeof(uint32_t), c->stream));
+      c->stamp_base = 0;
+   }
+   a.stamp_base = c->stamp_base;
+   KB2E_CUDA(c, cudaMemsetAsync(c->barrier, 0, 64, c->stream));
+   KB2E_CUDA(c, cudaMemsetAsync(c->loss_dev, 0, (size_t)K * n_epochs * sizeof(double), c->stream));
+   KB2E_CUDA(c, cudaMemsetAsync(c->counters + 6, 0, sizeof(unsigned long long), c->stream));
+   void* params[] = {&a};
+   KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+   KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(threads), params, smem, c->stream));
+   KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+   std::vector<long long> fixed((size_t)K * n_epochs);
+   unsigned long long cnt[7];
+   KB2E_CUDA(c, cudaMemcpyAsync(fixed.data(), c->loss_dev, fixed.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+   KB2E_CUDA(c, cudaMemcpyAsync(cnt, c->counters, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+   KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
+   c->stamp_base += (uint32_t)n_batches;
+   if (cnt[6]) return fail(c, KB2E_ERR_LIMIT, "internal: a touched-row list overflowed (tables may be inconsistent)");
+   float ms = 0.f;
+   KB2E_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+   c->tstats.kernel_ms += ms;
+   c->tstats.launches += 1;
+   c->tstats.samples += (uint64_t)K * (uint64_t)a.batchsize * (uint64_t)a.batches * (uint64_t)n_epochs;
+   c->tstats.active = cnt[0];
+   c->tstats.touched_ent = cnt[1];
+   c->tstats.touched_rel = cnt[2];
+   if (loss_out)
+      for (size_t i = 0; i < fixed.size(); i++) loss_out[i] = (double)fixed[i] / kSweepLossScale;
+   for (int t = 0; t < 3; t++) c->v64[t] = false;
+   c->tables_epoch++;
+   return KB2E_OK;
+}
+
 int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_dev, int64_t n_pairs, double* loss_out, bool phase1_only) {
+   if (c->K > 1) {
+      if (pairs_dev || phase1_only) return fail(c, KB2E_ERR_ARG, "the batch test hooks address one model: not available after kb2e_set_replicas(K > 1)");
+      if (n_epochs <= 0) return KB2E_OK;
+      return sweep_run(c, first_epoch, n_epochs, loss_out);
+   }
    { int rc = ensure32(c); if (rc) return rc; }
    TrainArgs a;
    if (n_epochs <= 0) return KB2E_OK;

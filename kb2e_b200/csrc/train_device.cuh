@@ -36,9 +36,17 @@ struct TrainArgs {
    float lr, margin;
    uint32_t seed_lo, seed_hi, flags;
    uint32_t stamp_base;           // batches this context has run before this launch: batch k of the launch stamps rows with stamp_base + k + 1
+   int replicas;                  // batched training (train_sweep_kernel): K models stacked in tab / dtab / flag, K x (nE + nR) rows
+   const struct RepParams* rep;   // [replicas] per-model learning rate, margin, seed
+   int tasks_per_group;           // sweep: (model, sample) tasks one group handles per batch (<= lanes per group)
    int phase1_only;               // test hook (kb2e_train_batch_deltas): stop after the accumulation phase
    int cap_ent, cap_rel;          // LIST kernels: capacities of the per-CTA touched-row lists (train.cu)
    unsigned long long* trace;     // tuning aid (KB2E_TRAIN_TRACE): per-CTA clock stamps of the first batches
+};
+
+struct RepParams {
+   float lr, margin;
+   uint32_t seed_lo, seed_hi;
 };
 
 // ---- small float4 helpers ----------------------------------------------------------------------
@@ -216,7 +224,7 @@ __device__ __forceinline__ int randmax_from(uint32_t x0, uint32_t x1, int x) {
    return res;
 }
 
-__device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32_t gb) {
+__device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32_t gb, uint32_t seed_lo, uint32_t seed_hi) {
    Pair s;
    if (a.pairs != nullptr) {
       const int32_t* p = a.pairs + 6ll * k;
@@ -227,13 +235,13 @@ __device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32
       return s;
    }
    uint32_t x[4];
-   philox4x32(k, gb, 0u, 0u, a.seed_lo, a.seed_hi, x);
+   philox4x32(k, gb, 0u, 0u, seed_lo, seed_hi, x);
    const bool randmax = (a.flags & KB2E_FLAG_SAMPLER_RANDMAX) != 0u;
    uint64_t i = mulhi64(((uint64_t)x[0] << 32) | x[1], (uint64_t)a.n_train);
    int j = (int)mulhi32(x[3], (uint32_t)a.nE);
    if (randmax) {
       uint32_t y[4];
-      philox4x32(k, gb, 0u, 1u, a.seed_lo, a.seed_hi, y);
+      philox4x32(k, gb, 0u, 1u, seed_lo, seed_hi, y);
       i = (uint64_t)randmax_from(x[0], x[1], (int)a.n_train);
       j = randmax_from(y[0], y[1], a.nE);
    }
@@ -244,13 +252,15 @@ __device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32
    for (uint32_t att = 1; att < 64; att++) {
       uint64_t key = s.corruptTail ? pack_triple(s.h, s.r, j) : pack_triple(j, s.r, s.t);
       if (!hash_contains(a.hash, a.hash_mask, key)) break;
-      philox4x32(k, gb, att, 0u, a.seed_lo, a.seed_hi, x);
+      philox4x32(k, gb, att, 0u, seed_lo, seed_hi, x);
       j = randmax ? randmax_from(x[0], x[1], a.nE) : (int)mulhi32(x[0], (uint32_t)a.nE);
    }
    s.c = j;
    return s;
 }
 
+
+__device__ __forceinline__ Pair draw_pair(const TrainArgs& a, uint32_t k, uint32_t gb) { return draw_pair(a, k, gb, a.seed_lo, a.seed_hi); }
 
 // ---- the same sampler in three stages, for software pipelining across the phases of a batch -------------------------
 // draw_pair is a chain of dependent loads (triple -> corruption side -> hash probe): 2-3 L2 round trips.  Run in one piece
@@ -269,21 +279,25 @@ struct DrawStage {
    int coin;   // 0..999, compared with the relation's corruption threshold
 };
 
-__device__ __forceinline__ void draw_begin(const TrainArgs& a, uint32_t k, uint32_t gb, DrawStage& d) {
+__device__ __forceinline__ void draw_begin(const TrainArgs& a, uint32_t k, uint32_t gb, DrawStage& d, uint32_t seed_lo, uint32_t seed_hi) {
    if (a.pairs != nullptr) return;
    uint32_t x[4];
-   philox4x32(k, gb, 0u, 0u, a.seed_lo, a.seed_hi, x);
+   philox4x32(k, gb, 0u, 0u, seed_lo, seed_hi, x);
    uint64_t i = mulhi64(((uint64_t)x[0] << 32) | x[1], (uint64_t)a.n_train);
    int j = (int)mulhi32(x[3], (uint32_t)a.nE);
    if (a.flags & KB2E_FLAG_SAMPLER_RANDMAX) {
       uint32_t y[4];
-      philox4x32(k, gb, 0u, 1u, a.seed_lo, a.seed_hi, y);
+      philox4x32(k, gb, 0u, 1u, seed_lo, seed_hi, y);
       i = (uint64_t)randmax_from(x[0], x[1], (int)a.n_train);
       j = randmax_from(y[0], y[1], a.nE);
    }
    d.j = j;
    d.coin = (int)(x[2] % 1000u);
    d.tr = ld_nc_int4_pinned(a.triples + i);
+}
+
+__device__ __forceinline__ void draw_begin(const TrainArgs& a, uint32_t k, uint32_t gb, DrawStage& d) {
+   draw_begin(a, k, gb, d, a.seed_lo, a.seed_hi);
 }
 
 __device__ __forceinline__ uint64_t draw_key(const DrawStage& d, bool& corruptTail) {
@@ -299,7 +313,7 @@ __device__ __forceinline__ void draw_probe(const TrainArgs& a, DrawStage& d) {
    d.v1 = ld_nc_u64_pinned(a.hash + ((slot + 1) & a.hash_mask));
 }
 
-__device__ __forceinline__ Pair draw_finish(const TrainArgs& a, uint32_t k, uint32_t gb, const DrawStage& d) {
+__device__ __forceinline__ Pair draw_finish(const TrainArgs& a, uint32_t k, uint32_t gb, const DrawStage& d, uint32_t seed_lo, uint32_t seed_hi) {
    if (a.pairs != nullptr) return draw_pair(a, k, gb);
    Pair s;
    s.h = d.tr.x; s.t = d.tr.y; s.r = d.tr.z;
@@ -320,7 +334,7 @@ __device__ __forceinline__ Pair draw_finish(const TrainArgs& a, uint32_t k, uint
    if (hit) {
       for (uint32_t att = 1; att < 64; att++) {
          uint32_t x[4];
-         philox4x32(k, gb, att, 0u, a.seed_lo, a.seed_hi, x);
+         philox4x32(k, gb, att, 0u, seed_lo, seed_hi, x);
          j = (a.flags & KB2E_FLAG_SAMPLER_RANDMAX) ? randmax_from(x[0], x[1], a.nE) : (int)mulhi32(x[0], (uint32_t)a.nE);
          const uint64_t key2 = s.corruptTail ? pack_triple(s.h, s.r, j) : pack_triple(j, s.r, s.t);
          if (!hash_contains(a.hash, a.hash_mask, key2)) break;
@@ -328,6 +342,10 @@ __device__ __forceinline__ Pair draw_finish(const TrainArgs& a, uint32_t k, uint
    }
    s.c = j;
    return s;
+}
+
+__device__ __forceinline__ Pair draw_finish(const TrainArgs& a, uint32_t k, uint32_t gb, const DrawStage& d) {
+   return draw_finish(a, k, gb, d, a.seed_lo, a.seed_hi);
 }
 
 // ---- phase-2 row walk ------------------------------------------------------------------------------

@@ -428,3 +428,75 @@ def test_deterministic_mode_is_bit_reproducible_and_equivalent(gpu_lib, oracle, 
     for got, want in ((ge, oe), (gr, orl)) + (((gw, ow),) if m != 0 else ()):
         diff = np.abs(got - want)
         assert (diff > 3e-6).mean() < 1e-2 and diff.max() <= 8 * LR
+
+
+@pytest.mark.parametrize("D,dist,K", [(100, 1, 4), (50, 0, 3), (20, 0, 7)])
+def test_batched_models_equal_the_same_models_trained_alone(gpu_lib, D, dist, K):
+    """kb2e_set_replicas: K TransE models (different seeds, rates, margins) trained in ONE persistent launch each compute
+    exactly what they compute alone.  In the deterministic mode (fixed-point accumulation: sums do not depend on the order
+    of the additions) the tables are bit-identical to K single-model runs; the per-epoch losses agree to the rounding of
+    the two loss accumulators."""
+    import kb2e_b200
+    from kb2e_b200 import kg, TABLE_ENTITY, TABLE_RELATION
+    g = kg.make_kg("tiny", seed=4)
+    nE, nR, batches = g["nE"], g["nR"], 10
+    hm, tm = kg.bern_stats(g["train"], nR)
+    seeds = [1000 + 17 * m for m in range(K)]
+    rates = [0.01 * (1 + 0.5 * (m % 3)) for m in range(K)]
+    margins = [1.0 + 0.25 * (m % 2) for m in range(K)]
+    alone = []
+    for m in range(K):
+        with make_ctx("transe", D, nE, nR, method=1, distance=dist, batches=batches, rate=rates[m], margin=margins[m], seed=seeds[m],
+                      flags=kb2e_b200.FLAG_DETERMINISTIC) as ctx:
+            ctx.set_train_triples(g["train"])
+            ctx.set_bern(hm, tm)
+            ctx.init_embeddings()
+            loss = np.concatenate([ctx.train_epochs(0, 4), ctx.train_epochs(4, 2)])
+            alone.append((loss, ctx.download(TABLE_ENTITY), ctx.download(TABLE_RELATION)))
+    with make_ctx("transe", D, nE, nR, method=1, distance=dist, batches=batches, rate=0.5, margin=9.0, seed=1,
+                  flags=kb2e_b200.FLAG_DETERMINISTIC) as ctx:
+        ctx.set_replicas(K, rates, margins, seeds)
+        ctx.set_train_triples(g["train"])
+        ctx.set_bern(hm, tm)
+        ctx.init_embeddings()
+        loss = np.concatenate([ctx.train_epochs(0, 4), ctx.train_epochs(4, 2)], axis=1)
+        assert loss.shape == (K, 6)
+        st = ctx.train_stats()
+        assert st["samples"] == K * 6 * batches * (len(g["train"]) // batches)
+        for m in range(K):
+            ctx.select_replica(m)
+            e, r = ctx.download(TABLE_ENTITY), ctx.download(TABLE_RELATION)
+            assert np.array_equal(e, alone[m][1]) and np.array_equal(r, alone[m][2]), m
+            assert np.allclose(loss[m], alone[m][0], rtol=1e-6)
+        # ranking addresses the selected model
+        ctx.set_test_triples(g["test"][:20])
+        ctx.add_filter_triples(g["train"])
+        ctx.select_replica(0)
+        r0 = ctx.rank()["sums"]
+        ctx.select_replica(K - 1)
+        r1 = ctx.rank()["sums"]
+        assert not np.array_equal(r0, r1)
+        with pytest.raises(kb2e_b200.Kb2eError):
+            ctx.train_batch_pairs(np.array([[0, 1, 0, 0, 2, 0]]))   # the batch hooks address one model
+
+
+def test_batched_models_default_mode_learn_like_single_models(gpu_lib):
+    """Default (floating-point RED) mode: every stacked model's loss curve follows the single-model run of its seed."""
+    from kb2e_b200 import kg
+    g = kg.make_kg("tiny", seed=4)
+    nE, nR, D, batches, K = g["nE"], g["nR"], 50, 10, 5
+    hm, tm = kg.bern_stats(g["train"], nR)
+    with make_ctx("transe", D, nE, nR, method=1, distance=0, batches=batches, rate=LR, margin=1.0, seed=40) as ctx:
+        ctx.set_replicas(K)
+        ctx.set_train_triples(g["train"])
+        ctx.set_bern(hm, tm)
+        ctx.init_embeddings()
+        loss = ctx.train_epochs(0, 30)
+    for m in (0, K - 1):
+        with make_ctx("transe", D, nE, nR, method=1, distance=0, batches=batches, rate=LR, margin=1.0, seed=40 + m) as ctx:
+            ctx.set_train_triples(g["train"])
+            ctx.set_bern(hm, tm)
+            ctx.init_embeddings()
+            single = ctx.train_epochs(0, 30)
+        assert np.allclose(loss[m][:3], single[:3], rtol=1e-3)
+        assert abs(loss[m][-1] - single[-1]) < 0.1 * single[-1] and loss[m][-1] < 0.5 * loss[m][0]
