@@ -300,6 +300,12 @@ def run_product(args):
         ev_h2d = int(ent_eval.nbytes + rel_eval.nbytes + 3 * p_test[0].nbytes + 3 * p_filt[0].nbytes)
         ev_d2h = int(4 * 4 * 2 * (hi - lo) + 32)
         ev_launches = int(r1["launches"] - r0["launches"])
+        # ---- batched training: 8 models of the same configuration (different seeds) in one launch ----------------------
+        sweep = None
+        try:
+            sweep = run_sweep(local, rank, train, head_mean, tail_mean, nE, nR, hbm_peak, peak_src, flush, K, W)
+        except Exception as exc:
+            sweep = {"error": repr(exc)}
         # ---- entity-partitioned training at the scaled shape (BASELINE configs[4]), N > 1 only ---------------
         part = None
         if not args.no_partitioned:
@@ -342,6 +348,7 @@ def run_product(args):
                      "algorithmic_bytes_per_launch": abytes / max(launches, 1),
                      "note": "algorithmic bytes (SURVEY 8d) / CUDA-event time of the persistent launch; tables are L2-resident, so DRAM traffic is far below the algorithmic bytes"},
         "cpu_baseline": cpu_train,
+        "sweep": sweep,
         "partitioned": part,
         "eval": {
             "metric": "eval_queries_per_s", "value": ev_value, "unit": "queries/s", "ms_per_step": sum(ev_ms) / KE, "steps": KE,
@@ -369,6 +376,44 @@ def run_product(args):
     ctx.close(); ev.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_sweep(local, rank, train, head_mean, tail_mean, nE, nR, hbm_peak, peak_src, flush, K, W, n_models=8):
+    """n_models independent TransE models of the headline configuration (seeds seed .. seed + n_models - 1)
+    trained in ONE persistent launch per epoch (kb2e_set_replicas).  One model leaves the B200 latency-bound (a batch is a chain
+    of L2 round trips and two grid barriers, profiles/README.md); stacked models share launch, phases and barriers, each
+    computing exactly what it computes alone (tests/test_gpu_train.py).  value = pairs of ALL models per second."""
+    import torch
+
+    import kb2e_b200
+    with kb2e_b200.Context(CFG["model"], CFG["dim"], nE, nR, method=CFG["method"], distance=CFG["distance"], batches=CFG["batches"],
+                           rate=CFG["rate"], margin=CFG["margin"], seed=1 + rank, device=local) as ctx:
+        ctx.set_replicas(n_models)
+        ctx.set_train_triples(train)
+        ctx.set_bern(head_mean, tail_mean)
+        ctx.init_embeddings()
+        for e in range(W):
+            ctx.train_epochs(e, 1)
+        s0 = ctx.train_stats()
+        for e in range(W, W + K):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            loss = ctx.train_epochs(e, 1)
+        s1 = ctx.train_stats()
+    ms = s1["kernel_ms"] - s0["kernel_ms"]
+    n = s1["samples"] - s0["samples"]
+    touched = (s1["touched_ent"] - s0["touched_ent"]) + (s1["touched_rel"] - s0["touched_rel"])
+    abytes, alpha = algorithmic_bytes(n, s1["active"] - s0["active"], touched, CFG["dim"])
+    achieved = abytes / (ms * 1e-3) / 1e9
+    return {"metric": "train_triples_per_s", "value": n / (ms * 1e-3), "unit": "triples/s", "models": n_models, "steps": K,
+            "ms_per_step": ms / K, "alpha": alpha,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "kb2e::train_sweep_kernel<16 lanes x 2 float4, 640 threads>",
+                         "note": "aggregate algorithmic bytes of the stacked models (SURVEY 8d) / CUDA-event time of the launch; "
+                                 "8 x 13 MB of tables stay L2-resident"},
+            "config": {"workload": WORKLOAD + " -- %d models, seeds %d..%d, one launch per epoch" % (n_models, 1 + rank, rank + n_models),
+                       "step": "one epoch of every model = %d x 100 batches x 4831 pairs" % n_models},
+            "final_loss_per_model": [float(x) for x in np.atleast_2d(loss)[:, -1]]}
 
 
 def run_scaled_single(local, hbm_peak, peak_src):

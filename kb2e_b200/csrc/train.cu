@@ -638,6 +638,13 @@ __global__ void __launch_bounds__(THREADS, 1) train_sweep_kernel(const __grid_co
    const uint32_t my_k = (uint32_t)(tau / K);
    RepParams mine = a.rep[my_model];
    DrawStage ds;
+   int trace_slot = 0;
+#define KB2E_STRACE()                                                                                 \
+   if (a.trace != nullptr && threadIdx.x == 0 && trace_slot < kTraceSlots) {                          \
+      unsigned long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+      a.trace[(size_t)blockIdx.x * kTraceSlots + trace_slot++] = t_;                                  \
+   }
    int4* my_slot = s_pairs + (size_t)group * T + gl;
    auto park = [&](const Pair& p) { *my_slot = make_int4(p.h, p.t, p.r, p.c | (p.corruptTail ? (int)0x80000000 : 0)); };
    if (threadIdx.x < 4) L.count[threadIdx.x] = 0;
@@ -657,6 +664,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_sweep_kernel(const __grid_co
       for (int batch = 0; batch < a.batches; batch++, rel_batch++) {
          const uint32_t gb = gb_first + rel_batch;
          const uint32_t stamp = a.stamp_base + rel_batch + 1u;
+         KB2E_STRACE();
          // ---- phase 1: the group's tasks, one after the other ----
          for (int t = 0; t < T; t++) {
             const int4 pk = s_pairs[(size_t)group * T + t];
@@ -669,14 +677,18 @@ __global__ void __launch_bounds__(THREADS, 1) train_sweep_kernel(const __grid_co
             process_pair_at<KB2E_MODEL_TRANSE, LPS, NV, true>(a, L, s, (size_t)m * R, rp.lr, rp.margin, gl, gmask, stamp, loss, active_acc);
             if (gl == 0 && loss != 0.0) atomicAdd(s_loss + m, (unsigned long long)__double2ll_rn(loss * kSweepLossScale));
          }
+         KB2E_STRACE();
          grid_barrier(a.barrier, bar_target);
+         KB2E_STRACE();
          const bool more = rel_batch + 1u < n_batches;
          if (samples && more) draw_probe(a, ds);
          // ---- phase 2: the CTA's list of stacked rows ----
          publish_list<KB2E_MODEL_TRANSE, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, stamp + 1u, gl, gmask,
                                                   tent_acc, trel_acc, nullptr, R);
+         KB2E_STRACE();
          __syncthreads();
          if (threadIdx.x == 0) L.count[0] = 0;
+         KB2E_STRACE();
          grid_arrive(a.barrier, bar_target);
          if (samples && more) {
             park(draw_finish(a, my_k, gb + 1u, ds, mine.seed_lo, mine.seed_hi));
@@ -1257,10 +1269,28 @@ static int sweep_run(kb2e_ctx* c, int first_epoch, int n_epochs, double* loss_ou
    KB2E_CUDA(c, cudaMemsetAsync(c->barrier, 0, 64, c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->loss_dev, 0, (size_t)K * n_epochs * sizeof(double), c->stream));
    KB2E_CUDA(c, cudaMemsetAsync(c->counters + 6, 0, sizeof(unsigned long long), c->stream));
+   const char* trace_path = getenv("KB2E_TRAIN_TRACE");
+   unsigned long long* trace_dev = nullptr;
+   if (trace_path) {
+      KB2E_CUDA(c, pool_alloc(c, &trace_dev, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long)));
+      KB2E_CUDA(c, cudaMemsetAsync(trace_dev, 0, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long), c->stream));
+      a.trace = trace_dev;
+   }
    void* params[] = {&a};
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
    KB2E_CUDA(c, cudaLaunchCooperativeKernel((void*)k, dim3(c->num_sms), dim3(threads), params, smem, c->stream));
    KB2E_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+   if (trace_dev) {
+      std::vector<unsigned long long> tr((size_t)c->num_sms * kTraceSlots);
+      cudaMemcpyAsync(tr.data(), trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+      cudaStreamSynchronize(c->stream);
+      pool_free(c, trace_dev);
+      if (FILE* f = fopen(trace_path, "w")) {
+         for (int b = 0; b < c->num_sms; b++)
+            for (int q = 0; q < kTraceSlots; q++) fprintf(f, "%llu%c", tr[(size_t)b * kTraceSlots + q], q + 1 == kTraceSlots ? '\n' : ' ');
+         fclose(f);
+      }
+   }
    std::vector<long long> fixed((size_t)K * n_epochs);
    unsigned long long cnt[7];
    KB2E_CUDA(c, cudaMemcpyAsync(fixed.data(), c->loss_dev, fixed.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
