@@ -24,6 +24,10 @@ ap.add_argument("--shape", default="scaled")
 ap.add_argument("--dim", type=int, default=200)
 ap.add_argument("--epochs", type=int, default=2)
 ap.add_argument("--skip-parity", action="store_true")
+ap.add_argument("--skip-throughput", action="store_true")
+ap.add_argument("--abort-test", action="store_true",
+                help="failure injection: the last rank never launches; the others must give up at their first cross-GPU barrier "
+                     "(KB2E_ERR_PEER after KB2E_DIST_TIMEOUT_MS) instead of hanging their GPUs")
 args = ap.parse_args()
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -60,7 +64,42 @@ if not args.skip_parity:
         assert np.allclose(loss1, loss, rtol=1e-3), (loss1, loss)
         assert np.abs(e1 - e2).mean() < 5e-5 and np.abs(r1 - r2).max() < 1e-2
 
+if args.abort_test and world > 1:
+    os.environ["KB2E_DIST_TIMEOUT_MS"] = "1500"
+    g = kg.make_kg("tiny", seed=3)
+    pt = PartitionedTrainer(24, g["nE"], g["nR"], rank, world, local, method=0, distance=1, batches=10, rate=0.01, margin=1.0, seed=5)
+    pt.set_training_set(g["train"], None, None)
+    pt.init_embeddings()
+    pt.train_epochs(0, 1)                       # a healthy collective launch first
+    t0 = time.time()
+    status = "skipped the launch"
+    if rank != world - 1:
+        try:
+            pt.ctx.dist_train_epochs(1, 1)      # the last rank never shows up
+            status = "returned OK (WRONG)"
+        except kb2e_b200.Kb2eError as e:
+            status = str(e)[:160]
+    took = time.time() - t0
+    again = None
+    if rank != world - 1:
+        try:
+            pt.ctx.dist_train_epochs(2, 1)
+        except kb2e_b200.Kb2eError as e:        # the context refuses further partitioned launches
+            again = str(e)[:80]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (rank, status, round(took, 2), again))
+    if rank == 0:
+        out["abort_test"] = gathered
+        assert all(("(5)" in s and t < 10 and a is not None) for r, s, t, a in gathered if r != world - 1), gathered
+    pt.ctx.close()
+
 nE, nR, ntr, _, _, _ = kg.SHAPES[args.shape]
+if args.skip_throughput:
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    sys.exit(0)
 rng = np.random.default_rng(1)   # same seed on every rank: identical synthetic triples (throughput only)
 train = (rng.integers(0, nE, ntr, dtype=np.int32), rng.integers(0, nE, ntr, dtype=np.int32), rng.integers(0, nR, ntr, dtype=np.int32))
 pt = PartitionedTrainer(args.dim, nE, nR, rank, world, local, method=0, distance=1, batches=100, rate=0.01, margin=1.0, seed=1)
