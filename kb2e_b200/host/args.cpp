@@ -76,6 +76,12 @@ EmbeddingArguments parseArgs(int argc, char** argv) {
       {"device", [&](const char* v) { a.device = atoi(v); }},
       {"gpus", [&](const char* v) { a.gpus = atoi(v); }},
       {"deterministic", [&](const char* v) { a.deterministic = atoi(v); }},
+      {"eval-every", [&](const char* v) { a.evalEvery = atoi(v); }},
+      {"eval-after", [&](const char* v) { a.evalAfter = atoi(v); }},
+      {"resume", [&](const char* v) { a.resume = atoi(v); }},
+      {"first-epoch", [&](const char* v) { a.firstEpoch = atoi(v); }},
+      {"checkpoint-every", [&](const char* v) { a.checkpointEvery = atoi(v); }},
+      {"seed-epochs", [&](const char* v) { a.seedEpochs = atoi(v); }},
       {"sampler", [&](const char* v) { a.samplerRandMax = (std::strcmp(v, "reference") == 0 || std::strcmp(v, "randmax") == 0 || atoi(v) == 1); }},
    };
    for (const Option& o : options) {
@@ -105,6 +111,12 @@ void printUsage(const char* invokedFile) {
    printf("   --%s [0] (B200 build only: CUDA device ordinal)\n", "device");
    printf("   --%s [1] (B200 build only, eval programs: shard the test triples over this many GPUs)\n", "gpus");
    printf("   --%s [0] (B200 build only, TransE / TransH training: 1 = bit-reproducible runs, fixed-point accumulation)\n", "deterministic");
+   printf("   --%s [0] (B200 build only, train programs: filtered rank of valid.txt every N epochs, tables stay on the device)\n", "eval-every");
+   printf("   --%s [0] (B200 build only, train programs: 1 = rank test.txt after training in the same process)\n", "eval-after");
+   printf("   --%s [0] (B200 build only, train programs: 1 = start from the tables in --outdir; see --first-epoch)\n", "resume");
+   printf("   --%s [0] (B200 build only, train programs: epoch number the run starts at)\n", "first-epoch");
+   printf("   --%s [0] (B200 build only, train programs: write the output files every N epochs as well)\n", "checkpoint-every");
+   printf("   --%s [0] (B200 build only, trainTransR: train the TransE seed model for N epochs in this process instead of reading seed files)\n", "seed-epochs");
    printf("   --%s [uniform] (B200 build only: 'reference' draws indices with the distribution of the reference's randMax)\n", "sampler");
 }
 

@@ -35,6 +35,13 @@ struct EmbeddingArguments {
    // (common/utils.cpp:113-120), for trained-model parity with the shipped reference
    int samplerRandMax = 0;
    int deterministic = 0;   // 1: bit-reproducible training (KB2E_FLAG_DETERMINISTIC; TransE, TransH)
+   // train programs, SURVEY.md 8f rows 2-4 (none of these exists in the reference; all default to its behaviour)
+   int evalEvery = 0;       // > 0: filtered MeanRank / Hits@10 of valid.txt every that many epochs, on the device-resident tables
+   int evalAfter = 0;       // 1: rank test.txt after training in the same process (the lines evalTrans* prints), no text round trip
+   int resume = 0;          // 1: start from the tables in --outdir (a previous run's output) instead of a fresh initialisation
+   int firstEpoch = 0;      // epoch number the run starts at (continues the counter-RNG stream and the "Epoch:" numbering of a resumed run)
+   int checkpointEvery = 0; // > 0: write the output files every that many epochs as well
+   int seedEpochs = 0;      // TransR: > 0 trains the TransE (--seedmethod) seed model for that many epochs in this process instead of reading seed files
 
    EmbeddingArguments();
    std::string to_string() const;  // the "Options: [...]" banner, byte-compatible with the reference

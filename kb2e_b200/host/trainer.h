@@ -37,6 +37,15 @@ class Trainer {
       std::vector<double> headMean_, tailMean_;  // relation{Head,Tail}MeanCooccurrence_ (trainer.h:53-55)
       std::vector<double> epochLoss_;
       kb2e_ctx* ctx_ = nullptr;
+      // --eval-every / --eval-after: valid.txt and test.txt (loaded on demand), ranked on the context that trains
+      std::vector<int> validH_, validT_, validR_, testH_, testT_, testR_;
+      bool evalSetsLoaded_ = false;
+      int rankingSet_ = -1;   // which working set the context currently holds: 0 valid, 1 test
+
+      void loadEvalSets();
+      void rankOnDevice(int which, int epoch);     // prints the evaluation lines (common/evaluation.cpp:247-250)
+      void seedTransRInProcess();                  // --seed-epochs: transr/trainer.cpp:88-113 without the text round trip
+      void loadResumeTables();                     // --resume
 
       void computeBernStatistics();  // common/trainer.cpp:171-194
       void prepTrain();              // common/trainer.cpp:34-58, transh/trainer.cpp:77-88, transr/trainer.cpp:70-114

@@ -189,3 +189,63 @@ def test_eval_program_shards_the_test_set_over_gpus(data, tmp_path):
         assert parse_eval(o) == one, (gpus, o)
     rc, o = run(os.path.join(OURS, "evalTransE"), *common, "--gpus", n + 1)
     assert rc == 3 and "kb2e_create failed" in o
+
+
+def test_validation_during_training_and_evaluation_in_the_same_process(data, tmp_path):
+    """--eval-every K ranks valid.txt on the device-resident tables while training, --eval-after 1 ranks
+    test.txt at the end with the lines evalTrans* prints; evalTransE on the written files (6-decimal text) agrees."""
+    datadir, g = data
+    out = str(tmp_path)
+    common = ["--datadir", datadir, "--outdir", out, "--size", 16, "--rate", 0.01, "--method", 1, "--batches", 10, "--seed", 5]
+    rc, o = run(os.path.join(OURS, "trainTransE"), *common, "--epochs", 40, "--eval-every", 10, "--eval-after", 1)
+    assert rc == 0, o
+    valid = re.findall(r"Valid @ epoch (\d+) -- Raw Rank: ([0-9.]+), Hits@10: ([0-9.]+); Filtered Rank: ([0-9.]+), Hits@10: ([0-9.]+)", o)
+    assert [int(v[0]) for v in valid] == [10, 20, 30, 40]
+    assert float(valid[-1][3]) < float(valid[0][3])          # validation rank improves
+    assert all(float(v[3]) <= float(v[1]) for v in valid)     # filtered <= raw
+    inproc = parse_eval(o)
+    rc, eo = run(os.path.join(OURS, "evalTransE"), *common)
+    assert rc == 0, eo
+    files = parse_eval(eo)
+    for k in ("Raw", "Filtered"):
+        assert abs(inproc[k][0] - files[k][0]) < 1.0 and abs(inproc[k][1] - files[k][1]) < 0.02, (inproc, files)
+
+
+def test_resume_and_checkpoints(data, tmp_path):
+    """--checkpoint-every writes the output files during the run; --resume 1 --first-epoch N continues
+    from them (same counter-RNG stream, same epoch numbering) where an uninterrupted run would be, up to the 6-decimal text."""
+    datadir, g = data
+    a, b = str(tmp_path / "straight"), str(tmp_path / "resumed")
+    os.makedirs(a), os.makedirs(b)
+    common = ["--datadir", datadir, "--size", 16, "--rate", 0.01, "--method", 1, "--batches", 10, "--seed", 5, "--deterministic", 1]
+    rc, oa = run(os.path.join(OURS, "trainTransE"), *common, "--outdir", a, "--epochs", 40)
+    assert rc == 0, oa
+    rc, ob1 = run(os.path.join(OURS, "trainTransE"), *common, "--outdir", b, "--epochs", 20, "--checkpoint-every", 10)
+    assert rc == 0, ob1
+    assert os.path.exists(os.path.join(b, "entity2vec.bern"))
+    rc, ob2 = run(os.path.join(OURS, "trainTransE"), *common, "--outdir", b, "--epochs", 20, "--resume", 1, "--first-epoch", 20)
+    assert rc == 0, ob2
+    la = dict((int(e), float(l)) for e, l in re.findall(r"Epoch: (\d+), Loss: ([0-9.]+)", oa))
+    lb = dict((int(e), float(l)) for e, l in re.findall(r"Epoch: (\d+), Loss: ([0-9.]+)", ob1 + ob2))
+    assert sorted(lb) == list(range(40))
+    assert all(la[e] == lb[e] for e in range(20))                       # deterministic mode: identical until the checkpoint
+    assert all(abs(la[e] - lb[e]) < 0.02 * la[e] for e in range(20, 40))  # then equal up to the text truncation of the tables
+    ea, eb = np.loadtxt(os.path.join(a, "entity2vec.bern")), np.loadtxt(os.path.join(b, "entity2vec.bern"))
+    assert np.abs(ea - eb).mean() < 2e-3
+
+
+def test_transr_seeded_in_process(data, tmp_path):
+    """trainTransR --seed-epochs N trains its TransE seed model in the same process and hands the tables
+    over as doubles (the reference couples the two programs through 6-decimal files, transr/trainer.cpp:88-113)."""
+    datadir, g = data
+    out = str(tmp_path)
+    rc, o = run(os.path.join(OURS, "trainTransR"), "--datadir", datadir, "--outdir", out, "--size", 16, "--rate", 0.01, "--method", 1,
+                "--batches", 10, "--seed", 5, "--epochs", 30, "--seed-epochs", 30, "--seedmethod", 0)
+    assert rc == 0, o
+    m = re.search(r"Seed model \(TransE unif\): 30 epochs, loss ([0-9.]+) -> ([0-9.]+)", o)
+    assert m and float(m.group(2)) < float(m.group(1))
+    losses = [float(x) for x in re.findall(r"Epoch: \d+, Loss: ([0-9.]+)", o)]
+    assert len(losses) == 30 and all(np.isfinite(losses))
+    assert sum(1 for _ in open(os.path.join(out, "weights.bern"))) == 12 * 16
+    rc, eo = run(os.path.join(OURS, "evalTransR"), "--datadir", datadir, "--outdir", out, "--size", 16, "--method", 1)
+    assert rc == 0 and parse_eval(eo)["Filtered"][0] < 200, eo
