@@ -72,9 +72,11 @@ __device__ __forceinline__ void list_push(int* count, int* list, int cap, int ro
 constexpr float kDetScale = 16777216.0f;   // 2^24
 constexpr double kDetLossScale = 1048576.0;   // 2^20: per-epoch loss as a 64-bit fixed-point sum
 
-template <int LPS, int NV>
-__device__ __forceinline__ void acc_row(const TrainArgs& a, float* base, int P, int gl, const float4 (&v)[NV]) {
-   if (!(a.flags & KB2E_FLAG_DETERMINISTIC)) {
+// DET is a template parameter, not a test of the flag at run time: the run-time branches cost the scan kernel of the
+// scaled shape 100 bytes of extra spills in its hot loop (332 -> 504 ms per epoch, measured).
+template <int LPS, int NV, bool DET>
+__device__ __forceinline__ void acc_row(float* base, int P, int gl, const float4 (&v)[NV]) {
+   if (!DET) {
       red_row<LPS, NV>(base, P, gl, v);
       return;
    }
@@ -100,7 +102,7 @@ __device__ __forceinline__ float4 det_to_float(float4 bits) {
 // ---- phase 1: one (positive, negative) pair, TransE and TransH -----------------------------------
 // row_base: first row of the model the pair belongs to in the stacked tables (0 unless several models are trained in one
 // launch, train_sweep_kernel); lr / margin: that model's learning rate and margin.
-template <int MODEL, int LPS, int NV, bool LIST>
+template <int MODEL, int LPS, int NV, bool LIST, bool DET>
 __device__ __forceinline__ void process_pair_at(const TrainArgs& a, const RowLists& L, const Pair s, size_t row_base, float lr, float margin,
                                                 int gl, uint32_t gmask, uint32_t stamp, double& loss_acc, uint32_t& active_acc) {
    const int P = a.P, D = a.D;
@@ -177,23 +179,23 @@ __device__ __forceinline__ void process_pair_at(const TrainArgs& a, const RowLis
    // relation row: -= m*lr*x  with m = -1 (positive), +1 (negative)
 #pragma unroll
    for (int q = 0; q < NV; q++) u[q] = gp[q] - gn[q];
-   acc_row<LPS, NV>(a, dr, P, gl, u);
+   acc_row<LPS, NV, DET>(dr, P, gl, u);
    if (s.corruptTail) {
       // negative = (h, r, c): head -= gn, c += gn; positive: head += gp, tail -= gp
-      acc_row<LPS, NV>(a, dh, P, gl, u);
+      acc_row<LPS, NV, DET>(dh, P, gl, u);
 #pragma unroll
       for (int q = 0; q < NV; q++) u[q] = -1.f * gp[q];
-      acc_row<LPS, NV>(a, dt, P, gl, u);
-      acc_row<LPS, NV>(a, dc, P, gl, gn);
+      acc_row<LPS, NV, DET>(dt, P, gl, u);
+      acc_row<LPS, NV, DET>(dc, P, gl, gn);
    } else {
       // negative = (c, r, t): c -= gn, tail += gn
-      acc_row<LPS, NV>(a, dh, P, gl, gp);
+      acc_row<LPS, NV, DET>(dh, P, gl, gp);
 #pragma unroll
       for (int q = 0; q < NV; q++) u[q] = gn[q] - gp[q];
-      acc_row<LPS, NV>(a, dt, P, gl, u);
+      acc_row<LPS, NV, DET>(dt, P, gl, u);
 #pragma unroll
       for (int q = 0; q < NV; q++) u[q] = -1.f * gn[q];
-      acc_row<LPS, NV>(a, dc, P, gl, u);
+      acc_row<LPS, NV, DET>(dc, P, gl, u);
    }
    if (MODEL == KB2E_MODEL_TRANSH) {
       // transh/trainer.cpp:33,39-40,44-45: w += beta*lr*(x*(hs-ts) + sum_x*(h - t)), with the RAW h, t.
@@ -216,7 +218,7 @@ __device__ __forceinline__ void process_pair_at(const TrainArgs& a, const RowLis
          float4 neg = (nhs - nts) * gn[q] + sxn * (nh - nt);
          u[q] = neg - pos;
       }
-      acc_row<LPS, NV>(a, a.dw + (size_t)s.r * P, P, gl, u);
+      acc_row<LPS, NV, DET>(a.dw + (size_t)s.r * P, P, gl, u);
    }
    // flag the touched rows (+ relation range per entity for the TransH/TransR constraints)
    if (gl < 3) {
@@ -245,29 +247,28 @@ __device__ __forceinline__ void process_pair_at(const TrainArgs& a, const RowLis
    }
 }
 
-template <int MODEL, int LPS, int NV, bool LIST>
+template <int MODEL, int LPS, int NV, bool LIST, bool DET>
 __device__ __forceinline__ void process_pair(const TrainArgs& a, const RowLists& L, const Pair s, int gl, uint32_t gmask, uint32_t stamp,
                                              double& loss_acc, uint32_t& active_acc) {
-   process_pair_at<MODEL, LPS, NV, LIST>(a, L, s, 0, a.lr, a.margin, gl, gmask, stamp, loss_acc, active_acc);
+   process_pair_at<MODEL, LPS, NV, LIST, DET>(a, L, s, 0, a.lr, a.margin, gl, gmask, stamp, loss_acc, active_acc);
 }
 
 // ---- phase 2 -------------------------------------------------------------------------------------
 // Common head of every publish: x = cur + delta, delta = 0 (rows arrive preloaded so that the loads of
 // two rows are in flight together).
-template <int LPS, int NV>
-__device__ __forceinline__ void apply_delta(const TrainArgs& a, float* del, int P, int gl, float4 (&x)[NV], float4 (&d)[NV]) {
-   const bool det = (a.flags & KB2E_FLAG_DETERMINISTIC) != 0u;
+template <int LPS, int NV, bool DET>
+__device__ __forceinline__ void apply_delta(float* del, int P, int gl, float4 (&x)[NV], float4 (&d)[NV]) {
 #pragma unroll
-   for (int q = 0; q < NV; q++) { x[q] = x[q] + (det ? det_to_float(d[q]) : d[q]); d[q] = f4(0.f); }
+   for (int q = 0; q < NV; q++) { x[q] = x[q] + (DET ? det_to_float(d[q]) : d[q]); d[q] = f4(0.f); }
    store_row<LPS, NV>(del, P, gl, d);
 }
 
 // Relation-side row r: d_r (and w_r).  transe/trainer.cpp:43, transh/trainer.cpp:48,52,56.
-template <int MODEL, int LPS, int NV>
+template <int MODEL, int LPS, int NV, bool DET>
 __device__ __forceinline__ void finish_relation(const TrainArgs& a, int r, int gl, uint32_t gmask, float4 (&x)[NV], float4 (&d)[NV]) {
    const int P = a.P;
    float* cur = a.tab + ((size_t)a.nE + r) * P;
-   apply_delta<LPS, NV>(a, a.dtab + ((size_t)a.nE + r) * P, P, gl, x, d);
+   apply_delta<LPS, NV, DET>(a.dtab + ((size_t)a.nE + r) * P, P, gl, x, d);
    norm_row<LPS, NV>(x, true, gmask);
    if (MODEL == KB2E_MODEL_TRANSH) {
       float* wc = a.w + (size_t)r * P;
@@ -275,7 +276,7 @@ __device__ __forceinline__ void finish_relation(const TrainArgs& a, int r, int g
       float4 b[NV], db[NV];
       load_row<LPS, NV>(wc, P, gl, b);
       load_row<LPS, NV>(wd, P, gl, db);
-      apply_delta<LPS, NV>(a, wd, P, gl, b, db);
+      apply_delta<LPS, NV, DET>(wd, P, gl, b, db);
       norm_row<LPS, NV>(b, false, gmask);          // transh/trainer.cpp:52
       norm_row<LPS, NV>(b, false, gmask);          // common/utils.cpp:82
       soft_orth_loop<LPS, NV>(x, b, a.lr, gmask);  // common/utils.cpp:83-108
@@ -286,12 +287,12 @@ __device__ __forceinline__ void finish_relation(const TrainArgs& a, int r, int g
 }
 
 // Entity row e.  transe/trainer.cpp:44-45, transh/trainer.cpp:49-50,57-58.
-template <int MODEL, int LPS, int NV, bool LIST>
+template <int MODEL, int LPS, int NV, bool LIST, bool DET>
 __device__ __forceinline__ void finish_entity(const TrainArgs& a, const RowLists& L, int e, int gl, uint32_t gmask, uint32_t next_stamp,
                                               float4 (&x)[NV], float4 (&d)[NV]) {
    const int P = a.P;
    float* cur = a.tab + (size_t)e * P;
-   apply_delta<LPS, NV>(a, a.dtab + (size_t)e * P, P, gl, x, d);
+   apply_delta<LPS, NV, DET>(a.dtab + (size_t)e * P, P, gl, x, d);
    norm_row<LPS, NV>(x, true, gmask);
    if (MODEL == KB2E_MODEL_TRANSH) {
       int r0 = __ldcg(a.rmin + e), r1 = __ldcg(a.rmax + e);
@@ -310,7 +311,7 @@ __device__ __forceinline__ void finish_entity(const TrainArgs& a, const RowLists
             norm_row<LPS, NV>(b, false, gmask);
 #pragma unroll
             for (int q = 0; q < NV; q++) b[q] = b[q] - b0[q];
-            acc_row<LPS, NV>(a, a.dw + (size_t)r * P, P, gl, b);
+            acc_row<LPS, NV, DET>(a.dw + (size_t)r * P, P, gl, b);
             if (gl == 0) {
                if (!LIST) {
                   a.flag[(size_t)a.nE + r] = next_stamp;
@@ -362,7 +363,7 @@ __device__ __forceinline__ void project3(const float* M, int D, int P, int lane,
 // Rows [row_begin, row_end) of the unified row space (entities, then relations) whose stamp says
 // "touched in this batch".  Two rows per group are examined per step, flags first, then both rows'
 // loads, then the arithmetic, so that the L2 round trips overlap.
-template <int MODEL, int LPS, int NV>
+template <int MODEL, int LPS, int NV, bool DET>
 __device__ __forceinline__ void publish_rows(const TrainArgs& a, long long row_begin, long long row_end, long long g0, long long G,
                                              uint32_t stamp, uint32_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel) {
    const int P = a.P;
@@ -372,8 +373,8 @@ __device__ __forceinline__ void publish_rows(const TrainArgs& a, long long row_b
    const RowLists none{};
    auto stamped = [&](long long r) { return __ldcg(a.flag + r) == stamp; };
    auto finish = [&](long long r, float4 (&x)[NV], float4 (&d)[NV]) {
-      if (r >= a.nE) { finish_relation<MODEL, LPS, NV>(a, (int)(r - a.nE), gl, gmask, x, d); trel += (gl == 0); }
-      else { finish_entity<MODEL, LPS, NV, false>(a, none, (int)r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
+      if (r >= a.nE) { finish_relation<MODEL, LPS, NV, DET>(a, (int)(r - a.nE), gl, gmask, x, d); trel += (gl == 0); }
+      else { finish_entity<MODEL, LPS, NV, false, DET>(a, none, (int)r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
    };
    for_stamped_rows<LPS>(first, end, gl, gmask, lane, stamped, [&](long long r0, long long r1) {
       float4 x0[NV], d0[NV], x1[NV], d1[NV];
@@ -391,7 +392,7 @@ __device__ __forceinline__ void publish_rows(const TrainArgs& a, long long row_b
 // LIST kernels: the CTA's own list, n entries, one per group and pass (two of a group in flight when the list is longer
 // than the CTA has groups).  The claim (atomic exchange of the row's stamp) travels with the loads of the row; a row that
 // another copy of the entry -- in this or in another CTA -- claimed first is dropped.
-template <int MODEL, int LPS, int NV>
+template <int MODEL, int LPS, int NV, bool DET>
 __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists& L, const int* list, int n, int group, int groups,
                                              uint32_t stamp, uint32_t next_stamp, int gl, uint32_t gmask, uint32_t& tent, uint32_t& trel,
                                              unsigned long long* fine = nullptr, int rows_per_model = 0) {
@@ -409,8 +410,8 @@ __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists&
    auto finish = [&](int r, float4 (&x)[NV], float4 (&d)[NV]) {
       // (several stacked models, TransE only: row r of the stack; relation and entity rows are finished alike)
       const bool is_rel = rows_per_model ? (r % rows_per_model) >= a.nE : r >= a.nE;
-      if (is_rel) { finish_relation<MODEL, LPS, NV>(a, r - a.nE, gl, gmask, x, d); trel += (gl == 0); }
-      else { finish_entity<MODEL, LPS, NV, true>(a, L, r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
+      if (is_rel) { finish_relation<MODEL, LPS, NV, DET>(a, r - a.nE, gl, gmask, x, d); trel += (gl == 0); }
+      else { finish_entity<MODEL, LPS, NV, true, DET>(a, L, r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
    };
    for (int i = group; i < n; i += 2 * groups) {
       const int r0 = list[i];
@@ -437,7 +438,7 @@ __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists&
    }
 }
 
-template <int MODEL, int LPS, int NV, int THREADS, bool LIST>
+template <int MODEL, int LPS, int NV, int THREADS, bool LIST, bool DET>
 __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant__ TrainArgs a) {
    __shared__ double s_loss[THREADS / 32];
    extern __shared__ int s_lists[];
@@ -474,9 +475,12 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
    DrawStage ds;
    const bool has_first = g0 < a.batchsize;
    const uint32_t n_batches = (uint32_t)a.n_epochs * (uint32_t)a.batches;
+   // (The pipelined stages are a LIST-kernel feature: small batches, one sample per group.  In the scan kernels -- hundreds
+   // of samples per group and batch, drawn inline -- their live registers only add spills to the hot loop: 240 instead of
+   // 96 bytes at the scaled shape, 504 instead of 332 ms per epoch, measured.)
    if (has_first) {
       pre = draw_pair(a, (uint32_t)g0, gb_first);
-      if (n_batches > 1u) draw_begin(a, (uint32_t)g0, gb_first + 1u, ds);   // pipelined from here on (train_device.cuh)
+      if (LIST && n_batches > 1u) draw_begin(a, (uint32_t)g0, gb_first + 1u, ds);   // pipelined from here on (train_device.cuh)
    }
    const int group = threadIdx.x / LPS;
    if (LIST) {
@@ -502,10 +506,10 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
          const uint32_t next_stamp = stamp + 1u;
          KB2E_TRACE();
          // ---- phase 1 ----
-         if (has_first) process_pair<MODEL, LPS, NV, LIST>(a, L, pre, gl, gmask, stamp, loss_acc, active_acc);
+         if (has_first) process_pair<MODEL, LPS, NV, LIST, DET>(a, L, pre, gl, gmask, stamp, loss_acc, active_acc);
          for (long long k = g0 + G; k < a.batchsize; k += G) {
             Pair s = draw_pair(a, (uint32_t)k, gb);
-            process_pair<MODEL, LPS, NV, LIST>(a, L, s, gl, gmask, stamp, loss_acc, active_acc);
+            process_pair<MODEL, LPS, NV, LIST, DET>(a, L, s, gl, gmask, stamp, loss_acc, active_acc);
          }
          KB2E_TRACE();
          grid_barrier(a.barrier, bar_target);
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
          if (a.phase1_only) continue;   // kb2e_train_batch_deltas: the caller reads the raw delta tables (one batch per launch)
          const bool more = rel_batch + 1u < n_batches;
          // next batch's sample, stage 2: its probe loads travel with the row loads of the publish below
-         if (has_first && more) draw_probe(a, ds);
+         if (LIST && has_first && more) draw_probe(a, ds);
          // ---- phase 2 ----
          if (LIST) {
             if (MODEL == KB2E_MODEL_TRANSE) {
@@ -522,38 +526,42 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
                   fine = a.trace + (size_t)blockIdx.x * kTraceSlots + trace_slot;
                   trace_slot += 6;
                }
-               publish_list<MODEL, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, next_stamp, gl, gmask,
+               publish_list<MODEL, LPS, NV, DET>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, next_stamp, gl, gmask,
                                             tent_acc, trel_acc, fine);
                KB2E_TRACE();
             } else {
                int* nrel = L.count + 1 + (stamp & 1u);
-               publish_list<MODEL, LPS, NV>(a, L, L.rel[stamp & 1u], min(*nrel, L.cap_rel), group, groups_per_block, stamp, next_stamp, gl, gmask,
+               publish_list<MODEL, LPS, NV, DET>(a, L, L.rel[stamp & 1u], min(*nrel, L.cap_rel), group, groups_per_block, stamp, next_stamp, gl, gmask,
                                             tent_acc, trel_acc);
                grid_barrier(a.barrier, bar_target);   // (its leading bar.sync also ends every read of *nrel)
                if (threadIdx.x == 0) *nrel = 0;
                KB2E_TRACE();
-               publish_list<MODEL, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, next_stamp, gl, gmask,
+               publish_list<MODEL, LPS, NV, DET>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, next_stamp, gl, gmask,
                                             tent_acc, trel_acc);
             }
             __syncthreads();
             if (threadIdx.x == 0) L.count[0] = 0;
          } else if (MODEL == KB2E_MODEL_TRANSE) {
             // no coupling between relation and entity rows: one pass over the whole row space
-            publish_rows<MODEL, LPS, NV>(a, 0, R, g0, G, stamp, next_stamp, gl, gmask, tent_acc, trel_acc);
+            publish_rows<MODEL, LPS, NV, DET>(a, 0, R, g0, G, stamp, next_stamp, gl, gmask, tent_acc, trel_acc);
             KB2E_TRACE();
          } else {
-            publish_rows<MODEL, LPS, NV>(a, a.nE, R, g0, G, stamp, next_stamp, gl, gmask, tent_acc, trel_acc);
+            publish_rows<MODEL, LPS, NV, DET>(a, a.nE, R, g0, G, stamp, next_stamp, gl, gmask, tent_acc, trel_acc);
             grid_barrier(a.barrier, bar_target);
             KB2E_TRACE();
-            publish_rows<MODEL, LPS, NV>(a, 0, a.nE, g0, G, stamp, next_stamp, gl, gmask, tent_acc, trel_acc);
+            publish_rows<MODEL, LPS, NV, DET>(a, 0, a.nE, g0, G, stamp, next_stamp, gl, gmask, tent_acc, trel_acc);
          }
          KB2E_TRACE();
          grid_arrive(a.barrier, bar_target);
          // next batch's sample, stage 3 (registers only unless the candidate has to be redrawn), and stage 1 of the batch
          // after it: the triple fetch is in flight until the probe stage needs it, one phase from now
          if (has_first && more) {
-            pre = draw_finish(a, (uint32_t)g0, gb + 1u, ds);
-            if (rel_batch + 2u < n_batches) draw_begin(a, (uint32_t)g0, gb + 2u, ds);
+            if (LIST) {
+               pre = draw_finish(a, (uint32_t)g0, gb + 1u, ds);
+               if (rel_batch + 2u < n_batches) draw_begin(a, (uint32_t)g0, gb + 2u, ds);
+            } else {
+               pre = draw_pair(a, (uint32_t)g0, gb + 1u);   // scan kernels: in one piece, while the other CTAs arrive
+            }
          }
          grid_wait(a.barrier, bar_target);
       }
@@ -567,7 +575,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
          double t = 0.0;
          for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += s_loss[i];
          if (t != 0.0) {
-            if (a.flags & KB2E_FLAG_DETERMINISTIC)   // CTA partial sums are reproducible; add them as integers
+            if (DET)   // CTA partial sums are reproducible; add them as integers
                atomicAdd(reinterpret_cast<unsigned long long*>(a.loss + ep), (unsigned long long)__double2ll_rn(t * kDetLossScale));
             else
                atomicAdd(a.loss + ep, t);
@@ -606,7 +614,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
 // The per-model epoch loss is accumulated in shared memory as a 64-bit fixed-point sum (2^-24 units).
 constexpr double kSweepLossScale = 16777216.0;
 
-template <int LPS, int NV, int THREADS>
+template <int LPS, int NV, int THREADS, bool DET>
 __global__ void __launch_bounds__(THREADS, 1) train_sweep_kernel(const __grid_constant__ TrainArgs a) {
    extern __shared__ int s_dyn[];
    const int K = a.replicas, T = a.tasks_per_group;
@@ -674,7 +682,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_sweep_kernel(const __grid_co
             const int m = (int)((g0 + (long long)t * G) % K);
             const RepParams rp = a.rep[m];
             double loss = 0.0;
-            process_pair_at<KB2E_MODEL_TRANSE, LPS, NV, true>(a, L, s, (size_t)m * R, rp.lr, rp.margin, gl, gmask, stamp, loss, active_acc);
+            process_pair_at<KB2E_MODEL_TRANSE, LPS, NV, true, DET>(a, L, s, (size_t)m * R, rp.lr, rp.margin, gl, gmask, stamp, loss, active_acc);
             if (gl == 0 && loss != 0.0) atomicAdd(s_loss + m, (unsigned long long)__double2ll_rn(loss * kSweepLossScale));
          }
          KB2E_STRACE();
@@ -683,7 +691,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_sweep_kernel(const __grid_co
          const bool more = rel_batch + 1u < n_batches;
          if (samples && more) draw_probe(a, ds);
          // ---- phase 2: the CTA's list of stacked rows ----
-         publish_list<KB2E_MODEL_TRANSE, LPS, NV>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, stamp + 1u, gl, gmask,
+         publish_list<KB2E_MODEL_TRANSE, LPS, NV, DET>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, stamp + 1u, gl, gmask,
                                                   tent_acc, trel_acc, nullptr, R);
          KB2E_STRACE();
          __syncthreads();
@@ -1102,9 +1110,9 @@ static int threads_for(int model, int nv) {
    return 1024;
 }
 
-template <int MODEL, bool LIST>
+template <int MODEL, bool LIST, bool DET>
 static TrainKernel pick_kernel(int lps, int nv, int threads) {
-#define KB2E_PICK(L, N, T) if (lps == L && nv == N) return train_kernel<MODEL, L, N, T, LIST>;
+#define KB2E_PICK(L, N, T) if (lps == L && nv == N) return train_kernel<MODEL, L, N, T, LIST, DET>;
    if (MODEL == KB2E_MODEL_TRANSH) {
       KB2E_PICK(8, 1, 512) KB2E_PICK(16, 1, 512) KB2E_PICK(32, 1, 512)
       KB2E_PICK(8, 2, 512) KB2E_PICK(16, 2, 512) KB2E_PICK(32, 2, 512)
@@ -1203,8 +1211,9 @@ int train_select_replica(kb2e_ctx* c, int m) {
 }
 
 typedef void (*SweepKernel)(const TrainArgs);
+template <bool DET>
 static SweepKernel pick_sweep(int lps, int nv, int threads) {
-#define KB2E_SWEEP(L, N, T) if (lps == L && nv == N && threads == T) return train_sweep_kernel<L, N, T>;
+#define KB2E_SWEEP(L, N, T) if (lps == L && nv == N && threads == T) return train_sweep_kernel<L, N, T, DET>;
    KB2E_SWEEP(8, 1, 1024) KB2E_SWEEP(16, 1, 1024) KB2E_SWEEP(32, 1, 1024)
    KB2E_SWEEP(8, 2, 640) KB2E_SWEEP(16, 2, 640) KB2E_SWEEP(32, 2, 640)
    KB2E_SWEEP(8, 4, 512) KB2E_SWEEP(16, 4, 512) KB2E_SWEEP(32, 4, 512)
@@ -1246,7 +1255,7 @@ static int sweep_run(kb2e_ctx* c, int first_epoch, int n_epochs, double* loss_ou
    int lps, nv, threads;
    choose_shape(c, a.batchsize, lps, nv, threads);
    if (nv == 2) threads = 640;
-   SweepKernel k = pick_sweep(lps, nv, threads);
+   SweepKernel k = (c->cfg.flags & KB2E_FLAG_DETERMINISTIC) ? pick_sweep<true>(lps, nv, threads) : pick_sweep<false>(lps, nv, threads);
    if (!k) return fail(c, KB2E_ERR_LIMIT, "no batched training kernel for this embedding size");
    const int groups = threads / lps;
    const long long G = (long long)c->num_sms * groups;
@@ -1365,10 +1374,15 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
       if (c->cfg.flags & KB2E_FLAG_DETERMINISTIC) return fail(c, KB2E_ERR_LIMIT, "KB2E_FLAG_DETERMINISTIC covers TransE and TransH");
    } else {
       list_bytes = list_shape(c, a.batchsize, threads / lps, a.cap_ent, a.cap_rel);
+      const bool det = (c->cfg.flags & KB2E_FLAG_DETERMINISTIC) != 0u;
+      if (det && !list_bytes)
+         return fail(c, KB2E_ERR_LIMIT, "KB2E_FLAG_DETERMINISTIC is built for the list kernels: the batch is too large for this embedding size");
       if (c->cfg.model == KB2E_MODEL_TRANSE)
-         k = list_bytes ? pick_kernel<KB2E_MODEL_TRANSE, true>(lps, nv, threads) : pick_kernel<KB2E_MODEL_TRANSE, false>(lps, nv, threads);
+         k = !list_bytes ? pick_kernel<KB2E_MODEL_TRANSE, false, false>(lps, nv, threads)
+                         : (det ? pick_kernel<KB2E_MODEL_TRANSE, true, true>(lps, nv, threads) : pick_kernel<KB2E_MODEL_TRANSE, true, false>(lps, nv, threads));
       else
-         k = list_bytes ? pick_kernel<KB2E_MODEL_TRANSH, true>(lps, nv, threads) : pick_kernel<KB2E_MODEL_TRANSH, false>(lps, nv, threads);
+         k = !list_bytes ? pick_kernel<KB2E_MODEL_TRANSH, false, false>(lps, nv, threads)
+                         : (det ? pick_kernel<KB2E_MODEL_TRANSH, true, true>(lps, nv, threads) : pick_kernel<KB2E_MODEL_TRANSH, true, false>(lps, nv, threads));
    }
    if (!k && !transr) return fail(c, KB2E_ERR_LIMIT, "no training kernel for this embedding size");
    // row stamps of this launch: stamp_base + 1 ... stamp_base + #batches, never reused by a later launch
