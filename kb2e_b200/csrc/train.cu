@@ -945,6 +945,7 @@ void train_free(kb2e_ctx* c) {
    pool_free(c, c->ent64); pool_free(c, c->rel64); pool_free(c, c->w64);
    pool_free(c, c->pend);
    pool_free(c, c->cflag);
+   pool_free(c, c->transr_aux);
    pool_free(c, c->filt_dev);
 }
 

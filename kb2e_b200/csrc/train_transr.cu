@@ -38,6 +38,11 @@ struct RArgs {
    int vec_off;        // offset of the vector slots inside a warp's slice (floats, multiple of 4)
    int warp_floats;    // floats per warp slice (multiple of 4)
    uint32_t p4_magic;  // ceil(2^32 / (P / 4)): f / (P/4) == umulhi(f, magic) for the flat indices used here
+   // phase 2b work list: every entity row a batch must visit, once, in one grid-wide array (built in phase 1)
+   uint32_t* claim;    // [nE] stamp of the batch the row was last put on the list for
+   uint32_t* qflag;    // [nR] stamp of the batch relation r was last touched by a SAMPLE (flag[nE + r] also moves on constraint carries)
+   uint32_t* gcount;   // [2] list length, indexed by stamp parity (the other one is zeroed during the batch)
+   int* glist;         // [nE]
 };
 
 __device__ __forceinline__ float rcomp(const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
@@ -234,13 +239,27 @@ __device__ __forceinline__ void transr_pair(const RArgs& ra, const Pair s, float
          red_add4(dc, -1.f * sn4);
       }
    }
+   int row = -1;
    if (lane < 3) {
       const int e = lane == 0 ? s.h : (lane == 1 ? s.t : s.c);
       a.flag[e] = stamp;
       atomicMin(a.rmin + e, s.r);
       atomicMax(a.rmax + e, s.r);
+      row = e;
    } else if (lane == 3) {
       a.flag[(size_t)a.nE + s.r] = stamp;
+      ra.qflag[s.r] = stamp;
+      // transr/trainer.cpp:187: entity row r is also visited when RELATION r was touched
+      if (!(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK) && s.r < a.nE) row = s.r;
+   }
+   // first toucher of the batch appends the row to the grid-wide phase 2b list
+   const bool first = row >= 0 && atomicExch(ra.claim + row, stamp) != stamp;
+   const uint32_t m = __ballot_sync(0xffffffffu, first);
+   if (m) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(ra.gcount + (stamp & 1u), (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (first) ra.glist[base + __popc(m & ((1u << lane) - 1u))] = row;
    }
    __syncwarp();
 }
@@ -434,7 +453,7 @@ __device__ __forceinline__ void transr_finish_entity(const RArgs& ra, int e, flo
       transr_constraint<NE>(ra, r0, sM, sV, lane, next_stamp, x);
       if (r1 != r0) transr_constraint<NE>(ra, r1, sM, sV, lane, next_stamp, x);
    }
-   const bool quirk = !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK) && e < a.nR && __ldcg(a.flag + a.nE + e) == stamp;
+   const bool quirk = !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK) && e < a.nR && __ldcg(ra.qflag + e) == stamp;
    if (quirk && !(own && (r0 == e || r1 == e))) transr_constraint<NE>(ra, e, sM, sV, lane, next_stamp, x);
    // slot S_H holds the final row (transr_constraint keeps it current)
    if (on) st_cg4(a.tab + (size_t)e * P + lane * 4, reinterpret_cast<const float4*>(sV + S_H * P)[lane]);
@@ -480,12 +499,6 @@ __device__ __forceinline__ void compact_rows(RowList& list, long long begin, lon
    }
 }
 
-__device__ __forceinline__ int take_item(RowList& list, int lane) {
-   int t = 0;
-   if (lane == 0) t = atomicAdd(&list.next, 1);
-   return __shfl_sync(0xffffffffu, t, 0);
-}
-
 template <int NE>
 __global__ void __launch_bounds__(kRMaxThreads, 1) train_transr_kernel(const __grid_constant__ RArgs ra) {
    extern __shared__ float4 smem4[];
@@ -499,11 +512,6 @@ __global__ void __launch_bounds__(kRMaxThreads, 1) train_transr_kernel(const __g
    const int warps = blockDim.x >> 5;
    const long long G = (long long)gridDim.x * warps;
    const long long g0 = (long long)warp * gridDim.x + blockIdx.x;   // round-robin over CTAs
-   const bool quirk_on = !(a.flags & KB2E_FLAG_TRANSR_NO_QUIRK);
-   // this CTA's contiguous share of the entity rows (phase 2b)
-   const long long ent_per = (a.nE + gridDim.x - 1) / gridDim.x;
-   const long long ent_first = min((long long)a.nE, ent_per * blockIdx.x);
-   const long long ent_end = min((long long)a.nE, ent_first + ent_per);
    uint32_t bar_target = 0;
    uint32_t active_acc = 0, tent_acc = 0, trel_acc = 0;
    int trace_slot = 0;
@@ -557,23 +565,17 @@ __global__ void __launch_bounds__(kRMaxThreads, 1) train_transr_kernel(const __g
          KB2E_RTRACE();
          grid_barrier(a.barrier, bar_target);
          KB2E_RTRACE();
-         // ---- phase 2b: this CTA's touched entity rows, taken one at a time by its warps
-         for (long long w0 = ent_first; w0 < ent_end; w0 += kListCap) {
-            const long long w1 = min(ent_end, w0 + kListCap);
-            compact_rows(s_list, w0, w1, [&](long long r) {
-               bool f = __ldcg(a.flag + r) == stamp;
-               // transr/trainer.cpp:187: entity row e is also visited when RELATION e was touched
-               if (quirk_on && r < a.nR) f = f || __ldcg(a.flag + a.nE + r) == stamp;
-               return f;
-            });
-            const int n = s_list.n;
-            for (int t = take_item(s_list, lane); t < n; t = take_item(s_list, lane)) {
-               const long long e = w0 + s_list.item[t];
+         // ---- phase 2b: the batch's list of entity rows (touched, or visited through the quirk), dealt round-robin over
+         // all warps of the grid: a row costs microseconds (it stages 10 KB matrices), so the count per warp is what matters
+         {
+            if (blockIdx.x == 0 && threadIdx.x == 0) ra.gcount[next_stamp & 1u] = 0u;   // last read in the previous batch's phase 2b
+            const long long n = __ldcg(ra.gcount + (stamp & 1u));
+            for (long long it = g0; it < n; it += G) {
+               const int e = __ldcg(ra.glist + it);
                const bool own = __ldcg(a.flag + e) == stamp;
-               transr_finish_entity<NE>(ra, (int)e, sM, sV, lane, stamp, next_stamp, own);
+               transr_finish_entity<NE>(ra, e, sM, sV, lane, stamp, next_stamp, own);
                tent_acc += (lane == 0 && own);
             }
-            __syncthreads();
          }
          KB2E_RTRACE();
          grid_arrive(a.barrier, bar_target);
@@ -616,6 +618,16 @@ int train_transr_launch(kb2e_ctx* c, const TrainArgs& base, int* threads_out) {
    a.warp_floats = a.vec_off + kRSlots * c->P;
    const int P4 = c->P / 4;
    a.p4_magic = (uint32_t)(((1ull << 32) + P4 - 1) / P4);
+   if (!c->transr_aux) {   // claim [nE] | qflag [nR] | glist [nE] | gcount [2]; stamps never recur, so zero once is enough
+      const size_t words = 2 * (size_t)c->nE + (size_t)c->nR + 2;
+      KB2E_CUDA(c, pool_alloc(c, &c->transr_aux, words * sizeof(uint32_t)));
+      KB2E_CUDA(c, cudaMemsetAsync(c->transr_aux, 0, words * sizeof(uint32_t), c->stream));
+   }
+   a.claim = c->transr_aux;
+   a.qflag = a.claim + c->nE;
+   a.glist = reinterpret_cast<int*>(a.qflag + c->nR);
+   a.gcount = reinterpret_cast<uint32_t*>(a.glist + c->nE);
+   KB2E_CUDA(c, cudaMemsetAsync(a.gcount, 0, 2 * sizeof(uint32_t), c->stream));
    int dev_smem = 0;
    KB2E_CUDA(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
    const size_t per_warp = (size_t)a.warp_floats * sizeof(float);

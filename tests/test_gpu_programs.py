@@ -164,9 +164,22 @@ def test_reference_side_binding_through_the_virtual_seam(data, tmp_path, model, 
         a, b = np.loadtxt(os.path.join(out_a, f)), np.loadtxt(os.path.join(out_b, f))
         assert a.shape == b.shape
         if not det:
-            assert np.abs(a - b).mean() < 0.03 and np.median(np.abs(a - b)) < 0.01, (f, np.abs(a - b).mean())
+            # after 25 epochs the two trajectories have drifted apart like two runs of one program do (measured: mean |d|
+            # 0.02 .. 0.06 on rows of unit length); the tight comparison is the 3-epoch run below
+            assert np.abs(a - b).mean() < 0.15, (f, np.abs(a - b).mean())
     e = np.loadtxt(os.path.join(out_a, files[0]))
     assert e.shape == (500, 16) and np.isfinite(e).all() and np.abs(e).max() > 0.01
+    if not det:
+        # three epochs: rounding differences have not been amplified yet, so the files agree to the printed precision's order
+        short = [x if x != 25 else 3 for x in common]
+        out_c, out_d = str(tmp_path / "binding3"), str(tmp_path / "ours3")
+        os.makedirs(out_c), os.makedirs(out_d)
+        rc_c, o_c = run(binding, *short, "--outdir", out_c)
+        rc_d, o_d = run(os.path.join(OURS, "train" + model), *short, "--outdir", out_d)
+        assert rc_c == 0 and rc_d == 0, (o_c, o_d)
+        for f in files:
+            a, b = np.loadtxt(os.path.join(out_c, f)), np.loadtxt(os.path.join(out_d, f))
+            assert np.abs(a - b).mean() < 2e-4 and np.abs(a - b).max() < 2e-2, (f, np.abs(a - b).mean(), np.abs(a - b).max())
 
 
 def test_eval_program_shards_the_test_set_over_gpus(data, tmp_path):
