@@ -1413,6 +1413,11 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
       KB2E_CUDA(c, cudaMemsetAsync(trace_dev, 0, (size_t)c->num_sms * kTraceSlots * sizeof(unsigned long long), c->stream));
       a.trace = trace_dev;
    }
+   const bool transr_stats = transr && getenv("KB2E_TRANSR_STATS") != nullptr;   // tuning aid: constraint-loop pass counts on stderr
+   if (transr_stats) {
+      a.flags |= 0x80000000u;
+      KB2E_CUDA(c, cudaMemsetAsync(c->counters + 3, 0, 3 * sizeof(unsigned long long), c->stream));
+   }
    void* params[] = {&a};
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
    if (transr) {
@@ -1434,6 +1439,9 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    KB2E_CUDA(c, cudaStreamSynchronize(c->stream));
    c->stamp_base += (uint32_t)n_batches;
    if (cnt[6]) return fail(c, KB2E_ERR_LIMIT, "internal: a touched-row list overflowed (tables may be inconsistent)");
+   if (transr_stats)
+      fprintf(stderr, "transRNorm over %d batches: %llu violating calls, %llu passes, longest call %llu passes; %llu entity rows\n", (int)n_batches,
+              cnt[4], cnt[3], cnt[5], cnt[1]);
    if (trace_dev) {
       std::vector<unsigned long long> tr((size_t)c->num_sms * kTraceSlots);
       cudaMemcpy(tr.data(), trace_dev, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);

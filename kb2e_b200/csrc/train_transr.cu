@@ -355,6 +355,7 @@ __device__ __forceinline__ void transr_constraint(const RArgs& ra, int r, float*
    cp_async_wait_all();
    __syncwarp();
    bool have_gram = false;
+   int passes = 0;
    for (int iter = 0; iter < 64; iter++) {
       float y[1][NE];
       const float* const vec[1] = {sV + S_H * P};
@@ -420,8 +421,16 @@ __device__ __forceinline__ void transr_constraint(const RArgs& ra, int r, float*
       __syncwarp();
       put_slot<NE>(sV + S_H * P, D, P, lane, x);
       __syncwarp();
+      passes++;
    }
-   if (have_gram && lane == 0) a.flag[(size_t)a.nE + r] = next_stamp;
+   if (have_gram && lane == 0) {
+      a.flag[(size_t)a.nE + r] = next_stamp;
+      if (a.flags & 0x80000000u) {   // KB2E_TRANSR_STATS: passes of the constraint loop (sum, violating calls, longest call)
+         atomicAdd(a.counters + 3, (unsigned long long)passes);
+         atomicAdd(a.counters + 4, 1ull);
+         atomicMax(a.counters + 5, (unsigned long long)passes);
+      }
+   }
    __syncwarp();
 }
 
