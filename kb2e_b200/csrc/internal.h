@@ -40,6 +40,7 @@ struct kb2e_ctx {
    float* dw = nullptr;
    size_t w_row = 0;           // elements per relation in w
    uint32_t* flag = nullptr;   // [nE + nR] stamp (global batch + 1) of the last batch that touched the row
+   float* relbuf1 = nullptr;         // TransH, few relations: second buffer of the relation-side deltas, [2][nR][P] (train_transh_sr_kernel)
    uint32_t* transr_aux = nullptr;   // TransR training: claim stamps, sample-touched relation stamps, the phase 2b row list (train_transr.cu)
    uint32_t* cflag = nullptr;  // [nR] TransH: batch a relation row was marked for by an entity-side constraint step (list kernels)
    bool thr_valid = false;     // triples[i].w holds the corruption threshold of the current pr table

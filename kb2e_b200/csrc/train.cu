@@ -56,7 +56,22 @@ struct RowLists {
    int* ent;
    int* rel[2];
    int cap_ent, cap_rel;
+   // train_transh_sr_kernel only (nullptr elsewhere, and the branches on it fold away): the relation-side rows live in
+   // shared memory for the whole launch, [nR][2][P] = (d_r, w_r), and the relation-side deltas ping-pong between two buffers
+   float* srel;
+   float* dr_cur;    // [nR][P] delta of d_r, this batch's RED target
+   float* dw_cur;    // [nR][P] delta of w_r, this batch's RED target
+   float* dw_next;   // [nR][P] delta of w_r the NEXT batch consumes (entity-side constraint carries)
 };
+
+template <int LPS, int NV>
+__device__ __forceinline__ void load_row_shared(const float* base, int P, int gl, float4 (&v)[NV]) {
+#pragma unroll
+   for (int q = 0; q < NV; q++) {
+      const int off = (q * LPS + gl) * 4;
+      v[q] = off < P ? *reinterpret_cast<const float4*>(base + off) : f4(0.f);
+   }
+}
 
 __device__ __forceinline__ void list_push(int* count, int* list, int cap, int row, unsigned long long* counters) {
    const int slot = atomicAdd(count, 1);
@@ -114,10 +129,13 @@ __device__ __forceinline__ void process_pair_at(const TrainArgs& a, const RowLis
    load_row<LPS, NV>(eh, P, gl, vh);
    load_row<LPS, NV>(et, P, gl, vt);
    load_row<LPS, NV>(ec, P, gl, vc);
-   load_row<LPS, NV>(er, P, gl, vr);
+   const bool sr = MODEL == KB2E_MODEL_TRANSH && L.srel != nullptr;
+   if (sr) load_row_shared<LPS, NV>(L.srel + (size_t)(2 * s.r) * P, P, gl, vr);
+   else load_row<LPS, NV>(er, P, gl, vr);
    float hs = 0.f, ts = 0.f, cs = 0.f;
    if (MODEL == KB2E_MODEL_TRANSH) {
-      load_row<LPS, NV>(a.w + (size_t)s.r * P, P, gl, vw);
+      if (sr) load_row_shared<LPS, NV>(L.srel + (size_t)(2 * s.r + 1) * P, P, gl, vw);
+      else load_row<LPS, NV>(a.w + (size_t)s.r * P, P, gl, vw);
 #pragma unroll
       for (int q = 0; q < NV; q++) {
          hs += dot4(vw[q], vh[q]);
@@ -174,7 +192,7 @@ __device__ __forceinline__ void process_pair_at(const TrainArgs& a, const RowLis
    float* dh = a.dtab + (row_base + s.h) * P;
    float* dt = a.dtab + (row_base + s.t) * P;
    float* dc = a.dtab + (row_base + s.c) * P;
-   float* dr = a.dtab + (row_base + a.nE + s.r) * P;
+   float* dr = sr ? L.dr_cur + (size_t)s.r * P : a.dtab + (row_base + a.nE + s.r) * P;
    float4 u[NV];
    // relation row: -= m*lr*x  with m = -1 (positive), +1 (negative)
 #pragma unroll
@@ -218,7 +236,7 @@ __device__ __forceinline__ void process_pair_at(const TrainArgs& a, const RowLis
          float4 neg = (nhs - nts) * gn[q] + sxn * (nh - nt);
          u[q] = neg - pos;
       }
-      acc_row<LPS, NV, DET>(a.dw + (size_t)s.r * P, P, gl, u);
+      acc_row<LPS, NV, DET>((sr ? L.dw_cur : a.dw) + (size_t)s.r * P, P, gl, u);
    }
    // flag the touched rows (+ relation range per entity for the TransH/TransR constraints)
    if (gl < 3) {
@@ -229,7 +247,7 @@ __device__ __forceinline__ void process_pair_at(const TrainArgs& a, const RowLis
          atomicMax(a.rmax + e, s.r);
       }
    } else if (gl == 3) {
-      if (!LIST) a.flag[(size_t)a.nE + s.r] = stamp;
+      if (!LIST || sr) a.flag[(size_t)a.nE + s.r] = stamp;
    }
    if (LIST) {
       // the sample's rows go on this CTA's lists (duplicates are resolved when the rows are claimed in phase 2)
@@ -241,7 +259,7 @@ __device__ __forceinline__ void process_pair_at(const TrainArgs& a, const RowLis
          const int row = (int)row_base + (gl == 0 ? s.h : (gl == 1 ? s.t : (gl == 2 ? s.c : a.nE + s.r)));
          if (slot + gl < L.cap_ent) L.ent[slot + gl] = row;
          else a.counters[6] = 1ull;   // cannot happen with the host's capacities; reported as an error if it ever does
-      } else if (gl == 3) {
+      } else if (gl == 3 && !sr) {
          list_push(L.count + 1 + (stamp & 1u), L.rel[stamp & 1u], L.cap_rel, a.nE + s.r, a.counters);
       }
    }
@@ -264,6 +282,15 @@ __device__ __forceinline__ void apply_delta(float* del, int P, int gl, float4 (&
 }
 
 // Relation-side row r: d_r (and w_r).  transe/trainer.cpp:43, transh/trainer.cpp:48,52,56.
+// w_r after its delta, against the finished d_r (x): transh/trainer.cpp:52-54
+template <int LPS, int NV>
+__device__ __forceinline__ void finish_hyperplane(float4 (&x)[NV], float4 (&b)[NV], float lr, uint32_t gmask) {
+   norm_row<LPS, NV>(b, false, gmask);          // transh/trainer.cpp:52
+   norm_row<LPS, NV>(b, false, gmask);          // common/utils.cpp:82
+   soft_orth_loop<LPS, NV>(x, b, lr, gmask);    // common/utils.cpp:83-108
+   norm_row<LPS, NV>(b, false, gmask);          // common/utils.cpp:110
+}
+
 template <int MODEL, int LPS, int NV, bool DET>
 __device__ __forceinline__ void finish_relation(const TrainArgs& a, int r, int gl, uint32_t gmask, float4 (&x)[NV], float4 (&d)[NV]) {
    const int P = a.P;
@@ -277,10 +304,7 @@ __device__ __forceinline__ void finish_relation(const TrainArgs& a, int r, int g
       load_row<LPS, NV>(wc, P, gl, b);
       load_row<LPS, NV>(wd, P, gl, db);
       apply_delta<LPS, NV, DET>(wd, P, gl, b, db);
-      norm_row<LPS, NV>(b, false, gmask);          // transh/trainer.cpp:52
-      norm_row<LPS, NV>(b, false, gmask);          // common/utils.cpp:82
-      soft_orth_loop<LPS, NV>(x, b, a.lr, gmask);  // common/utils.cpp:83-108
-      norm_row<LPS, NV>(b, false, gmask);          // common/utils.cpp:110
+      finish_hyperplane<LPS, NV>(x, b, a.lr, gmask);
       store_row<LPS, NV>(wc, P, gl, b);
    }
    store_row<LPS, NV>(cur, P, gl, x);
@@ -301,7 +325,9 @@ __device__ __forceinline__ void finish_entity(const TrainArgs& a, const RowLists
          int r = pass == 0 ? r0 : r1;
          if (pass == 1 && r1 == r0) break;
          float4 b[NV], b0[NV];
-         load_row<LPS, NV>(a.w + (size_t)r * P, P, gl, b0);
+         const bool sr = L.srel != nullptr;
+         if (sr) load_row_shared<LPS, NV>(L.srel + (size_t)(2 * r + 1) * P, P, gl, b0);
+         else load_row<LPS, NV>(a.w + (size_t)r * P, P, gl, b0);
 #pragma unroll
          for (int q = 0; q < NV; q++) b[q] = b0[q];
          int iters = soft_orth_loop<LPS, NV>(x, b, a.lr, gmask);
@@ -311,10 +337,12 @@ __device__ __forceinline__ void finish_entity(const TrainArgs& a, const RowLists
             norm_row<LPS, NV>(b, false, gmask);
 #pragma unroll
             for (int q = 0; q < NV; q++) b[q] = b[q] - b0[q];
-            acc_row<LPS, NV, DET>(a.dw + (size_t)r * P, P, gl, b);
+            acc_row<LPS, NV, DET>((sr ? L.dw_next : a.dw) + (size_t)r * P, P, gl, b);
             if (gl == 0) {
                if (!LIST) {
                   a.flag[(size_t)a.nE + r] = next_stamp;
+               } else if (sr) {
+                  a.cflag[r] = next_stamp;
                } else {
                   // next batch's relation list of this CTA; cflag keeps the mark across the end of a launch
                   a.cflag[r] = next_stamp;
@@ -584,6 +612,184 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
       __syncthreads();
    }
    // counters
+   uint32_t c0 = (gl == 0) ? active_acc : 0u, c1 = tent_acc, c2 = trel_acc;
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+   }
+   if (lane == 0) {
+      if (c0) atomicAdd(a.counters + 0, (unsigned long long)c0);
+      if (c1) atomicAdd(a.counters + 1, (unsigned long long)c1);
+      if (c2) atomicAdd(a.counters + 2, (unsigned long long)c2);
+   }
+}
+
+
+// ================================ TransH with a small relation set: relation rows resident in shared memory ==========
+// WN18 has 18 relations (BASELINE config 2).  In train_kernel the relation-side publish is then a phase of its own in which
+// 18 groups of the whole grid work and everybody else waits at a barrier (6 us of a 14-us batch, per-phase trace), and every
+// entity row of the next phase starts with a dependent L2 load of w_r.  Here EVERY CTA keeps all relation-side rows
+// (d_r, w_r) in its shared memory for the whole launch and finishes the touched ones itself after the first barrier --
+// the inputs (published row + the batch's delta) are the same everywhere and the arithmetic is deterministic, so the 148
+// copies stay bit-identical; CTA 0 writes them back when the launch ends.  What this needs:
+//   * the relation-side deltas cannot be zeroed by "the" publisher while other CTAs still read them, so they ping-pong:
+//     in-launch batch i accumulates into buffer i & 1 (0 = the context's dtab / dw, 1 = relbuf1), the entity-side
+//     constraint carries of batch i go to buffer (i + 1) & 1, and that buffer is zeroed during phase 1 of batch i (its
+//     last readers finished before the previous end-of-batch barrier);
+//   * at the end of the launch the pending carries are moved to buffer 0 and buffer 1 is left zero, so every other kernel
+//     of the context finds the usual state.
+// Same samples, same arithmetic, same order of operations per row as train_kernel<TransH, ..., LIST>: in the deterministic
+// mode the tables are bit-identical (tests/test_gpu_train.py).  Two grid barriers per batch instead of three.
+template <int LPS, int NV, int THREADS, bool DET>
+__global__ void __launch_bounds__(THREADS, 1) train_transh_sr_kernel(const __grid_constant__ TrainArgs a) {
+   constexpr int MODEL = KB2E_MODEL_TRANSH;
+   __shared__ double s_loss[THREADS / 32];
+   extern __shared__ int s_lists[];
+   const int P = a.P, P4 = P >> 2;
+   RowLists L{};
+   L.count = s_lists;
+   L.cap_ent = a.cap_ent;
+   L.cap_rel = 0;
+   L.ent = s_lists + 4;
+   L.srel = reinterpret_cast<float*>(s_lists + 4 + ((a.cap_ent + 3) & ~3));
+   const int lane = threadIdx.x & 31;
+   const int gl = lane % LPS;
+   const uint32_t gmask = LPS == 32 ? 0xffffffffu : (((1u << LPS) - 1u) << ((lane / LPS) * LPS));
+   const int groups_per_block = blockDim.x / LPS;
+   const long long G = (long long)gridDim.x * groups_per_block;
+   const long long g0 = (long long)(threadIdx.x / LPS) * gridDim.x + blockIdx.x;
+   const int group = threadIdx.x / LPS;
+   uint32_t bar_target = 0;
+   uint32_t active_acc = 0, tent_acc = 0, trel_acc = 0;
+   int trace_slot = 0;
+   const uint32_t gb_first = (uint32_t)a.first_epoch * (uint32_t)a.batches;
+   const uint32_t n_batches = (uint32_t)a.n_epochs * (uint32_t)a.batches;
+   float* const dr_buf0 = a.dtab + (size_t)a.nE * P;
+   float* const dr_buf1 = a.relbuf1;
+   float* const dw_buf0 = a.dw;
+   float* const dw_buf1 = a.relbuf1 + (size_t)a.nR * P;
+   Pair pre;
+   DrawStage ds;
+   const bool has_first = g0 < a.batchsize;
+   if (has_first) {
+      pre = draw_pair(a, (uint32_t)g0, gb_first);
+      if (n_batches > 1u) draw_begin(a, (uint32_t)g0, gb_first + 1u, ds);
+   }
+   for (int i = threadIdx.x; i < a.nR * P4; i += blockDim.x) {
+      const int r = i / P4, k = i - r * P4;
+      reinterpret_cast<float4*>(L.srel)[(size_t)(2 * r) * P4 + k] = ld_cg4(a.tab + ((size_t)a.nE + r) * P + 4 * k);
+      reinterpret_cast<float4*>(L.srel)[(size_t)(2 * r + 1) * P4 + k] = ld_cg4(a.w + (size_t)r * P + 4 * k);
+   }
+   if (threadIdx.x < 4) L.count[threadIdx.x] = 0;
+   __syncthreads();
+
+   uint32_t rel_batch = 0;
+   for (int ep = 0; ep < a.n_epochs; ep++) {
+      double loss_acc = 0.0;
+      for (int batch = 0; batch < a.batches; batch++, rel_batch++) {
+         const uint32_t gb = gb_first + rel_batch;
+         const uint32_t stamp = a.stamp_base + rel_batch + 1u;
+         const uint32_t next_stamp = stamp + 1u;
+         const int cur = (int)(rel_batch & 1u);
+         L.dr_cur = cur ? dr_buf1 : dr_buf0;
+         L.dw_cur = cur ? dw_buf1 : dw_buf0;
+         L.dw_next = cur ? dw_buf0 : dw_buf1;
+         float* const dr_next = cur ? dr_buf0 : dr_buf1;
+         KB2E_TRACE();
+         // the buffer the carries of this batch go to: consumed one batch ago, zero it (relation r by CTA r % gridDim.x)
+         for (int r = blockIdx.x; r < a.nR; r += gridDim.x)
+            for (int k = threadIdx.x; k < 2 * P4; k += blockDim.x)
+               st_cg4((k < P4 ? dr_next : L.dw_next) + (size_t)r * P + 4 * (k < P4 ? k : k - P4), f4(0.f));
+         // ---- phase 1 ----
+         if (has_first) process_pair<MODEL, LPS, NV, true, DET>(a, L, pre, gl, gmask, stamp, loss_acc, active_acc);
+         for (long long k = g0 + G; k < a.batchsize; k += G) {
+            Pair s = draw_pair(a, (uint32_t)k, gb);
+            process_pair<MODEL, LPS, NV, true, DET>(a, L, s, gl, gmask, stamp, loss_acc, active_acc);
+         }
+         KB2E_TRACE();
+         grid_barrier(a.barrier, bar_target);   // (ends every read of the shared relation rows in this CTA, too)
+         KB2E_TRACE();
+         if (a.phase1_only) continue;
+         const bool more = rel_batch + 1u < n_batches;
+         if (has_first && more) draw_probe(a, ds);
+         // ---- phase 2a, in every CTA: the touched relation-side rows, shared memory to shared memory ----
+         for (int r = group; r < a.nR; r += groups_per_block) {
+            const bool touched = __ldcg(a.flag + a.nE + r) == stamp || __ldcg(a.cflag + r) == stamp;
+            if (touched) {
+               float4 x[NV], d[NV], b[NV], db[NV];
+               load_row<LPS, NV>(L.dr_cur + (size_t)r * P, P, gl, d);
+               load_row<LPS, NV>(L.dw_cur + (size_t)r * P, P, gl, db);
+               load_row_shared<LPS, NV>(L.srel + (size_t)(2 * r) * P, P, gl, x);
+               load_row_shared<LPS, NV>(L.srel + (size_t)(2 * r + 1) * P, P, gl, b);
+#pragma unroll
+               for (int q = 0; q < NV; q++) {
+                  x[q] = x[q] + (DET ? det_to_float(d[q]) : d[q]);
+                  b[q] = b[q] + (DET ? det_to_float(db[q]) : db[q]);
+               }
+               norm_row<LPS, NV>(x, true, gmask);
+               finish_hyperplane<LPS, NV>(x, b, a.lr, gmask);
+#pragma unroll
+               for (int q = 0; q < NV; q++) {
+                  const int off = (q * LPS + gl) * 4;
+                  if (off < P) {
+                     *reinterpret_cast<float4*>(L.srel + (size_t)(2 * r) * P + off) = x[q];
+                     *reinterpret_cast<float4*>(L.srel + (size_t)(2 * r + 1) * P + off) = b[q];
+                  }
+               }
+               trel_acc += (gl == 0 && blockIdx.x == 0);
+            }
+         }
+         __syncthreads();
+         KB2E_TRACE();
+         // ---- phase 2b: entity rows (w_r from shared memory) ----
+         publish_list<MODEL, LPS, NV, DET>(a, L, L.ent, min(L.count[0], L.cap_ent), group, groups_per_block, stamp, next_stamp, gl, gmask,
+                                           tent_acc, trel_acc);
+         __syncthreads();
+         if (threadIdx.x == 0) L.count[0] = 0;
+         KB2E_TRACE();
+         grid_arrive(a.barrier, bar_target);
+         if (has_first && more) {
+            pre = draw_finish(a, (uint32_t)g0, gb + 1u, ds);
+            if (rel_batch + 2u < n_batches) draw_begin(a, (uint32_t)g0, gb + 2u, ds);
+         }
+         grid_wait(a.barrier, bar_target);
+      }
+      double v = (gl == 0) ? loss_acc : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_loss[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+         double t = 0.0;
+         for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += s_loss[i];
+         if (t != 0.0) {
+            if (DET)
+               atomicAdd(reinterpret_cast<unsigned long long*>(a.loss + ep), (unsigned long long)__double2ll_rn(t * kDetLossScale));
+            else
+               atomicAdd(a.loss + ep, t);
+         }
+      }
+      __syncthreads();
+   }
+   // ---- end of the launch (after the last end-of-batch barrier: nobody reads a delta buffer any more) ----
+   if (blockIdx.x == 0 && !a.phase1_only) {
+      for (int i = threadIdx.x; i < a.nR * P4; i += blockDim.x) {
+         const int r = i / P4, k = i - r * P4;
+         st_cg4(a.tab + ((size_t)a.nE + r) * P + 4 * k, reinterpret_cast<const float4*>(L.srel)[(size_t)(2 * r) * P4 + k]);
+         st_cg4(a.w + (size_t)r * P + 4 * k, reinterpret_cast<const float4*>(L.srel)[(size_t)(2 * r + 1) * P4 + k]);
+         // pending carries -> buffer 0; buffer 1 zero.  The last batch (index n - 1) accumulated into buffer (n - 1) & 1, which
+         // is spent, and carried into buffer n & 1.
+         const size_t off = (size_t)r * P + 4 * k;
+         if (n_batches & 1u) {
+            st_cg4(dr_buf0 + off, ld_cg4(dr_buf1 + off));
+            st_cg4(dw_buf0 + off, ld_cg4(dw_buf1 + off));
+         }
+         st_cg4(dr_buf1 + off, f4(0.f));
+         st_cg4(dw_buf1 + off, f4(0.f));
+      }
+   }
    uint32_t c0 = (gl == 0) ? active_acc : 0u, c1 = tent_acc, c2 = trel_acc;
 #pragma unroll
    for (int o = 16; o > 0; o >>= 1) {
@@ -946,6 +1152,7 @@ void train_free(kb2e_ctx* c) {
    pool_free(c, c->pend);
    pool_free(c, c->cflag);
    pool_free(c, c->transr_aux);
+   pool_free(c, c->relbuf1);
    pool_free(c, c->filt_dev);
 }
 
@@ -1123,6 +1330,17 @@ static TrainKernel pick_kernel(int lps, int nv, int threads) {
       KB2E_PICK(8, 2, 768) KB2E_PICK(16, 2, 768) KB2E_PICK(32, 2, 768)
       KB2E_PICK(8, 4, 512) KB2E_PICK(16, 4, 512) KB2E_PICK(32, 4, 512)
    }
+#undef KB2E_PICK
+   return nullptr;
+}
+
+constexpr int kSmallRelations = 32;   // train_transh_sr_kernel: 2 * 32 rows of <= 512 floats next to the entity list
+
+template <bool DET>
+static TrainKernel pick_transh_sr(int lps, int nv) {
+#define KB2E_PICK(L, N) if (lps == L && nv == N) return train_transh_sr_kernel<L, N, 512, DET>;
+   KB2E_PICK(8, 1) KB2E_PICK(16, 1) KB2E_PICK(32, 1)
+   KB2E_PICK(8, 2) KB2E_PICK(16, 2) KB2E_PICK(32, 2)
 #undef KB2E_PICK
    return nullptr;
 }
@@ -1384,6 +1602,22 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
       else
          k = !list_bytes ? pick_kernel<KB2E_MODEL_TRANSH, false, false>(lps, nv, threads)
                          : (det ? pick_kernel<KB2E_MODEL_TRANSH, true, true>(lps, nv, threads) : pick_kernel<KB2E_MODEL_TRANSH, true, false>(lps, nv, threads));
+      // few relations (WN18: 18): relation-side rows resident in every CTA's shared memory, two barriers per batch
+      const char* sr_env = getenv("KB2E_TRANSH_SR");   // 0: off (A-B measurements, the bit-identity test)
+      if (c->cfg.model == KB2E_MODEL_TRANSH && list_bytes && c->nR <= kSmallRelations && !(sr_env && atoi(sr_env) == 0)) {
+         TrainKernel ksr = det ? pick_transh_sr<true>(lps, nv) : pick_transh_sr<false>(lps, nv);
+         const size_t sr_bytes = (size_t)(4 + ((a.cap_ent + 3) & ~3)) * sizeof(int) + 2 * (size_t)c->nR * c->P * sizeof(float);
+         if (ksr && sr_bytes <= 48 * 1024) {
+            if (!c->relbuf1) {
+               KB2E_CUDA(c, pool_alloc(c, &c->relbuf1, 2 * (size_t)c->nR * c->P * sizeof(float)));
+               KB2E_CUDA(c, cudaMemsetAsync(c->relbuf1, 0, 2 * (size_t)c->nR * c->P * sizeof(float), c->stream));
+            }
+            a.relbuf1 = c->relbuf1;
+            a.cap_rel = 0;
+            list_bytes = sr_bytes;
+            k = ksr;
+         }
+      }
    }
    if (!k && !transr) return fail(c, KB2E_ERR_LIMIT, "no training kernel for this embedding size");
    // row stamps of this launch: stamp_base + 1 ... stamp_base + #batches, never reused by a later launch

@@ -39,6 +39,7 @@ struct TrainArgs {
    int replicas;                  // batched training (train_sweep_kernel): K models stacked in tab / dtab / flag, K x (nE + nR) rows
    const struct RepParams* rep;   // [replicas] per-model learning rate, margin, seed
    int tasks_per_group;           // sweep: (model, sample) tasks one group handles per batch (<= lanes per group)
+   float* relbuf1;                // train_transh_sr_kernel: second buffer of the relation-side deltas, [2][nR][P]
    int phase1_only;               // test hook (kb2e_train_batch_deltas): stop after the accumulation phase
    int cap_ent, cap_rel;          // LIST kernels: capacities of the per-CTA touched-row lists (train.cu)
    unsigned long long* trace;     // tuning aid (KB2E_TRAIN_TRACE): per-CTA clock stamps of the first batches

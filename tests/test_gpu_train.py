@@ -430,6 +430,42 @@ def test_deterministic_mode_is_bit_reproducible_and_equivalent(gpu_lib, oracle, 
         assert (diff > 3e-6).mean() < 1e-2 and diff.max() <= 8 * LR
 
 
+@pytest.mark.parametrize("D,batches", [(100, 7), (50, 10), (200, 3)])
+def test_transh_relations_resident_in_shared_memory_is_the_same_computation(gpu_lib, monkeypatch, D, batches):
+    """TransH with at most 32 relations (WN18: 18) runs train_transh_sr_kernel: every CTA keeps the relation-side rows in shared
+    memory and finishes them itself, the relation-side deltas ping-pong between two buffers, two barriers per batch instead of
+    three.  Same samples and the same arithmetic per row as the three-barrier list kernel (KB2E_TRANSH_SR=0): in the
+    deterministic mode the losses and all three tables are bit-identical -- over launches with odd and even batch counts
+    (the end-of-launch hand-over of the pending carries) and when the two kernels alternate on one context."""
+    import kb2e_b200
+    from kb2e_b200 import kg
+    g = kg.make_kg("tiny", seed=6)
+    nE, nR = g["nE"], g["nR"]
+    assert nR <= 32
+    hm, tm = kg.bern_stats(g["train"], nR)
+
+    def run(schedule):
+        with make_ctx("transh", D, nE, nR, method=1, distance=0, batches=batches, rate=LR, margin=1.0, seed=77,
+                      flags=kb2e_b200.FLAG_DETERMINISTIC) as ctx:
+            ctx.set_train_triples(g["train"])
+            ctx.set_bern(hm, tm)
+            ctx.init_embeddings()
+            losses, first = [], 0
+            for sr, n in schedule:
+                monkeypatch.setenv("KB2E_TRANSH_SR", "1" if sr else "0")
+                losses.append(ctx.train_epochs(first, n))
+                first += n
+            monkeypatch.delenv("KB2E_TRANSH_SR")
+            return (np.concatenate(losses),) + download_tables(ctx)
+
+    want = run([(False, 5), (False, 1), (False, 4), (False, 2)])
+    assert want[0][-1] < want[0][0]
+    for schedule in ([(True, 5), (True, 1), (True, 4), (True, 2)], [(True, 5), (False, 1), (True, 4), (False, 2)]):
+        got = run(schedule)
+        for x, y in zip(got, want):
+            assert np.array_equal(x, y), schedule
+
+
 @pytest.mark.parametrize("D,dist,K", [(100, 1, 4), (50, 0, 3), (20, 0, 7)])
 def test_batched_models_equal_the_same_models_trained_alone(gpu_lib, D, dist, K):
     """kb2e_set_replicas: K TransE models (different seeds, rates, margins) trained in ONE persistent launch each compute
