@@ -70,6 +70,12 @@ __device__ __forceinline__ float4 ld_cg4_pinned(const float* p) {
    return v;
 }
 
+__device__ __forceinline__ uint32_t ld_cg_u32_pinned(const uint32_t* p) {
+   uint32_t v;
+   asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+   return v;
+}
+
 // Vector reduction into global memory: one 16-byte RED instead of four scalar atomics (sm_90+).
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"

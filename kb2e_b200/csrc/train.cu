@@ -284,11 +284,12 @@ __device__ __forceinline__ void apply_delta(float* del, int P, int gl, float4 (&
 // Relation-side row r: d_r (and w_r).  transe/trainer.cpp:43, transh/trainer.cpp:48,52,56.
 // w_r after its delta, against the finished d_r (x): transh/trainer.cpp:52-54
 template <int LPS, int NV>
-__device__ __forceinline__ void finish_hyperplane(float4 (&x)[NV], float4 (&b)[NV], float lr, uint32_t gmask) {
+__device__ __forceinline__ int finish_hyperplane(float4 (&x)[NV], float4 (&b)[NV], float lr, uint32_t gmask) {
    norm_row<LPS, NV>(b, false, gmask);          // transh/trainer.cpp:52
    norm_row<LPS, NV>(b, false, gmask);          // common/utils.cpp:82
-   soft_orth_loop<LPS, NV>(x, b, lr, gmask);    // common/utils.cpp:83-108
+   const int steps = soft_orth_loop<LPS, NV>(x, b, lr, gmask);    // common/utils.cpp:83-108
    norm_row<LPS, NV>(b, false, gmask);          // common/utils.cpp:110
+   return steps;
 }
 
 template <int MODEL, int LPS, int NV, bool DET>
@@ -642,6 +643,55 @@ __global__ void __launch_bounds__(THREADS, 1) train_kernel(const __grid_constant
 //     of the context finds the usual state.
 // Same samples, same arithmetic, same order of operations per row as train_kernel<TransH, ..., LIST>: in the deterministic
 // mode the tables are bit-identical (tests/test_gpu_train.py).  Two grid barriers per batch instead of three.
+// Phase 2a of train_transh_sr_kernel: groups of RL lanes, one touched relation each; the stamps and both delta rows are
+// requested together (pinned loads: one L2 round trip, not two).  Returns 1 per finished relation in lane 0 of its group, CTA 0.
+template <int RL, int RNV, bool DET>
+__device__ __forceinline__ uint32_t sr_finish_relations(const TrainArgs& a, const RowLists& L, uint32_t stamp, unsigned long long* fine = nullptr) {
+   // tuning aid (KB2E_TRAIN_TRACE_FINE): thread 0 stamps "deltas arrived", "d_r normalised", "w_r finished" + the loop's step count
+   auto mark = [&](int k, unsigned long long extra) {
+      if (fine != nullptr && threadIdx.x == 0) {
+         unsigned long long t_;
+         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+         fine[k] = extra ? extra : t_;
+      }
+   };
+   const int P = a.P;
+   const int lane = threadIdx.x & 31;
+   const int gl = lane % RL;
+   const uint32_t gmask = RL == 32 ? 0xffffffffu : (((1u << RL) - 1u) << ((lane / RL) * RL));
+   const int group = threadIdx.x / RL, groups = blockDim.x / RL;
+   uint32_t done = 0;
+   for (int r = group; r < a.nR; r += groups) {
+      float4 x[RNV], d[RNV], b[RNV], db[RNV];
+      const uint32_t f0 = ld_cg_u32_pinned(a.flag + a.nE + r), f1 = ld_cg_u32_pinned(a.cflag + r);
+      load_row_pinned<RL, RNV>(L.dr_cur + (size_t)r * P, P, gl, d);
+      load_row_pinned<RL, RNV>(L.dw_cur + (size_t)r * P, P, gl, db);
+      if (f0 != stamp && f1 != stamp) continue;
+      if (fine != nullptr) { asm volatile("" :: "f"(d[0].x), "f"(db[0].x)); mark(0, 0); }
+      load_row_shared<RL, RNV>(L.srel + (size_t)(2 * r) * P, P, gl, x);
+      load_row_shared<RL, RNV>(L.srel + (size_t)(2 * r + 1) * P, P, gl, b);
+#pragma unroll
+      for (int q = 0; q < RNV; q++) {
+         x[q] = x[q] + (DET ? det_to_float(d[q]) : d[q]);
+         b[q] = b[q] + (DET ? det_to_float(db[q]) : db[q]);
+      }
+      norm_row<RL, RNV>(x, true, gmask);
+      if (fine != nullptr) { asm volatile("" :: "f"(x[0].x)); mark(1, 0); }
+      const int steps = finish_hyperplane<RL, RNV>(x, b, a.lr, gmask);
+      if (fine != nullptr) { asm volatile("" :: "f"(b[0].x)); mark(2, 0); mark(3, 1000000ull + (unsigned long long)steps); }
+#pragma unroll
+      for (int q = 0; q < RNV; q++) {
+         const int off = (q * RL + gl) * 4;
+         if (off < P) {
+            *reinterpret_cast<float4*>(L.srel + (size_t)(2 * r) * P + off) = x[q];
+            *reinterpret_cast<float4*>(L.srel + (size_t)(2 * r + 1) * P + off) = b[q];
+         }
+      }
+      done += (gl == 0 && blockIdx.x == 0);
+   }
+   return done;
+}
+
 template <int LPS, int NV, int THREADS, bool DET>
 __global__ void __launch_bounds__(THREADS, 1) train_transh_sr_kernel(const __grid_constant__ TrainArgs a) {
    constexpr int MODEL = KB2E_MODEL_TRANSH;
@@ -715,32 +765,16 @@ __global__ void __launch_bounds__(THREADS, 1) train_transh_sr_kernel(const __gri
          const bool more = rel_batch + 1u < n_batches;
          if (has_first && more) draw_probe(a, ds);
          // ---- phase 2a, in every CTA: the touched relation-side rows, shared memory to shared memory ----
-         for (int r = group; r < a.nR; r += groups_per_block) {
-            const bool touched = __ldcg(a.flag + a.nE + r) == stamp || __ldcg(a.cflag + r) == stamp;
-            if (touched) {
-               float4 x[NV], d[NV], b[NV], db[NV];
-               load_row<LPS, NV>(L.dr_cur + (size_t)r * P, P, gl, d);
-               load_row<LPS, NV>(L.dw_cur + (size_t)r * P, P, gl, db);
-               load_row_shared<LPS, NV>(L.srel + (size_t)(2 * r) * P, P, gl, x);
-               load_row_shared<LPS, NV>(L.srel + (size_t)(2 * r + 1) * P, P, gl, b);
-#pragma unroll
-               for (int q = 0; q < NV; q++) {
-                  x[q] = x[q] + (DET ? det_to_float(d[q]) : d[q]);
-                  b[q] = b[q] + (DET ? det_to_float(db[q]) : db[q]);
-               }
-               norm_row<LPS, NV>(x, true, gmask);
-               finish_hyperplane<LPS, NV>(x, b, a.lr, gmask);
-#pragma unroll
-               for (int q = 0; q < NV; q++) {
-                  const int off = (q * LPS + gl) * 4;
-                  if (off < P) {
-                     *reinterpret_cast<float4*>(L.srel + (size_t)(2 * r) * P + off) = x[q];
-                     *reinterpret_cast<float4*>(L.srel + (size_t)(2 * r + 1) * P + off) = b[q];
-                  }
-               }
-               trel_acc += (gl == 0 && blockIdx.x == 0);
-            }
+         // 32 x 1 rows are handled by half-warps (16 lanes x 2 vectors): twice the groups, so WN18's 18 relations take one
+         // round instead of two.  The sums come out bit-identical: lane i adds elements i and i + 16 first, which is exactly
+         // the first stage of the 32-lane butterfly.
+         unsigned long long* fine = nullptr;
+         if ((a.flags & 0x80000000u) && a.trace != nullptr && trace_slot + 6 < kTraceSlots) {
+            fine = a.trace + (size_t)blockIdx.x * kTraceSlots + trace_slot;
+            trace_slot += 4;
          }
+         if (LPS == 32 && NV == 1) trel_acc += sr_finish_relations<16, 2, DET>(a, L, stamp, fine);
+         else trel_acc += sr_finish_relations<LPS, NV, DET>(a, L, stamp, fine);
          __syncthreads();
          KB2E_TRACE();
          // ---- phase 2b: entity rows (w_r from shared memory) ----

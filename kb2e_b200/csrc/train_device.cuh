@@ -120,7 +120,11 @@ __device__ __forceinline__ void norm_row(float4 (&v)[NV], bool ignoreShort, uint
    float len = sqrtf(len2_row<LPS, NV>(v, gmask));
    if (!ignoreShort || len > 1.f) {
 #pragma unroll
-      for (int q = 0; q < NV; q++) v[q] = make_float4(v[q].x / len, v[q].y / len, v[q].z / len, v[q].w / len);
+      // one IEEE reciprocal, then multiplications: eight IEEE divisions by the same number compile to eight serialised
+      // MUFU.RCP + FCHK + 5-FFMA sequences (each its own reconvergence region), measured at ~1 us per row
+      // (tools/trace_transh_sr_fine.py) on the critical path of every publish; <= 1 ulp from the divided value
+      const float inv = 1.f / len;
+      for (int q = 0; q < NV; q++) v[q] = make_float4(v[q].x * inv, v[q].y * inv, v[q].z * inv, v[q].w * inv);
    }
 }
 
@@ -150,8 +154,13 @@ __device__ __forceinline__ int soft_orth_loop(float4 (&a)[NV], float4 (&b)[NV], 
    float a1 = 1.f, a2 = 0.f, b1 = 0.f, b2 = 1.f, sum = 0.f;
    int iters = 0;
    while (true) {
-      sum = sqrtf(sum + B);
-      const float inv = 1.f / sum;
+      // sum = sqrt(sum + B), b /= sum: one approximate reciprocal square root (2 ulp) instead of an IEEE square root and an
+      // IEEE division on the loop-carried path -- the chain per iteration is ~45 instead of ~110 cycles, and tens of
+      // iterations are common.  inv scales b, B and X consistently, so its rounding is a slightly different normalisation of
+      // b (renormalised after the loop), not an inconsistency.
+      const float s2 = sum + B;
+      const float inv = rsqrtf(s2);
+      sum = s2 * inv;
       b1 *= inv; b2 *= inv;            // b /= sum
       B *= inv * inv;
       X *= inv;                        // x = a . b

@@ -306,7 +306,8 @@ __device__ __forceinline__ void transr_finish_relation(const RArgs& ra, int r, i
       const float len = sqrtf(warp_sum(dot4(x, x)));
       if (on) {
          st_cg4(a.dtab + ((size_t)a.nE + r) * P + lane * 4, f4(0.f));
-         st_cg4(a.tab + ((size_t)a.nE + r) * P + lane * 4, make_float4(x.x / len, x.y / len, x.z / len, x.w / len));
+         const float inv = 1.f / len;   // one reciprocal, four products (norm_row, train_device.cuh)
+         st_cg4(a.tab + ((size_t)a.nE + r) * P + lane * 4, make_float4(x.x * inv, x.y * inv, x.z * inv, x.w * inv));
       }
    }
    __syncwarp();
@@ -327,7 +328,8 @@ __device__ __forceinline__ void transr_finish_relation(const RArgs& ra, int r, i
       const int j = (int)__umulhi((uint32_t)f, ra.p4_magic);
       const float4 m = *reinterpret_cast<const float4*>(sM + j * ra.pitch + 4 * (f - j * P4));
       const float lj = sV[S_SP * P + j];
-      st_cg4(M + 4 * (size_t)f, make_float4(m.x / lj, m.y / lj, m.z / lj, m.w / lj));
+      const float ij = 1.f / lj;
+      st_cg4(M + 4 * (size_t)f, make_float4(m.x * ij, m.y * ij, m.z * ij, m.w * ij));
    }
    __syncwarp();
 }
@@ -450,7 +452,8 @@ __device__ __forceinline__ void transr_finish_entity(const RArgs& ra, int e, flo
       r1 = __ldcg(a.rmax + e);
       x4 = x4 + d4;
       const float len = sqrtf(warp_sum(dot4(x4, x4)));
-      x4 = make_float4(x4.x / len, x4.y / len, x4.z / len, x4.w / len);
+      const float inv = 1.f / len;
+      x4 = make_float4(x4.x * inv, x4.y * inv, x4.z * inv, x4.w * inv);
       if (on) st_cg4(a.dtab + (size_t)e * P + lane * 4, f4(0.f));
       if (lane == 0) { a.rmin[e] = 0x7fffffff; a.rmax[e] = -1; }
    }
@@ -474,7 +477,7 @@ __device__ __forceinline__ void transr_finish_entity(const RArgs& ra, int e, flo
 // matrices), so static row ranges leave most warps idle behind the unlucky ones.  Instead the CTA compacts
 // the stamps of a window of rows into an ordered list in shared memory (ballot + warp-count prefix) and its
 // warps take list entries one at a time.
-constexpr int kListCap = 1024;
+constexpr int kListCap = 1536;   // FB15k: 1,345 relations in one window; 18 warps of D = 50 still fit next to it
 
 struct RowList {
    int n;
@@ -489,22 +492,34 @@ __device__ __forceinline__ void compact_rows(RowList& list, long long begin, lon
    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
    if (threadIdx.x == 0) { list.n = 0; list.next = 0; }
    __syncthreads();
-   for (long long base = begin; base < end; base += blockDim.x) {
-      const long long r = base + threadIdx.x;
-      const bool f = r < end && pred(r);
-      const uint32_t m = __ballot_sync(0xffffffffu, f);
-      if (lane == 0) list.wcnt[warp] = __popc(m);
-      __syncthreads();
-      int off = list.n, total = 0;
-      for (int w = 0; w < warps; w++) {
-         const int c = list.wcnt[w];
-         if (w < warp) off += c;
-         total += c;
+   constexpr int U = 4;   // stamps of four strides are loaded together: one L2 round trip instead of four
+   for (long long base0 = begin; base0 < end; base0 += (long long)U * blockDim.x) {
+      bool fs[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+         const long long r = base0 + (long long)u * blockDim.x + threadIdx.x;
+         fs[u] = r < end && pred(r);
       }
-      if (f) list.item[off + __popc(m & ((1u << lane) - 1u))] = (int)(r - begin);
-      __syncthreads();
-      if (threadIdx.x == 0) list.n += total;
-      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+         const long long base = base0 + (long long)u * blockDim.x;
+         if (base >= end) break;
+         const long long r = base + threadIdx.x;
+         const bool f = fs[u];
+         const uint32_t m = __ballot_sync(0xffffffffu, f);
+         if (lane == 0) list.wcnt[warp] = __popc(m);
+         __syncthreads();
+         int off = list.n, total = 0;
+         for (int w = 0; w < warps; w++) {
+            const int c = list.wcnt[w];
+            if (w < warp) off += c;
+            total += c;
+         }
+         if (f) list.item[off + __popc(m & ((1u << lane) - 1u))] = (int)(r - begin);
+         __syncthreads();
+         if (threadIdx.x == 0) list.n += total;
+         __syncthreads();
+      }
    }
 }
 

@@ -436,13 +436,17 @@ def test_transh_relations_resident_in_shared_memory_is_the_same_computation(gpu_
     memory and finishes them itself, the relation-side deltas ping-pong between two buffers, two barriers per batch instead of
     three.  Same samples and the same arithmetic per row as the three-barrier list kernel (KB2E_TRANSH_SR=0): in the
     deterministic mode the losses and all three tables are bit-identical -- over launches with odd and even batch counts
-    (the end-of-launch hand-over of the pending carries) and when the two kernels alternate on one context."""
+    (the end-of-launch hand-over of the pending carries) and when the two kernels alternate on one context.  D = 100 is the
+    one shape whose relation rows are finished by half-warps (16 lanes x 2 vectors instead of 32 x 1: 18 relations in one
+    round); its sums round differently in the last bit (measured: tables differ by <= 5e-7 after 6,000 batches), so that
+    case is compared over a short run with a tolerance, and bit for bit against itself."""
     import kb2e_b200
     from kb2e_b200 import kg
     g = kg.make_kg("tiny", seed=6)
     nE, nR = g["nE"], g["nR"]
     assert nR <= 32
     hm, tm = kg.bern_stats(g["train"], nR)
+    exact = D != 100
 
     def run(schedule):
         with make_ctx("transh", D, nE, nR, method=1, distance=0, batches=batches, rate=LR, margin=1.0, seed=77,
@@ -458,12 +462,24 @@ def test_transh_relations_resident_in_shared_memory_is_the_same_computation(gpu_
             monkeypatch.delenv("KB2E_TRANSH_SR")
             return (np.concatenate(losses),) + download_tables(ctx)
 
-    want = run([(False, 5), (False, 1), (False, 4), (False, 2)])
+    if exact:
+        plain = [(False, 5), (False, 1), (False, 4), (False, 2)]
+        schedules = ([(True, 5), (True, 1), (True, 4), (True, 2)], [(True, 5), (False, 1), (True, 4), (False, 2)])
+    else:
+        plain = [(False, 2), (False, 1)]
+        schedules = ([(True, 2), (True, 1)], [(True, 2), (False, 1)], [(False, 2), (True, 1)])
+    want = run(plain)
     assert want[0][-1] < want[0][0]
-    for schedule in ([(True, 5), (True, 1), (True, 4), (True, 2)], [(True, 5), (False, 1), (True, 4), (False, 2)]):
+    for schedule in schedules:
         got = run(schedule)
         for x, y in zip(got, want):
-            assert np.array_equal(x, y), schedule
+            if exact:
+                assert np.array_equal(x, y), schedule
+            else:
+                assert np.allclose(x, y, rtol=1e-5, atol=2e-5), (schedule, np.abs(x - y).max())
+    again = run(schedules[0])
+    for x, y in zip(again, run(schedules[0])):
+        assert np.array_equal(x, y)
 
 
 @pytest.mark.parametrize("D,dist,K", [(100, 1, 4), (50, 0, 3), (20, 0, 7)])

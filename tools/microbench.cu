@@ -49,6 +49,31 @@ __global__ void barrier_test(uint32_t* counter, int iters, int mode, long long* 
    if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
 }
 
+// 2b. hierarchical variant (round-1 review suggestion): barrier.cluster over a 4-CTA cluster, ONE arrival per cluster on the
+//     global counter (37 instead of 148), the cluster leader polls, a second barrier.cluster releases its three siblings
+__global__ void barrier_cluster_test(uint32_t* counter, int iters, long long* out) {
+   uint32_t target = 0;
+   uint32_t rank;
+   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+   const uint32_t n_clusters = gridDim.x / 4;
+   long long t0 = clock64();
+   for (int i = 0; i < iters; i++) {
+      // every thread of the cluster takes part in barrier.cluster (it counts threads, not CTAs): it stands in for bar.sync
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      target += n_clusters;
+      if (rank == 0 && threadIdx.x == 0) {
+         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(counter), "r"(1u) : "memory");
+         while ((int32_t)(ld_rlx(counter) - target) < 0) {}
+         asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      }
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+   }
+   long long t1 = clock64();
+   if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+}
+
 // 3. RED.128 throughput: every thread adds float4 to pseudo-random rows of a table [rows][pitch]
 __global__ void red_test(float* tab, int rows, int pitch4, int per_thread, long long* out) {
    int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,6 +143,31 @@ int main() {
       cudaEventRecord(e1); CK(cudaDeviceSynchronize());
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       printf("grid barrier (%d CTAs x %d thr, mode %d): %.0f ns each (%.0f cycles)\n", sms, threads, mode, ms * 1e6 / iters, (double)out[0] / iters);
+   }
+   for (int threads : {1024, 256}) {
+      // 148 = 37 clusters of 4; every CTA is resident (one per SM), so the plain launch is as good as a cooperative one here
+      CK(cudaMemset(counter, 0, 4));
+      int iters = 2000;
+      // a spinning barrier needs every cluster resident at once: ask how many fit (GPCs with an SM count that is not a
+      // multiple of 4 leave SMs unused) and launch no more than that
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((sms / 4) * 4); cfg.blockDim = dim3(threads);
+      cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int max_clusters = 0;
+      CK(cudaOccupancyMaxActiveClusters(&max_clusters, barrier_cluster_test, &cfg));
+      const int clusters = max_clusters < sms / 4 ? max_clusters : sms / 4;
+      if (clusters < 1) { printf("cluster barrier: no resident cluster\n"); break; }
+      cfg.gridDim = dim3(clusters * 4);
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      cudaEventRecord(e0);
+      CK(cudaLaunchKernelEx(&cfg, barrier_cluster_test, counter, iters, out));
+      cudaEventRecord(e1);
+      cudaError_t err = cudaDeviceSynchronize();
+      if (err != cudaSuccess) { printf("cluster barrier launch: %s\n", cudaGetErrorString(err)); break; }
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      printf("grid barrier (%d CTAs x %d thr in %d resident clusters of 4 (of %d wanted): barrier.cluster + one arrival per cluster): %.0f ns each (%.0f cycles)\n",
+             clusters * 4, threads, clusters, sms / 4, ms * 1e6 / iters, (double)out[0] / iters);
    }
    // RED throughput: rows of 100 floats (25 float4), table of 16296 rows, total ~ 480k RED.128 (one batch at alpha=1)
    int rows = 16296, pitch4 = 25;
