@@ -314,21 +314,31 @@ __device__ __forceinline__ void finish_relation(const TrainArgs& a, int r, int g
 // Entity row e.  transe/trainer.cpp:44-45, transh/trainer.cpp:49-50,57-58.
 template <int MODEL, int LPS, int NV, bool LIST, bool DET>
 __device__ __forceinline__ void finish_entity(const TrainArgs& a, const RowLists& L, int e, int gl, uint32_t gmask, uint32_t next_stamp,
-                                              float4 (&x)[NV], float4 (&d)[NV]) {
+                                              float4 (&x)[NV], float4 (&d)[NV], bool have_range = false, int pre_r0 = 0, int pre_r1 = -1) {
    const int P = a.P;
    float* cur = a.tab + (size_t)e * P;
    apply_delta<LPS, NV, DET>(a.dtab + (size_t)e * P, P, gl, x, d);
    norm_row<LPS, NV>(x, true, gmask);
    if (MODEL == KB2E_MODEL_TRANSH) {
-      int r0 = __ldcg(a.rmin + e), r1 = __ldcg(a.rmax + e);
+      // (list publish: the range was requested together with the row, not after the claim came back)
+      int r0 = have_range ? pre_r0 : __ldcg(a.rmin + e), r1 = have_range ? pre_r1 : __ldcg(a.rmax + e);
       if (gl == 0) { a.rmin[e] = 0x7fffffff; a.rmax[e] = -1; }
+      const bool sr = L.srel != nullptr;
+      // both hyperplanes are requested up front (global copies: one L2 round trip instead of one per pass)
+      float4 w_hi[NV];
+      if (!sr && r1 >= 0 && r1 != r0) load_row<LPS, NV>(a.w + (size_t)r1 * P, P, gl, w_hi);
       for (int pass = 0; pass < 2 && r1 >= 0; pass++) {
          int r = pass == 0 ? r0 : r1;
          if (pass == 1 && r1 == r0) break;
          float4 b[NV], b0[NV];
-         const bool sr = L.srel != nullptr;
-         if (sr) load_row_shared<LPS, NV>(L.srel + (size_t)(2 * r + 1) * P, P, gl, b0);
-         else load_row<LPS, NV>(a.w + (size_t)r * P, P, gl, b0);
+         if (sr) {
+            load_row_shared<LPS, NV>(L.srel + (size_t)(2 * r + 1) * P, P, gl, b0);
+         } else if (pass == 0) {
+            load_row<LPS, NV>(a.w + (size_t)r * P, P, gl, b0);
+         } else {
+#pragma unroll
+            for (int q = 0; q < NV; q++) b0[q] = w_hi[q];
+         }
 #pragma unroll
          for (int q = 0; q < NV; q++) b[q] = b0[q];
          int iters = soft_orth_loop<LPS, NV>(x, b, a.lr, gmask);
@@ -436,11 +446,11 @@ __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists&
          fine[k + 3] = extra;
       }
    };
-   auto finish = [&](int r, float4 (&x)[NV], float4 (&d)[NV]) {
+   auto finish = [&](int r, float4 (&x)[NV], float4 (&d)[NV], int rlo, int rhi) {
       // (several stacked models, TransE only: row r of the stack; relation and entity rows are finished alike)
       const bool is_rel = rows_per_model ? (r % rows_per_model) >= a.nE : r >= a.nE;
       if (is_rel) { finish_relation<MODEL, LPS, NV, DET>(a, r - a.nE, gl, gmask, x, d); trel += (gl == 0); }
-      else { finish_entity<MODEL, LPS, NV, true, DET>(a, L, r, gl, gmask, next_stamp, x, d); tent += (gl == 0); }
+      else { finish_entity<MODEL, LPS, NV, true, DET>(a, L, r, gl, gmask, next_stamp, x, d, MODEL != KB2E_MODEL_TRANSE, rlo, rhi); tent += (gl == 0); }
    };
    for (int i = group; i < n; i += 2 * groups) {
       const int r0 = list[i];
@@ -453,16 +463,26 @@ __device__ __forceinline__ void publish_list(const TrainArgs& a, const RowLists&
       float4 x0[NV], d0[NV], x1[NV], d1[NV];
       load_row_pinned<LPS, NV>(a.tab + (size_t)r0 * P, P, gl, x0);   // pinned: issued with the claim, not after it
       load_row_pinned<LPS, NV>(a.dtab + (size_t)r0 * P, P, gl, d0);
+      // TransH entity rows: the range of relations that touched the row (a dependent L2 round trip if left to finish_entity)
+      int lo0 = 0, hi0 = -1, lo1 = 0, hi1 = -1;
+      if (MODEL != KB2E_MODEL_TRANSE && r0 < a.nE) {
+         lo0 = (int)ld_cg_u32_pinned(reinterpret_cast<const uint32_t*>(a.rmin + r0));
+         hi0 = (int)ld_cg_u32_pinned(reinterpret_cast<const uint32_t*>(a.rmax + r0));
+      }
       if (r1 >= 0) {
          load_row_pinned<LPS, NV>(a.tab + (size_t)r1 * P, P, gl, x1);
          load_row_pinned<LPS, NV>(a.dtab + (size_t)r1 * P, P, gl, d1);
+         if (MODEL != KB2E_MODEL_TRANSE && r1 < a.nE) {
+            lo1 = (int)ld_cg_u32_pinned(reinterpret_cast<const uint32_t*>(a.rmin + r1));
+            hi1 = (int)ld_cg_u32_pinned(reinterpret_cast<const uint32_t*>(a.rmax + r1));
+         }
       }
       mine0 = __shfl_sync(gmask, mine0, leader);
       mine1 = __shfl_sync(gmask, mine1, leader);
       mark(0, (unsigned long long)n);
-      if (mine0) finish(r0, x0, d0);
+      if (mine0) finish(r0, x0, d0, lo0, hi0);
       mark(1, (unsigned long long)(mine0 + 2 * mine1));
-      if (mine1) finish(r1, x1, d1);
+      if (mine1) finish(r1, x1, d1, lo1, hi1);
       mark(2, (unsigned long long)(r1 >= 0));
    }
 }
