@@ -30,9 +30,15 @@ traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
 lines = []
 for spec in sys.argv[2:]:
     name, rep = spec.split("=", 1)
+    if not os.path.exists(rep):   # (the capture's kernel filter matched nothing: say so, keep the other summaries)
+        lines.append("## %s: no report (%s)" % (name, rep))
+        continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    hdr = next((i for i, r in enumerate(rows) if r and r[0] == "ID"), None)
+    if hdr is None:
+        lines.append("## %s: unreadable report (%s)" % (name, rep))
+        continue
     cols, units, vals = rows[hdr], rows[hdr + 1], rows[hdr + 2]
     ix = {c: i for i, c in enumerate(cols)}
     lines.append("## %s: %s" % (name, vals[ix["Kernel Name"]]))
