@@ -12,6 +12,6 @@ timeout 600 python -m pytest tests/test_gpu_programs.py -m gpu -q -k "shards or 
 timeout 900 $TR bench.py --gpus 2 --steps 3 --warmup 3 > $O/r02_bench_2gpu.json 2> $O/r02_bench_2gpu.err || tail -20 $O/r02_bench_2gpu.err
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/r02_bench_2gpu.json'))
+d=[json.loads(l) for l in open('gpurun_out/r02_bench_2gpu.json') if l.startswith('{')][-1]   # (NCCL prints its version line first)
 print('N=2 train value %.1f M/s | eval value %.1f M q/s e2e cold %.1f resident %.1f | partitioned %s' % (d['value']/1e6, d['eval']['value']/1e6, d['eval']['e2e']['value']/1e6, d['eval']['e2e']['resident']['value']/1e6, {k: d['partitioned'].get(k) for k in ('value','ms_per_epoch','error')} if d.get('partitioned') else None))
 PY
