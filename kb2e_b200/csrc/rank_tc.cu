@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -40,8 +41,9 @@ constexpr int KSTEPS = KC / 2;   // one MMA consumes K = 16 bf16 = 2 chunks
 constexpr int TILE_BYTES = BM * KC * 16;   // one operand tile: [chunk][row][16 B]
 constexpr int STAGES = 2;        // B-tile ring and TMEM accumulator ring
 constexpr int MT = 2;            // 128-query tiles per CTA: every candidate tile fetched from L2 feeds MT accumulators
-constexpr int EPI_WARPS = 4 * MT;
-constexpr int THREADS = 32 * (EPI_WARPS + 2);   // epilogue warps (TMEM lane quarters), + copy producer, + MMA issuer
+constexpr int CSPLIT = 1;        // epilogue warps per (accumulator, TMEM lane quarter): each takes BN / CSPLIT columns (2 was measured: no gain)
+constexpr int EPI_WARPS = 4 * MT * CSPLIT;
+constexpr int THREADS = 32 * (EPI_WARPS + 2);   // epilogue warps, + copy producer, + MMA issuer
 constexpr int SMEM_BYTES = (2 * MT + 2 * STAGES) * TILE_BYTES + 128;
 constexpr int TMEM_COLS = STAGES * MT * BN;      // 512: the whole tensor memory of the SM
 
@@ -102,12 +104,16 @@ __global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) 
    unsigned char* sA = smem;                             // MT x [hi | lo]
    unsigned char* sB = smem + 2 * MT * TILE_BYTES;       // STAGES x [hi | lo]
    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 * MT + 2 * STAGES) * TILE_BYTES);
-   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
+   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5 + 2 * STAGES * MT);
    const uint32_t bar_a = smem_u32(bars + 0);
    const uint32_t bar_full = smem_u32(bars + 1);         // + stage
    const uint32_t bar_empty = smem_u32(bars + 3);        // + stage
-   const uint32_t bar_tfull = smem_u32(bars + 5);        // + accumulator
-   const uint32_t bar_tempty = smem_u32(bars + 7);       // + accumulator
+   // one pair per ACCUMULATOR (stage, query tile), not per stage: the four epilogue warps of query tile 0 start on its
+   // accumulator while the tensor core is still busy with tile 1, and the MMAs of tile 0 two stages on wait only for those
+   // four warps.  (With one pair per stage both sides spent ~40 % of their time waiting for each other: ncu source view.)
+   const uint32_t bar_tfull = smem_u32(bars + 5);                      // + stage * MT + query tile
+   const uint32_t bar_tempty = smem_u32(bars + 5 + STAGES * MT);       // + stage * MT + query tile
+   static_assert((5 + 2 * STAGES * MT) * 8 + 4 <= 128, "barrier block");
 
    const int warp = threadIdx.x >> 5;
    const int lane = threadIdx.x & 31;
@@ -116,14 +122,22 @@ __global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) 
    const int t_begin = (int)((long long)tiles_total * blockIdx.y / gridDim.y);
    const int t_end = (int)((long long)tiles_total * (blockIdx.y + 1) / gridDim.y);
    const int n_iter = t_end - t_begin;
+   // Every CTA walks its candidate range from a different starting tile.  With a common order all 148 SMs ask the L2 for
+   // the same 57 KB at the same moment, and requests for one line are served one after the other: the operand loads then
+   // take about as long as the MMAs they feed and cannot hide behind two stages (ncu source view of the common-order
+   // kernel: 30 % of all stall samples are epilogue warps waiting for an accumulator, the tensor pipe is 55 % busy).
+   const int rot = n_iter > 1 ? (int)(((uint32_t)blockIdx.x * 2654435761u >> 10) % (uint32_t)n_iter) : 0;
+   auto tile_of = [&](int i) { const int t = i + rot; return t_begin + (t >= n_iter ? t - n_iter : t); };
 
    if (threadIdx.x == 0) {
       mbar_init(bar_a, 1);
       for (int s = 0; s < STAGES; s++) {
          mbar_init(bar_full + 8 * s, 1);
          mbar_init(bar_empty + 8 * s, 1);
-         mbar_init(bar_tfull + 8 * s, 1);
-         mbar_init(bar_tempty + 8 * s, EPI_WARPS);
+         for (int m = 0; m < MT; m++) {
+            mbar_init(bar_tfull + 8 * (s * MT + m), 1);
+            mbar_init(bar_tempty + 8 * (s * MT + m), 4 * CSPLIT);
+         }
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
@@ -148,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) 
          for (int i = 0; i < n_iter; i++) {
             const int s = i & 1;
             mbar_wait(bar_empty + 8 * s, ((i >> 1) & 1) ^ 1);   // slot free (passes at once the first time round)
-            const size_t off = (size_t)(t_begin + i) * TILE_BYTES;
+            const size_t off = (size_t)tile_of(i) * TILE_BYTES;
             mbar_expect_tx(bar_full + 8 * s, 2 * TILE_BYTES);
             bulk_copy(smem_u32(sB + (2 * s) * TILE_BYTES), reinterpret_cast<const unsigned char*>(a.c_hi) + off, TILE_BYTES, bar_full + 8 * s);
             bulk_copy(smem_u32(sB + (2 * s + 1) * TILE_BYTES), reinterpret_cast<const unsigned char*>(a.c_lo) + off, TILE_BYTES, bar_full + 8 * s);
@@ -161,12 +175,12 @@ __global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) 
          for (int i = 0; i < n_iter; i++) {
             const int s = i & 1;
             const uint32_t ph = (i >> 1) & 1;
-            mbar_wait(bar_tempty + 8 * s, ph ^ 1);   // accumulator drained by the epilogue
             mbar_wait(bar_full + 8 * s, ph);         // operand bytes have landed
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t bh = smem_u32(sB + (2 * s) * TILE_BYTES), bl = smem_u32(sB + (2 * s + 1) * TILE_BYTES);
 #pragma unroll
             for (int m = 0; m < MT; m++) {
+               mbar_wait(bar_tempty + 8 * (s * MT + m), ph ^ 1);   // this accumulator drained by its four epilogue warps
+               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                const uint32_t ah = smem_u32(sA + (2 * m) * TILE_BYTES), al = smem_u32(sA + (2 * m + 1) * TILE_BYTES);
                const uint32_t acc = tmem_base + (uint32_t)((s * MT + m) * BN);
 #pragma unroll
@@ -176,15 +190,20 @@ __global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) 
                   mma_bf16(acc, make_desc(ah + off), make_desc(bl + off), 1u);                 // hi * lo
                   mma_bf16(acc, make_desc(al + off), make_desc(bh + off), 1u);                 // lo * hi
                }
+               umma_commit(bar_tfull + 8 * (s * MT + m));    // this accumulator is ready for its epilogue warps
             }
             umma_commit(bar_empty + 8 * s);    // shared-memory slot can be refilled
-            umma_commit(bar_tfull + 8 * s);    // accumulator ready for the epilogue
          }
       }
    } else {
-      // ===== epilogue: warp w reads TMEM lanes 32(w%4).. of accumulator w/4; thread = one query =====
-      const int mhalf = warp >> 2;
-      const long long q = q0 + threadIdx.x;
+      // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. of accumulator (w / 4) % MT, columns [BN / CSPLIT * (w / (4 MT)) ..);
+      // thread = one query.  Measured with KB2E_TC_EXPERIMENT (timing only): without the compare-and-count the kernel takes
+      // 0.72 ms instead of 0.88 ms, with one TMEM load in four 0.75 ms -- the TMEM reads are free, the ~0.72 ms are the MMAs
+      // (both operands from shared memory: 8 KB per 128 x 128 x 16 MMA is the shared-memory bandwidth of the SM), and the
+      // compare-and-count is not fully hidden behind them; sixteen epilogue warps instead of eight changed nothing (0.883 ms).
+      const int mhalf = (warp >> 2) % MT;
+      const int chalf = warp / (4 * MT);
+      const long long q = q0 + mhalf * BM + (warp & 3) * 32 + lane;
       const float g_lo = a.thr_lo[q];   // g >  g_lo           -> candidate certainly ranks before the truth
       const float g_hi = a.thr_hi[q];   // g_hi <= g <= g_lo   -> undecided: exact fp64 recheck
       // The hot loop sees every accumulator value once, so it is kept to 3.5 independent instructions per value
@@ -200,12 +219,13 @@ __global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) 
       int less = 0;
       for (int i = 0; i < n_iter; i++) {
          const int s = i & 1;
-         mbar_wait(bar_tfull + 8 * s, (i >> 1) & 1);
+         mbar_wait(bar_tfull + 8 * (s * MT + mhalf), (i >> 1) & 1);
          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-         const long long c0 = (long long)(t_begin + i) * BN;
+         const long long c0 = (long long)tile_of(i) * BN;
 #pragma unroll 1
-         for (int cb = 0; cb < BN; cb += 32) {
+         for (int cb = chalf * (BN / CSPLIT); cb < (chalf + 1) * (BN / CSPLIT); cb += 32) {
             uint32_t v[32];
+            if (a.experiment == 2 && (cb & 96) != 0) continue;
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((s * MT + mhalf) * BN + cb);
             asm volatile(
                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -217,6 +237,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) 
                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (a.experiment == 1) { less += (int)(v[0] & 1u); continue; }
             int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
             float m0 = 3.0e38f, m1 = 3.0e38f;
 #pragma unroll
@@ -245,11 +266,10 @@ __global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) 
          // this warp has finished reading the accumulator
          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
          __syncwarp();
-         if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
+         if (lane == 0) mbar_arrive(bar_tempty + 8 * (s * MT + mhalf));
       }
       if (q < a.nq) {
-         if (gridDim.y == 1) a.q_less[q] = less;
-         else if (less) atomicAdd(a.q_less + q, less);
+         if (less) atomicAdd(a.q_less + q, less);   // (CSPLIT warps and gridDim.y CTAs share a query; q_less is zeroed by the host)
       }
    }
    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -402,6 +422,7 @@ int tc_run(kb2e_ctx* c, TcState* s, const int32_t* q_fixed, const int32_t* q_rel
    a.thr_lo = s->thr_lo; a.thr_hi = s->thr_hi;
    a.q_less = q_less; a.band = s->band; a.band_count = band_count; a.band_cap = s->band_cap;
    a.nq = nq; a.n_pad = s->n_pad;
+   { const char* e = getenv("KB2E_TC_EXPERIMENT"); a.experiment = e ? atoi(e) : 0; }
    const unsigned mtiles = (unsigned)(q_pad / (tc::MT * tc::BM));
    const int ntiles = s->n_pad / tc::BN;
    // one CTA per SM: cut the candidate range so that the work items fill whole waves (tail < 5 %)
@@ -414,7 +435,7 @@ int tc_run(kb2e_ctx* c, TcState* s, const int32_t* q_fixed, const int32_t* q_rel
    }
    splits = std::min<long long>(splits, ntiles);
    KB2E_CUDA(c, cudaFuncSetAttribute(tc::rank_l2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-   if (splits > 1) KB2E_CUDA(c, cudaMemsetAsync(q_less, 0, (size_t)nq * sizeof(int32_t), c->stream));
+   KB2E_CUDA(c, cudaMemsetAsync(q_less, 0, (size_t)nq * sizeof(int32_t), c->stream));
    KB2E_CUDA(c, cudaEventRecord(s->e0, c->stream));
    tc::rank_l2_tc_kernel<<<dim3(mtiles, (unsigned)splits), tc::THREADS, tc::SMEM_BYTES, c->stream>>>(a);
    KB2E_CUDA(c, cudaEventRecord(s->e1, c->stream));

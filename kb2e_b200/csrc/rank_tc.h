@@ -26,6 +26,7 @@ struct TcArgs {
    unsigned int band_cap;
    long long nq;
    int n_pad;
+   int experiment;   // KB2E_TC_EXPERIMENT (timing only, WRONG ranks): 1 = TMEM loads without the compare-and-count, 2 = one TMEM load in four
 };
 
 struct TcState {
