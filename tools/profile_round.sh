@@ -41,6 +41,10 @@ python tools/trace_report.py $O/${R}_trace_transr.txt 6 > $O/${R}_trace_transr_r
 rm -f $O/${R}_trace_transr.txt
 KB2E_TRANSR_STATS=1 python tools/probe.py --model transr --dim 50 --distance 0 --epochs 20 --test 10 2>&1 | grep -E "epochs|transRNorm" >> $O/${R}_trace_transr_report.txt
 KB2E_TRAIN_TRACE=$O/${R}_trace_transh.txt python tools/probe.py --model transh --shape wn18 --dim 100 --distance 0 --epochs 6 --test 10 > /dev/null 2>&1
+python tools/trace_report.py $O/${R}_trace_transh.txt 5 > $O/${R}_trace_transh_sr_report.txt 2>/dev/null
+KB2E_TRAIN_TRACE=$O/${R}_trace_transh.txt KB2E_TRAIN_TRACE_FINE=1 python tools/probe.py --model transh --shape wn18 --dim 100 --distance 0 --epochs 6 --test 10 > /dev/null 2>&1
+python tools/trace_transh_sr_fine.py $O/${R}_trace_transh.txt >> $O/${R}_trace_transh_sr_report.txt 2>/dev/null
+KB2E_TRANSH_SR=0 KB2E_TRAIN_TRACE=$O/${R}_trace_transh.txt python tools/probe.py --model transh --shape wn18 --dim 100 --distance 0 --epochs 6 --test 10 > /dev/null 2>&1
 python tools/trace_report.py $O/${R}_trace_transh.txt 5 > $O/${R}_trace_transh_report.txt 2>/dev/null
 rm -f $O/${R}_trace_transh.txt
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > $O/${R}_pytest_gpu.txt
