@@ -11,14 +11,15 @@
 // approximate score lies within a proven band around T is re-scored in exact fp64 with the
 // reference's operation order (recheck_kernel in rank.cu), so the integer ranks stay bit-exact.
 //
-// Kernel shape (one CTA = 128 queries x a range of 128-candidate tiles, 4 warps, 2 CTAs per SM):
-//   A (u_hi, u_lo) is loaded once into shared memory, K-major, no swizzle: core matrix = 8 rows x 16 B,
+// Kernel shape (one CTA per SM = 2 x 128 queries x a range of 128-candidate tiles; 8 epilogue warps + a copy producer +
+// an MMA issuer; 229 KB of shared memory, all 512 TMEM columns):
+//   A (u_hi, u_lo of both query tiles) is loaded once into shared memory, K-major, no swizzle: core matrix = 8 rows x 16 B,
 //   laid out [16-byte K chunk][row] so LBO = 2048 B (next K chunk), SBO = 128 B (next 8 rows);
-//   per candidate tile: B (c_hi, c_lo) + n_c -> shared memory; one elected thread issues
-//   21 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16) into a 128-column TMEM accumulator
-//   and commits to an mbarrier; each warp then reads its 32 TMEM lanes (= 32 queries) with
-//   tcgen05.ld 32x32b.x32 and counts / collects band candidates.  With two CTAs resident per SM one
-//   CTA's epilogue and loads overlap the other's MMAs.
+//   per candidate tile: B (c_hi, c_lo; |c|^2 rides in three bias columns) -> a 2-stage shared-memory ring by 1-D bulk copies;
+//   one elected thread issues 21 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16) per query tile into that tile's
+//   128-column TMEM accumulator (2 stages x 2 query tiles) and commits to the accumulator's own mbarrier; the four warps
+//   of a query tile then read their 32 TMEM lanes (= 32 queries) with tcgen05.ld 32x32b.x32 and count / collect band
+//   candidates while the tensor core works on the other accumulators.
 
 #include <cuda_bf16.h>
 
