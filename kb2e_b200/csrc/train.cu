@@ -27,7 +27,7 @@
 //         trip -- and publishes it unless another CTA's copy of the same row claimed it first.  No stamp scan, no
 //         dependence on where in the row space the touched rows fall, and the lists are balanced by construction
 //         (every CTA holds the same number of samples).  At FB15k shape: ~10 active samples = ~40 list entries per CTA
-//         against 48 groups, so the publish is a single pass.
+//         against 40 groups (640 threads), so the publish is a single pass.
 //
 // Work distribution: a "group" of LPS lanes owns one sample (LPS*NV float4 >= row pitch), so a
 // D=50 row uses 16 lanes and a D=100 row 16 lanes x 2 vectors or 32 x 1, whichever lets one batch
