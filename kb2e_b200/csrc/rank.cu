@@ -823,9 +823,18 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    bool f32_started = false;
    // Opt-in (KB2E_RANK_OVERLAP=1): measured on B200 at FB15k shape the filter pass beside the tensor-core kernel costs that
    // kernel more issue slots than the overlap saves (1.83 ms with, 1.43 ms without: profiles/r02_rank_probes.txt)
-   const bool overlap = passes.size() == 1 && s->n_ent != 0 && getenv("KB2E_RANK_OVERLAP") != nullptr;
+   const char* ov_env = getenv("KB2E_RANK_OVERLAP");
+   const bool overlap = passes.size() == 1 && s->n_ent != 0 && ov_env != nullptr && atoi(ov_env) != 0;
+   // KB2E_RANK_OVERLAP=2 (tensor-core path): the filter pass is enqueued AFTER the MMA kernel, on a low-priority stream and
+   // with a small footprint (two 256-thread CTAs per SM), so that it runs in the threads and registers the one-CTA-per-SM
+   // MMA kernel leaves free instead of delaying its CTAs.  Measured: whole call 1.303 ms against 1.348 ms without overlap
+   // (the MMA kernel itself stretches from 0.89 to 1.08 ms beside the filter warps) -- a 3 % gain that blurs the per-kernel
+   // accounting of the bench, so it stays opt-in too.
+   const bool overlap_late = overlap && atoi(ov_env) == 2;
    if (overlap && !s->side) {
-      KB2E_CUDA(c, cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+      int lo = 0, hi = 0;
+      KB2E_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      KB2E_CUDA(c, cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, lo));
       KB2E_CUDA(c, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
       KB2E_CUDA(c, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
    }
@@ -833,7 +842,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
    auto run_filter = [&](cudaStream_t st) -> int {
       KB2E_CUDA(c, cudaMemsetAsync(s->chunk_count, 0, sizeof(unsigned int), st));
       filter_plan_kernel<<<nblk(a.q_end - a.q_begin, 256), 256, 0, st>>>(a, s->seg_end, s->chunks, s->chunk_count, s->chunk_cap);
-      const unsigned fb = 8 * c->num_sms;   // persistent: 8 x 256 threads per SM striding over the pair list
+      const unsigned fb = (overlap_late && st != c->stream ? 2 : 8) * c->num_sms;   // persistent: 8 (2) x 256 threads per SM striding over the pair list
       if (use_trp) {
          int rc2 = trp_filter(c, &s->trp, l2, s->q_int, nq, s->q_etrue, s->chunks, s->chunk_count, s->chunk_cap, s->q_cnt, st);
          if (rc2) return rc2;
@@ -848,13 +857,20 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       return KB2E_OK;
    };
    // fork: everything enqueued on the main stream so far (E_true of the pass) happens before the filter pass starts
-   auto fork_filter = [&]() -> int {
+   auto fork_mark = [&]() -> int {
       KB2E_CUDA(c, cudaEventRecord(s->ev_fork, c->stream));
+      return KB2E_OK;
+   };
+   auto fork_launch = [&]() -> int {
       KB2E_CUDA(c, cudaStreamWaitEvent(s->side, s->ev_fork, 0));
       int rc2 = run_filter(s->side);
       if (rc2) return rc2;
       KB2E_CUDA(c, cudaEventRecord(s->ev_join, s->side));
       return KB2E_OK;
+   };
+   auto fork_filter = [&]() -> int {
+      int rc2 = fork_mark();
+      return rc2 ? rc2 : fork_launch();
    };
    // Everything below is enqueued without a host wait; the one synchronisation is at the end of the call.
    KB2E_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -894,7 +910,8 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
       } else {
          if (l2) etrue_kernel<1><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
          else etrue_kernel<0><<<nblk(pq, 128), 128, 0, c->stream>>>(a);
-         if (overlap && (rc = fork_filter())) return rc;
+         if (overlap && use_tc && overlap_late) { if ((rc = fork_mark())) return rc; }
+         else if (overlap && (rc = fork_filter())) return rc;
       }
       if (use_trp) {
          // scored above
@@ -903,6 +920,7 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
          rc = tc_run(c, &s->tc, a.q_fixed + ps.q_begin, a.q_rel + ps.q_begin, a.q_side + ps.q_begin, a.q_etrue + ps.q_begin,
                      pq, s->q_cnt + ps.q_begin);
          if (rc) return rc;
+         if (overlap && overlap_late && (rc = fork_launch())) return rc;   // behind the MMA kernel in issue order
          // band entries hold query indices relative to the pass window
          recheck_kernel<1><<<4 * c->num_sms, 128, 0, c->stream>>>(
             s->tc.band, s->tc.scalars + 1, s->tc.band_cap, c->ent64, c->rel64, a.q_fixed + ps.q_begin, a.q_truth + ps.q_begin,
