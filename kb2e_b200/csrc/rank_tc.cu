@@ -205,18 +205,17 @@ __global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) 
       const int mhalf = (warp >> 2) % MT;
       const int chalf = warp / (4 * MT);
       const long long q = q0 + mhalf * BM + (warp & 3) * 32 + lane;
-      const float g_lo = a.thr_lo[q];   // g >  g_lo           -> candidate certainly ranks before the truth
-      const float g_hi = a.thr_hi[q];   // g_hi <= g <= g_lo   -> undecided: exact fp64 recheck
-      // The hot loop sees every accumulator value once, so it is kept to 3.5 independent instructions per value
-      // (subtract, compare + predicated add, one three-input min of |.| per two values; the straightforward
-      // `less += g > g_lo; band |= g >= g_hi && !(g > g_lo)` compiled to 7 with a serial chain and made the
-      // kernel epilogue-bound: 1.22 -> 0.97 ms):  d = g - mid;  "certainly before" <=> d > T;  "a band candidate
-      // may be in this chunk" <=> min |d| <= T, with T = half the band width plus a few ulps, so that d > T implies
-      // g > g_lo exactly and g in [g_hi, g_lo] implies |d| <= T.  Values between g_lo and mid + T are merely sent
-      // to the exact recheck as well.  (Loading the whole 128-column row with two x64 TMEM loads before one wait was
-      // measured 2.3x SLOWER than four x32 load / wait / process rounds.)
-      const float mid = 0.5f * g_lo + 0.5f * g_hi;
-      const float T = fmaxf(g_lo - mid, mid - g_hi) + 1.0e-6f * fmaxf(fabsf(g_lo), fabsf(g_hi)) + 1.0e-37f;
+      const float g_lo = a.thr_lo[q];   // d >  g_lo           -> candidate certainly ranks before the truth
+      const float g_hi = a.thr_hi[q];   // g_hi <= d <= g_lo   -> undecided: exact fp64 recheck
+      // The hot loop sees every accumulator value once, so it is kept to 2.5 independent instructions per value (compare +
+      // predicated add, one three-input min of |.| per two values; the straightforward
+      // `less += d > g_lo; band |= d >= g_hi && !(d > g_lo)` compiled to 7 with a serial chain and made the kernel
+      // epilogue-bound: 1.22 -> 0.97 ms):  "certainly before" <=> d > T;  "a band candidate may be in this chunk" <=>
+      // min |d| <= T, with T = max(|g_lo|, |g_hi|), so that d > T implies d > g_lo and d in [g_hi, g_lo] implies |d| <= T.
+      // Values between g_lo and T are merely sent to the exact recheck as well.  (Loading the whole 128-column row with two
+      // x64 TMEM loads before one wait was measured 2.3x SLOWER than four x32 load / wait / process rounds.)
+      // (g_lo, g_hi) straddle zero almost symmetrically: the query's threshold is part of the accumulator (prep_queries_kernel)
+      const float T = fmaxf(fabsf(g_lo), fabsf(g_hi)) + 1.0e-37f;
       int less = 0;
       for (int i = 0; i < n_iter; i++) {
          const int s = i & 1;
@@ -243,8 +242,8 @@ __global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) 
             float m0 = 3.0e38f, m1 = 3.0e38f;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-               const float d0 = __uint_as_float(v[j]) - mid, d1 = __uint_as_float(v[j + 1]) - mid;
-               const float d2 = __uint_as_float(v[j + 2]) - mid, d3 = __uint_as_float(v[j + 3]) - mid;
+               const float d0 = __uint_as_float(v[j]), d1 = __uint_as_float(v[j + 1]);
+               const float d2 = __uint_as_float(v[j + 2]), d3 = __uint_as_float(v[j + 3]);
                asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(l0) : "f"(d0), "f"(T));
                asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(l1) : "f"(d1), "f"(T));
                asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(l2) : "f"(d2), "f"(T));
@@ -256,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_l2_tc_kernel(const TcArgs a) 
             if (fminf(m0, m1) <= T) {   // rare: collect the undecided candidates of this 32-column chunk
 #pragma unroll
                for (int j = 0; j < 32; j++) {
-                  const float d = __uint_as_float(v[j]) - mid;
+                  const float d = __uint_as_float(v[j]);
                   if (fabsf(d) <= T) {
                      unsigned int slot = atomicAdd(a.band_count, 1u);
                      if (slot < a.band_cap) a.band[slot] = make_int2((int)q, (int)(c0 + cb + j));
@@ -314,6 +313,7 @@ __global__ void prep_candidates_kernel(const double* __restrict__ c64, int n, in
    }
 #pragma unroll
    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+   __syncwarp();   // the loop's zeros in the bias columns are overwritten below by lane 0
    if (lane == 0) {
       // padding rows get a huge negative bias: they never rank before anything (finite, so 0 * bias stays 0)
       float b = row < n ? (float)(-0.5 * s) : -1.0e30f;
@@ -324,6 +324,11 @@ __global__ void prep_candidates_kernel(const double* __restrict__ c64, int n, in
       c_hi[tiled_index(row, D + 0)] = b0;
       c_hi[tiled_index(row, D + 1)] = b1;
       c_hi[tiled_index(row, D + 2)] = b2;
+      // columns D+3 .. D+5: 1.0 against the query's threshold terms (prep_queries_kernel)
+      const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
+      c_hi[tiled_index(row, D + 3)] = one;
+      c_hi[tiled_index(row, D + 4)] = one;
+      c_hi[tiled_index(row, D + 5)] = one;
       if (row < n) atomicMax(cmax_bits, __float_as_uint((float)sqrt(s) * 1.0000002f));
    }
 }
@@ -353,19 +358,35 @@ __global__ void prep_queries_kernel(const double* __restrict__ c64, const double
    }
 #pragma unroll
    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+   __syncwarp();   // the loop's zeros in the threshold columns are overwritten below by lane 0
    if (lane == 0) {
       if (!real) {
-         thr_lo[q] = __int_as_float(0x7f800000);  // +inf: padding rows never count ...
-         thr_hi[q] = __int_as_float(0x7f800000);  // ... and never recheck (g >= +inf is false for finite g)
+         thr_lo[q] = __int_as_float(0x7fc00000);  // NaN: every comparison of a padding row is false -- it never counts and
+         thr_hi[q] = __int_as_float(0x7fc00000);  // never sends a candidate to the recheck
       } else {
          const double cmax = (double)__uint_as_float(*cmax_bits);
          const double G = 0.5 * (s - q_etrue[q]);
-         // |g~ - g| <= 1.9e-5 |u||c| (three-product bf16 split) + ~2e-5 |u||c| (fp32 accumulation of 336
-         // products) + 3 bf16 terms of |c|^2/2 (<= 2^-25 |c|^2) ; the band 2^-13 |u||c|max + eps is > 2x that.
+         // The threshold itself goes INTO the GEMM: columns D+3 .. D+5 of the query carry -G as three bf16 terms (the
+         // candidates hold 1.0 there), so the accumulator is d = u.c - |c|^2/2 - G~ and the epilogue tests d against +-T
+         // with no per-value subtraction.  G~ = the exact sum of the three terms; T absorbs G - G~.
+         const float gneg = (float)(-G);
+         const __nv_bfloat16 t0 = __float2bfloat16_rn(gneg);
+         const float r1 = gneg - __bfloat162float(t0);
+         const __nv_bfloat16 t1 = __float2bfloat16_rn(r1);
+         const __nv_bfloat16 t2 = __float2bfloat16_rn(r1 - __bfloat162float(t1));
+         u_hi[tiled_index(q, D + 3)] = t0;
+         u_hi[tiled_index(q, D + 4)] = t1;
+         u_hi[tiled_index(q, D + 5)] = t2;
+         const double Gt = -((double)__bfloat162float(t0) + (double)__bfloat162float(t1) + (double)__bfloat162float(t2));
+         // |d~ - d| <= 1.9e-5 |u||c| (three-product bf16 split) + ~2e-5 (|u||c| + |G|) (fp32 accumulation of 345
+         // products) + 3 bf16 terms of |c|^2/2 (<= 2^-25 |c|^2); |G| <= (|u| + |c|max)^2 / 2.  The band
+         // 2^-13 |u||c|max + eps is > 2x that.
          const double unorm = sqrt(s);
-         const double delta = 4.0 * (1.0 / 32768.0) * unorm * cmax + 3e-6 * (1.0 + unorm * cmax + cmax * cmax);
-         thr_lo[q] = __double2float_ru(G + delta);
-         thr_hi[q] = __double2float_rd(G - delta);
+         const double delta = 4.0 * (1.0 / 32768.0) * unorm * cmax + 3e-6 * (1.0 + unorm * cmax + cmax * cmax) +
+                              2e-6 * (unorm + cmax) * (unorm + cmax);
+         // certainly before the truth: g~ > G + delta  <=>  d > (G - G~) + delta;  undecided: |d - (G - G~)| <= delta
+         thr_lo[q] = __double2float_ru((G - Gt) + delta);
+         thr_hi[q] = __double2float_rd((G - Gt) - delta);
       }
    }
 }
@@ -376,7 +397,7 @@ __global__ void prep_queries_kernel(const double* __restrict__ c64, const double
 static inline unsigned nblk2(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 bool tc_supported(const kb2e_ctx* c) {
-   return c->cfg.model == KB2E_MODEL_TRANSE && c->cfg.distance == KB2E_DISTANCE_L2 && c->D + 3 <= tc::kRowChunks * 8 &&
+   return c->cfg.model == KB2E_MODEL_TRANSE && c->cfg.distance == KB2E_DISTANCE_L2 && c->D + 6 <= tc::kRowChunks * 8 &&
           !(c->cfg.flags & KB2E_FLAG_RANK_EXACT_ONLY);
 }
 
