@@ -850,6 +850,11 @@ int rank_run(kb2e_ctx* c, int64_t first, int64_t count, int32_t* raw_rank, int32
          if (l2) filter_pairs_kernel<1, false><<<fb, 256, 0, st>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
          else filter_pairs_kernel<0, false><<<fb, 256, 0, st>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
       } else {
+         // tensor-core path, filter enqueued behind tc_run of this window: most pairs are decided from its operand tiles
+         if (use_tc && st == c->stream && !getenv("KB2E_RANK_NO_FILTER_PREFILTER")) {
+            int rc2 = tc_filter_prefilter(c, &s->tc, a.q_begin, s->chunks, s->chunk_count, s->chunk_cap, s->q_cnt + 2 * nq, st);
+            if (rc2) return rc2;
+         }
          if (l2) filter_pairs_kernel<1, true><<<fb, 256, 0, st>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
          else filter_pairs_kernel<0, true><<<fb, 256, 0, st>>>(a, c->ent64, s->chunks, s->chunk_count, s->chunk_cap);
       }

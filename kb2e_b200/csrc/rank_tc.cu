@@ -391,9 +391,67 @@ __global__ void prep_queries_kernel(const double* __restrict__ c64, const double
    }
 }
 
+// Filter pass, first cut: the (query, known-true neighbour) pairs are scored from the SAME bf16 hi / lo operand tiles and
+// against the same thresholds as the tensor-core kernel -- d = sum_k (u_hi + u_lo)_k (c_hi + c_lo)_k over all columns, the
+// bias columns included, in fp32 (8-column dots added chunk by chunk: error (8 + 14) 2^-24 of sum |terms|, well inside the
+// band the thresholds carry; the lo * lo products the MMA leaves out only bring d closer to the exact value).
+// d > T: the neighbour certainly ranks before the truth -> counted here; d < -T: certainly not; both are struck from the
+// list (candidate = -1), so that the exact fp64 filter_pairs_kernel that follows scores only the undecided few.
+// 896 bytes of operands per pair instead of 2,400, no chain of dependent fp64 additions.
+__global__ void filter_prefilter_kernel(const __nv_bfloat16* __restrict__ u_hi, const __nv_bfloat16* __restrict__ u_lo,
+                                        const __nv_bfloat16* __restrict__ c_hi, const __nv_bfloat16* __restrict__ c_lo,
+                                        const float* __restrict__ thr_lo, const float* __restrict__ thr_hi, long long q_base,
+                                        int2* pairs, const unsigned int* __restrict__ pair_count, unsigned int pair_cap,
+                                        int32_t* q_filt_less) {
+   const unsigned int n = min(*pair_count, pair_cap);
+   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+      const int2 pr = pairs[k];
+      if (pr.y < 0) continue;
+      const long long q = (long long)pr.x - q_base;
+      const float T = fmaxf(fabsf(thr_lo[q]), fabsf(thr_hi[q]));
+      float d = 0.f;
+#pragma unroll 2
+      for (int ch = 0; ch < KC; ch++) {
+         const uint4 uh = *reinterpret_cast<const uint4*>(u_hi + tiled_index(q, 8 * ch));
+         const uint4 ul = *reinterpret_cast<const uint4*>(u_lo + tiled_index(q, 8 * ch));
+         const uint4 xh = *reinterpret_cast<const uint4*>(c_hi + tiled_index(pr.y, 8 * ch));
+         const uint4 xl = *reinterpret_cast<const uint4*>(c_lo + tiled_index(pr.y, 8 * ch));
+         const uint32_t a4[4] = {uh.x, uh.y, uh.z, uh.w}, b4[4] = {ul.x, ul.y, ul.z, ul.w};
+         const uint32_t c4[4] = {xh.x, xh.y, xh.z, xh.w}, d4[4] = {xl.x, xl.y, xl.z, xl.w};
+         float part = 0.f;
+#pragma unroll
+         for (int j = 0; j < 4; j++) {
+            // a bf16 is the upper half of an fp32: element 2j in the low 16 bits, 2j + 1 in the high 16 bits
+            const float u0 = __uint_as_float(a4[j] << 16) + __uint_as_float(b4[j] << 16);
+            const float u1 = __uint_as_float(a4[j] & 0xffff0000u) + __uint_as_float(b4[j] & 0xffff0000u);
+            const float x0 = __uint_as_float(c4[j] << 16) + __uint_as_float(d4[j] << 16);
+            const float x1 = __uint_as_float(c4[j] & 0xffff0000u) + __uint_as_float(d4[j] & 0xffff0000u);
+            part = fmaf(u0, x0, part);
+            part = fmaf(u1, x1, part);
+         }
+         d += part;
+      }
+      if (d > T) {
+         atomicAdd(q_filt_less + pr.x, 1);
+         pairs[k].y = -1;
+      } else if (d < -T) {
+         pairs[k].y = -1;
+      }
+   }
+}
+
 }  // namespace tc
 
 // ---- host -------------------------------------------------------------------------------------------
+int tc_filter_prefilter(kb2e_ctx* c, TcState* s, long long q_base, int2* pairs, const unsigned int* pair_count, unsigned int pair_cap,
+                        int32_t* q_filt_less, cudaStream_t stream) {
+   tc::filter_prefilter_kernel<<<8 * c->num_sms, 256, 0, stream>>>(
+      (const __nv_bfloat16*)s->u_hi, (const __nv_bfloat16*)s->u_lo, (const __nv_bfloat16*)s->c_hi, (const __nv_bfloat16*)s->c_lo,
+      s->thr_lo, s->thr_hi, q_base, pairs, pair_count, pair_cap, q_filt_less);
+   KB2E_CUDA(c, cudaGetLastError());
+   return KB2E_OK;
+}
+
 static inline unsigned nblk2(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 bool tc_supported(const kb2e_ctx* c) {

@@ -56,6 +56,11 @@ int tc_prepare_candidates(kb2e_ctx* c, TcState* s);
 int tc_run(kb2e_ctx* c, TcState* s, const int32_t* q_fixed, const int32_t* q_rel, const int32_t* q_side, const double* q_etrue,
            long long nq, int32_t* q_less);
 int tc_collect(kb2e_ctx* c, TcState* s, bool* overflow);
+// After tc_run of the same query window: decide the filter pass's (query, neighbour) pairs from the operand tiles and
+// thresholds of that run where the band allows it (counted into q_filt_less, struck from the list); the rest stays for the
+// exact kernel.  q_base = first query of the window (pairs carry global query indices).
+int tc_filter_prefilter(kb2e_ctx* c, TcState* s, long long q_base, int2* pairs, const unsigned int* pair_count, unsigned int pair_cap,
+                        int32_t* q_filt_less, cudaStream_t stream);
 void tc_free(kb2e_ctx* c, TcState* s);
 
 }  // namespace kb2e
