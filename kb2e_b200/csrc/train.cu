@@ -1678,7 +1678,11 @@ int train_run(kb2e_ctx* c, int first_epoch, int n_epochs, const int32_t* pairs_d
    const uint64_t n_batches = (uint64_t)a.batches * (uint64_t)n_epochs;
    if (n_batches >= (1ull << 31)) return fail(c, KB2E_ERR_LIMIT, "more than 2^31 batches in one launch");
    if ((uint64_t)c->stamp_base + n_batches + 2 >= (1ull << 32)) {
+      // the stamp counter starts over: every array that holds stamps is cleared with it (a pending TransH carry mark is
+      // dropped -- its delta stays in dw and is applied the next time a sample touches the relation)
       KB2E_CUDA(c, cudaMemsetAsync(c->flag, 0, ((size_t)c->nE + c->nR) * sizeof(uint32_t), c->stream));
+      KB2E_CUDA(c, cudaMemsetAsync(c->cflag, 0, (size_t)c->nR * sizeof(uint32_t), c->stream));
+      if (c->transr_aux) KB2E_CUDA(c, cudaMemsetAsync(c->transr_aux, 0, (2 * (size_t)c->nE + (size_t)c->nR + 2) * sizeof(uint32_t), c->stream));
       c->stamp_base = 0;
    }
    a.stamp_base = c->stamp_base;
