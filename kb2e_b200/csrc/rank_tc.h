@@ -10,7 +10,7 @@ struct kb2e_ctx;
 namespace kb2e {
 
 namespace tc {
-constexpr int kRowChunks = 14;  // operand rows hold 14 x 16 B = 112 bf16: embedding sizes up to 109 + 3 bias columns
+constexpr int kRowChunks = 14;  // operand rows hold 14 x 16 B = 112 bf16: embedding sizes up to 106 + 6 bias columns (norm, threshold); larger: fp32 pre-filter
 }
 
 struct TcArgs {

@@ -127,11 +127,12 @@ def test_full_shape_properties(gpu_lib):
         assert st["queries"] == 2 * n
 
 
-@pytest.mark.parametrize("D,nE,n_test", [(100, 3000, 300), (64, 1500, 130), (109, 700, 50)])
+@pytest.mark.parametrize("D,nE,n_test", [(100, 3000, 300), (64, 1500, 130), (106, 700, 50), (109, 700, 50)])
 def test_tensor_core_prefilter_equals_exact_kernel(gpu_lib, oracle, D, nE, n_test):
     """TransE squared-L2: the tcgen05 pre-filter + exact fp64 recheck band must give the very same
     integer ranks and tie counts as the exact fp64 kernel (and as the oracle), including on clustered
-    embeddings where many candidates score within the band of the truth."""
+    embeddings where many candidates score within the band of the truth.  D = 106 is the largest size the
+    tensor-core tiles hold (106 + 3 norm + 3 threshold columns = 112); D = 109 takes the fp32 pre-filter."""
     from kb2e_b200.api import FLAG_RANK_EXACT_ONLY
     nR = 9
     rng = np.random.default_rng(D)
