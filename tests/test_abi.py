@@ -63,3 +63,35 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"(#\s*include|import|from|CDLL|dlopen)[^\n]*(oracle|_ref)|libkb2e_(ref|oracle)|/root/reference", text):
                     bad.append(os.path.join(base, f))
     assert not bad, bad
+
+
+def _sass_of(kernel_regex):
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(ROOT, "kb2e_b200", "lib", "libkb2e_b200.so")
+    names = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
+    funcs = sorted(set(re.findall(r"\.text\.(\S*%s\S*)" % kernel_regex, names)))
+    assert funcs, "no kernel matching " + kernel_regex
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", funcs[0], lib], capture_output=True, text=True).stdout
+    assert "arch = sm_100a" in out or "sm_100" in out
+    return out
+
+
+def test_tensor_core_kernels_contain_blackwell_mma_and_tma():
+    """The built library is sm_100a code that really issues tcgen05 (SASS: UTCHMMA), reads its accumulators from TMEM (LDTM)
+    and stages operands with bulk copies (UBLKCP) -- in the squared-L2 ranking kernel and in the TransR projection kernel."""
+    for kernel in ("rank_l2_tc_kernel", "project_tc_kernel"):
+        sass = _sass_of(kernel)
+        assert sass.count("UTCHMMA") >= 20, kernel
+        assert "LDTM" in sass and "UBLKCP" in sass and "SYNCS" in sass, kernel
+
+
+def test_training_kernel_uses_vector_reds_and_one_reciprocal_per_row():
+    """Phase 1 accumulates with 16-byte vector REDs; the publish normalises a row with ONE reciprocal (eight IEEE
+    divisions by the same number used to serialise into ~1 us per row): no FCHK division sequence is left in the kernel."""
+    sass = _sass_of("train_kernelILi0ELi16ELi2ELi640ELb1ELb0")
+    assert "REDG.E.ADD.F32x4" in sass
+    assert "ATOMG.E.EXCH" in sass          # publish-time row claim
+    assert sass.count("FCHK") == 0
